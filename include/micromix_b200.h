@@ -1,0 +1,112 @@
+/*
+ * micromix_b200.h -- C ABI of libmicromix_b200.so, the B200 (sm_100a) drop-in for MicroMix's hot path.
+ *
+ * Every entry point replaces one pybind op of the reference's `mixedgemm` module
+ * (/root/reference/mgemm/src/bindings.cpp:682-742) and is what a maintainer's binding would call
+ * (see INTEGRATION.md for the ctypes / pybind stub).  Plain pointers and sizes only: no torch types.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers, 16-byte aligned, contiguous row-major; the library never allocates
+ *     or frees caller-visible memory and keeps no state between calls except a cache of TMA descriptors;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what the reference
+ *     launches on: reorder.cu:455, w4a4.cu:182); calls are asynchronous and CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (mmx_last_error() gives the text; nothing throws or exits,
+ *     unlike the reference's CHECK_CUDA -> exit(), gemm_utils.h:53-61);
+ *   - K = KN + KS + KO, each a multiple of 128 (model/qLinearLayer.py:40), K <= 32767 (int16 reorder_index).
+ *     Unlike the reference (bindings.cpp:134-147: ten hard-coded K) any such K is accepted.
+ *
+ * Data formats (bit-identical to the reference):
+ *   codes   FP4 E2M1 two per byte, even channel in the low nibble  [rows, Kseg/2]      (reorder.cu:30-33)
+ *           FP6 E3M2 four codes in three bytes, little-endian bits  [rows, Kseg*3/4]    (reorder.cu:54-63)
+ *           FP8 E4M3 one per byte                                   [rows, Kseg]
+ *   scales  UE8M0, one per 32 channels, in the 512-byte "SfKMajorAtom" swizzle
+ *           offset(r,g) = (r/128)*ceil(Kseg/128)*512 + (g/4)*512 + (r%32)*16 + ((r/32)%4)*4 + g%4
+ *           (cutlass/detail/sm100_blockscaled_layout.hpp:54-55,93 via mgemm/include/reorder.cuh:120-125)
+ */
+#ifndef MICROMIX_B200_H_
+#define MICROMIX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMX_OK 0
+#define MMX_ERR_INVALID (-1)  /* bad shape / alignment / null pointer */
+#define MMX_ERR_CUDA (-2)     /* a CUDA runtime or driver call failed */
+#define MMX_ERR_ARCH (-3)     /* device is not sm_100 */
+
+/* Library version (major*100 + minor). */
+int mmx_version(void);
+
+/* Text of the last error on the calling thread ("" if none). */
+const char* mmx_last_error(void);
+
+/* Bytes of a scale-factor buffer, exactly as the reference allocates them:
+ *   activations (M/128+1)*128*Kseg/32          bindings.cpp:120-123
+ *   weights     ceil(N/128)*128*Kseg/32        bindings.cpp:170-172 (== N*Kseg/32 for N % 128 == 0) */
+int64_t mmx_sf_bytes_act(int64_t M, int64_t Kseg);
+int64_t mmx_sf_bytes_wgt(int64_t N, int64_t Kseg);
+
+/* Byte offset of the scale of (row, 32-channel group) in a segment of Kseg channels. */
+int64_t mmx_sf_offset(int64_t row, int64_t group, int64_t Kseg);
+
+/*
+ * mixedgemm.reorder_quantize_x(X, reorder_index, KN, KS, KO)            bindings.cpp:104-151
+ *   -> run_reorder_quantize_x<32,K> -> reorder_quantize_mixed_kernel      reorder.cu:434-469, 94-269
+ * Per row: gather X[r, idx[j]], per-32 absmax, E8M0 scale, convert to FP4 | FP6 | FP8, pack, store.
+ *   x   bf16 [M, K]          idx int16 [K]
+ *   xn  u8 [M, KN/2]   xs u8 [M, KS*3/4]   xo u8 [M, KO]
+ *   sfn/sfs/sfo  u8, mmx_sf_bytes_act(M, Kseg) bytes each; rows >= M of a partly filled 128-row block are
+ *   written with defined bytes (the reference leaves them uninitialised).
+ * Pointers of an empty segment (Kseg == 0) may be NULL.
+ */
+int mmx_reorder_quantize_x(const void* x, int64_t M, int K, const int16_t* idx, int KN, int KS, int KO, uint8_t* xn,
+                           uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/*
+ * mixedgemm.reorder_quantize_w(W, reorder_index, KN, KS, KO)            bindings.cpp:155-202
+ *   -> run_reorder_quantize_w<32,K>                                       reorder.cu:471-506
+ * Same as _x on weight rows (FP4 | FP6 | FP8), SF buffers of mmx_sf_bytes_wgt(N, Kseg) bytes.
+ */
+int mmx_reorder_quantize_w(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO, uint8_t* wn,
+                           uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/*
+ * mixedgemm.reorder_quantize_w4(W, reorder_index, KN, KS, KO)           bindings.cpp:206-253
+ *   -> run_reorder_quantize_w4<32,K> -> reorder_quantize_mxfp4_kernel     reorder.cu:508-543, 271-432
+ * All three segments FP4:  wn u8 [N, KN/2]   ws u8 [N, KS/2]   wo u8 [N, KO/2].
+ */
+int mmx_reorder_quantize_w4(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO, uint8_t* wn,
+                            uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/*
+ * mixedgemm.matmul(AN,BN,AS,BS,AO,BO,SFAN,SFBN,SFAS,SFBS,SFAO,SFBO)      bindings.cpp:50-102
+ *   -> matmul_w4_host (w4 != 0: W4A4 + W4A6 + W4A8)                        gemm.cu:53-78
+ *   -> matmul_host    (w4 == 0: W4A4 + W6A6 + W8A8)                        gemm.cu:26-51
+ * C[M,N] (bf16) = sum over the three K segments of (A_seg o SFA_seg)(B_seg o SFB_seg)^T.
+ * One persistent tcgen05 kernel; all segments accumulate in one fp32 TMEM accumulator and are rounded to bf16
+ * once (the reference rounds to bf16 after each of its three launches).  C needs no pre-zeroing.
+ *   bias  optional bf16 [N] (NULL = none): C = bf16(float(bf16(acc)) + bias), i.e. exactly the reference's
+ *         separate `y + self.bias` (model/qLinearLayer.py:70-71) fused into the epilogue.
+ *   N must be a multiple of 128 (the reference's SF sizing assumes it, bindings.cpp:170-172).
+ */
+int mmx_matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+               const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+               const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+               const void* bias, void* c, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
+int64_t mmx_launch_count(void);
+
+/* Debug/bring-up knobs (tests only): key in {"gemm_watchdog","gemm_tx_mode","quant_rows","gemm_ctas"}. */
+int mmx_set_option(const char* key, int64_t value);
+
+/* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n). */
+int mmx_gemm_debug_status(uint32_t* out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICROMIX_B200_H_ */

@@ -1,0 +1,60 @@
+"""ctypes loader for libmicromix_b200.so (the C ABI declared in include/micromix_b200.h).
+
+There is NO fallback: if the library is missing or cannot be loaded, importing the ops raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmicromix_b200.so")
+
+# every symbol include/micromix_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+_QUANT_ARGS = [_vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+SYMBOLS = {
+    "mmx_version": (_i32, []),
+    "mmx_last_error": (ctypes.c_char_p, []),
+    "mmx_sf_bytes_act": (_i64, [_i64, _i64]),
+    "mmx_sf_bytes_wgt": (_i64, [_i64, _i64]),
+    "mmx_sf_offset": (_i64, [_i64, _i64, _i64]),
+    "mmx_reorder_quantize_x": (_i32, _QUANT_ARGS),
+    "mmx_reorder_quantize_w": (_i32, _QUANT_ARGS),
+    "mmx_reorder_quantize_w4": (_i32, _QUANT_ARGS),
+    "mmx_matmul": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_launch_count": (_i64, []),
+    "mmx_set_option": (_i32, [ctypes.c_char_p, _i64]),
+    "mmx_gemm_debug_status": (_i32, [ctypes.POINTER(ctypes.c_uint32), _i32]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise loudly when it is absent (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  micromix_b200 has no fallback path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().mmx_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = last_error()
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,614 @@
+// gemm.cu -- three-segment mixed-MX GEMM as ONE persistent tcgen05 kernel for sm_100a.
+//
+// Replaces /root/reference/mgemm/src/gemm.cu:26-78 (matmul_host / matmul_w4_host: three CUTLASS Sm120 mma.sync
+// launches chained through a bf16 D in HBM, w4a4.cu:176 / w4a6.cu:178 / w4a8.cu:178) behind mmx_matmul.
+//
+//   C[M,N] = sum_seg (A_seg o SFA_seg) (B_seg o SFB_seg)^T ,  seg in {FP4xFP4, FP6xFP4|FP6, FP8xFP4|FP8}
+//
+// Kernel shape
+//   * persistent, one CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+//     warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+//   * CTA tile 128 x 256; one fp32 accumulator of 256 TMEM columns shared by all three K segments, so the
+//     output is rounded to bf16 exactly once and C is written exactly once (no memset, no beta=1 re-reads).
+//   * smem pipeline of 4 stages; every stage is [A 128 rows x 128 B][B 256 rows x 128 B][SFA][SFB], 128B-swizzled:
+//       FP4xFP4 segment : kind::mxf4.block_scale.block32, packed nibbles, 256 K per stage, 4 MMAs of K=64
+//       other segments  : kind::mxf8f6f4.block_scale, TMA expands FP6/FP4 to the 16-byte-aligned "unpacked"
+//                         smem form (CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B / 16U4_ALIGN16B), 128 K per stage,
+//                         4 MMAs of K=32
+//     so both kinds advance the smem descriptors by 32 bytes per MMA and use identical stage geometry.
+//   * scale factors: the gmem layout (512-byte SfKMajorAtom per 128 rows x 128 K) is already the layout
+//     tcgen05.cp.32x128b.warpx4 wants, so SF tiles go gmem -> smem with cp.async.bulk (no descriptor) and
+//     smem -> TMEM with tcgen05.cp issued by the MMA thread right before the stage's MMAs.
+//   * epilogue: tcgen05.ld 32x32b.x32 -> fp32 -> bf16 (+ optional bias, rounded like the reference's separate add)
+//     -> 64-byte-per-thread global stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.h"
+
+namespace mmx {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int kStages = 4;
+constexpr int kStageA = BM * 128;            // 16 KB
+constexpr int kStageB = BN * 128;            // 32 KB
+constexpr int kStageSFA = 2 * 512;           // up to two 128-K atoms per stage
+constexpr int kStageSFB = (BN / 128) * 2 * 512;
+constexpr int kStageBytes = kStageA + kStageB + kStageSFA + kStageSFB;  // 52224
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColSFA = 256;            // 8 columns  (2 atoms x 4)
+constexpr uint32_t kColSFB = 264;            // 16 columns (2 atoms x 2 n-blocks x 4)
+
+struct GemmSeg {
+  const uint8_t* sfa;
+  const uint8_t* sfb;
+  int ktiles;          // pipeline stages this segment contributes per output tile
+  int kind;            // 0: kind::mxf4 (256 K per stage)   1: kind::mxf8f6f4 (128 K per stage)
+  int kelems;          // K elements per stage
+  int katoms;          // Kseg / 128
+  int atoms_per_tile;  // 128-K scale atoms per stage: 2 (mxf4) or 1
+  int last_atoms;      // atoms in the last stage (1 when an mxf4 segment has Kseg % 256 == 128)
+  uint32_t idesc;      // instruction descriptor, sf ids zero
+  uint32_t tx_bytes;   // bytes the two TMA tile loads complete on the stage barrier
+};
+
+struct GemmParams {
+  GemmSeg seg[3];
+  int nseg;
+  int m_tiles, n_tiles;
+  int64_t M, N;
+  __nv_bfloat16* c;
+  const __nv_bfloat16* bias;
+  uint32_t* dbg;
+};
+
+struct alignas(64) TmapSet {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+__device__ uint32_t g_gemm_dbg[64];
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// WD = watchdog build: bounded spin, returns false on timeout so a wrong descriptor cannot hang the GPU.
+template <bool WD>
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if constexpr (WD) {
+    for (uint32_t spins = 0; spins < (1u << 24); ++spins)
+      if (mbar_test_wait(bar, parity)) return true;
+    return false;
+  } else {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    return true;
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_cp_sf(uint32_t tmem_dst, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
+}
+__device__ __forceinline__ void mma_mxf4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa,
+                                         uint32_t sfb, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+__device__ __forceinline__ void mma_mxf8f6f4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa,
+                                             uint32_t sfb, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart).
+// bits: [0,14) addr>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Scale-factor chunk: 32 rows x 16 bytes, no swizzle; 8-row core matrices 128 bytes apart (SBO), one atom along K.
+__device__ __forceinline__ uint64_t make_desc_sf(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <bool WD>
+__global__ void __launch_bounds__(kThreads, 1)
+mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barriers: full[kStages] | empty[kStages] | tmem_full | tmem_empty | tmem_ptr(u32)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
+  const uint32_t tmem_empty_bar = bar_base + 8u * (2 * kStages + 1);
+  const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      prefetch_tmap(&tmaps.a[s]);
+      prefetch_tmap(&tmaps.b[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ======================================================================== TMA producer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+        const int m_blk = tile % p.m_tiles;
+        const int n_blk = tile / p.m_tiles;
+        const int nb_valid = ((int64_t)(n_blk * 2 + 1) * 128 < p.N) ? 2 : 1;
+        for (int s = 0; s < p.nseg && ok; ++s) {
+          const GemmSeg& sg = p.seg[s];
+          for (int kt = 0; kt < sg.ktiles; ++kt) {
+            if (!mbar_wait<WD>(empty_bar(stage), phase ^ 1)) {
+              if (WD) atomicOr(&p.dbg[0], 0x1u | (uint32_t)(stage << 8) | (uint32_t)(s << 16));
+              ok = false;
+              break;
+            }
+            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : sg.atoms_per_tile;
+            const uint32_t sf_chunk = (uint32_t)natoms * 512u;
+            const uint32_t sbase = smem_base + stage * kStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), sg.tx_bytes + sf_chunk * (1 + nb_valid));
+            tma_load_2d(sbase, &tmaps.a[s], full_bar(stage), kt * sg.kelems, m_blk * BM);
+            tma_load_2d(sbase + kStageA, &tmaps.b[s], full_bar(stage), kt * sg.kelems, n_blk * BN);
+            const int64_t ka = (int64_t)kt * sg.atoms_per_tile;
+            bulk_load(sbase + kStageA + kStageB, sg.sfa + ((int64_t)m_blk * sg.katoms + ka) * 512, sf_chunk,
+                      full_bar(stage));
+            for (int nb = 0; nb < nb_valid; ++nb)
+              bulk_load(sbase + kStageA + kStageB + kStageSFA + nb * 1024,
+                        sg.sfb + ((int64_t)(n_blk * 2 + nb) * sg.katoms + ka) * 512, sf_chunk, full_bar(stage));
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================== MMA issuer (one lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tphase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+        if (!mbar_wait<WD>(tmem_empty_bar, tphase ^ 1)) {
+          if (WD) atomicOr(&p.dbg[1], 0x2u);
+          ok = false;
+          break;
+        }
+        tc_fence_after();
+        uint32_t acc = 0;
+        for (int s = 0; s < p.nseg && ok; ++s) {
+          const GemmSeg& sg = p.seg[s];
+          for (int kt = 0; kt < sg.ktiles; ++kt) {
+            if (!mbar_wait<WD>(full_bar(stage), phase)) {
+              if (WD) atomicOr(&p.dbg[1], 0x4u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (uint32_t)(kt << 20));
+              ok = false;
+              break;
+            }
+            tc_fence_after();
+            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : sg.atoms_per_tile;
+            const uint32_t sbase = smem_base + stage * kStageBytes;
+            const uint32_t sfa_s = sbase + kStageA + kStageB;
+            const uint32_t sfb_s = sfa_s + kStageSFA;
+            for (int a = 0; a < natoms; ++a) {
+              tc_cp_sf(tmem_base + kColSFA + 4 * a, make_desc_sf(sfa_s + 512 * a));
+              tc_cp_sf(tmem_base + kColSFB + 8 * a, make_desc_sf(sfb_s + 512 * a));
+              tc_cp_sf(tmem_base + kColSFB + 8 * a + 4, make_desc_sf(sfb_s + 1024 + 512 * a));
+            }
+            const uint64_t da = make_desc_sw128(sbase);
+            const uint64_t db = make_desc_sw128(sbase + kStageA);
+            if (sg.kind == 0) {
+              const int nmma = 2 * natoms;  // K=64 each; two scales per row per MMA: sf id 0 or 2
+#pragma unroll 4
+              for (int j = 0; j < nmma; ++j) {
+                const uint32_t a = (uint32_t)j >> 1, sid = ((uint32_t)j & 1u) * 2u;
+                const uint32_t idesc = sg.idesc | (sid << 29) | (sid << 4);
+                mma_mxf4(tmem_base, da + 2u * j, db + 2u * j, idesc, tmem_base + kColSFA + 4 * a,
+                         tmem_base + kColSFB + 8 * a, acc);
+                acc = 1;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // K=32 each; sf id = k-block within the 128-K atom
+                const uint32_t idesc = sg.idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4);
+                mma_mxf8f6f4(tmem_base, da + 2u * j, db + 2u * j, idesc, tmem_base + kColSFA, tmem_base + kColSFB, acc);
+                acc = 1;
+              }
+            }
+            tc_commit(empty_bar(stage));  // frees the smem slot once the MMAs (and SF copies) have read it
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        tc_commit(tmem_full_bar);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    // ======================================================================== epilogue warps 2..5
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.m_tiles;
+      const int n_blk = tile / p.m_tiles;
+      if (!mbar_wait<WD>(tmem_full_bar, tphase)) {
+        if (WD && lane == 0) atomicOr(&p.dbg[2], 0x8u | (uint32_t)(q << 8));
+        break;
+      }
+      tc_fence_after();
+      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
+      __nv_bfloat16* crow = p.c + row * p.N;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int64_t col0 = (int64_t)n_blk * BN + ch * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          uint32_t o[16];
+          if (p.bias != nullptr) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 bv = __ldg(bp + v);
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int e = v * 8 + u * 2;
+                // y = bf16(acc); y = bf16(y + bias): the reference's matmul followed by `y + self.bias`
+                const uint32_t y = pack_bf16(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+                const float y0 = __uint_as_float(y << 16) + __uint_as_float(bw[u] << 16);
+                const float y1 = __uint_as_float(y & 0xffff0000u) + __uint_as_float(bw[u] & 0xffff0000u);
+                o[v * 4 + u] = pack_bf16(y0, y1);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+          }
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar);
+      tphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int64_t rows;
+  int kseg;
+  int dtype;
+  int box_rows;
+  int box_k;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && kseg == o.kseg && dtype == o.dtype && box_rows == o.box_rows &&
+           box_k == o.box_k;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h ^= std::hash<int64_t>()(k.rows * 1000003 + k.kseg) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    h ^= std::hash<int>()(k.dtype * 31 + k.box_rows * 7 + k.box_k) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// operand tile map: 2-D tensor [rows, Kseg] of sub-byte / byte codes, K fastest, box = box_k x box_rows, swizzle 128B
+static int get_tmap(const void* ptr, int64_t rows, int kseg, int bits, bool unpack, int box_rows, CUtensorMap* out) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  CUtensorMapDataType dt;
+  int box_k;
+  if (bits == 4 && !unpack) { dt = CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN8B; box_k = 256; }
+  else if (bits == 4) { dt = CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B; box_k = 128; }
+  else if (bits == 6) { dt = CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B; box_k = 128; }
+  else { dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; box_k = 128; }
+  TmapKey key{ptr, rows, kseg, (int)dt, box_rows, box_k};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return MMX_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MMX_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)kseg, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)kseg * bits / 8};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%lld kseg=%d bits=%d unpack=%d box=%dx%d", (int)r, ptr,
+              (long long)rows, kseg, bits, (int)unpack, box_k, box_rows);
+    return MMX_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return MMX_OK;
+}
+
+static uint32_t make_idesc(int kind, int a_bits, int b_bits) {
+  auto fmt_f8f6f4 = [](int bits) -> uint32_t { return bits == 8 ? 0u : (bits == 6 ? 4u : 5u); };  // E4M3, E3M2, E2M1
+  const uint32_t afmt = kind == 0 ? 1u : fmt_f8f6f4(a_bits);  // MXF4Format::E2M1 = 1
+  const uint32_t bfmt = kind == 0 ? 1u : fmt_f8f6f4(b_bits);
+  uint32_t d = 0;
+  d |= afmt << 7;
+  d |= bfmt << 10;
+  // bits 13,14 negate = 0; bits 15,16 major = 0 (K-major)
+  d |= (uint32_t)(BN >> 3) << 17;
+  d |= 1u << 23;  // scale format UE8M0
+  d |= (uint32_t)(BM >> 4) << 24;
+  return d;
+}
+
+static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                  const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                  const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                  const void* bias, void* c, void* stream) {
+  if (M < 0 || N <= 0 || KN < 0 || KS < 0 || KO < 0 || (KN % 128) || (KS % 128) || (KO % 128) || KN + KS + KO == 0) {
+    set_error("matmul: bad shape M=%lld N=%lld (KN,KS,KO)=(%d,%d,%d)", (long long)M, (long long)N, KN, KS, KO);
+    return MMX_ERR_INVALID;
+  }
+  if (N % 128) {
+    set_error("matmul: N=%lld must be a multiple of 128", (long long)N);
+    return MMX_ERR_INVALID;
+  }
+  if (!c) {
+    set_error("matmul: null output");
+    return MMX_ERR_INVALID;
+  }
+  if (M == 0) return MMX_OK;
+  if (!device_is_sm100()) {
+    set_error("matmul: this library only runs on sm_100 (B200) devices");
+    return MMX_ERR_ARCH;
+  }
+  const uint8_t* A[3] = {an, as, ao};
+  const uint8_t* B[3] = {bn, bs, bo};
+  const uint8_t* SA[3] = {sfan, sfas, sfao};
+  const uint8_t* SB[3] = {sfbn, sfbs, sfbo};
+  const int ks[3] = {KN, KS, KO};
+  const int abits[3] = {4, 6, 8};
+  const int bbits[3] = {4, w4 ? 4 : 6, w4 ? 4 : 8};
+  TmapSet tm;
+  GemmParams p;
+  memset(&tm, 0, sizeof(tm));
+  memset(&p, 0, sizeof(p));
+  int ns = 0;
+  for (int s = 0; s < 3; ++s) {
+    if (ks[s] == 0) continue;
+    if (!A[s] || !B[s] || !SA[s] || !SB[s]) {
+      set_error("matmul: null pointer for non-empty segment %d", s);
+      return MMX_ERR_INVALID;
+    }
+    if (((uintptr_t)A[s] | (uintptr_t)B[s]) & 31 || ((uintptr_t)SA[s] | (uintptr_t)SB[s]) & 15) {
+      set_error("matmul: segment %d operands must be 32-byte aligned (scale factors 16)", s);
+      return MMX_ERR_INVALID;
+    }
+    GemmSeg& g = p.seg[ns];
+    g.kind = (s == 0) ? 0 : 1;
+    g.kelems = (s == 0) ? 256 : 128;
+    g.katoms = ks[s] / 128;
+    g.atoms_per_tile = (s == 0) ? 2 : 1;
+    g.ktiles = (ks[s] + g.kelems - 1) / g.kelems;
+    g.last_atoms = g.katoms - (g.ktiles - 1) * g.atoms_per_tile;
+    g.idesc = make_idesc(g.kind, abits[s], bbits[s]);
+    g.sfa = SA[s];
+    g.sfb = SB[s];
+    const bool unpack = g.kind == 1;
+    // bytes TMA reports per row of 128 smem bytes: packed gmem bytes (mode 0) or the smem footprint (mode 1)
+    auto row_tx = [&](int bits) -> uint32_t {
+      if (!unpack) return 128u;
+      if (options().gemm_tx_mode == 1) return 128u;
+      return (uint32_t)(128 * bits / 8);
+    };
+    g.tx_bytes = (uint32_t)BM * row_tx(abits[s]) + (uint32_t)BN * row_tx(bbits[s]);
+    int rc = get_tmap(A[s], M, ks[s], abits[s], unpack, BM, &tm.a[ns]);
+    if (rc) return rc;
+    rc = get_tmap(B[s], N, ks[s], bbits[s], unpack, BN, &tm.b[ns]);
+    if (rc) return rc;
+    ++ns;
+  }
+  p.nseg = ns;
+  p.M = M;
+  p.N = N;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (int)((N + BN - 1) / BN);
+  p.c = static_cast<__nv_bfloat16*>(c);
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  uint32_t* dbg = nullptr;
+  MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&dbg), g_gemm_dbg));
+  p.dbg = dbg;
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int64_t grid = options().gemm_ctas > 0 ? options().gemm_ctas : sm_count();
+  if (grid > tiles) grid = tiles;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_done[2] = {false, false};
+  const bool wd = options().gemm_watchdog != 0;
+  auto kern = wd ? mixed_gemm_kernel<true> : mixed_gemm_kernel<false>;
+  if (!attr_done[wd]) {
+    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_done[wd] = true;
+  }
+  if (wd) MMX_CUDA_TRY(cudaMemsetAsync(dbg, 0, 64 * sizeof(uint32_t), st));
+  kern<<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tm, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MMX_CUDA_TRY(cudaGetLastError());
+  return MMX_OK;
+}
+
+}  // namespace mmx
+
+extern "C" __attribute__((visibility("default"))) int mmx_matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                          const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                          const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
+                          int64_t N, int KN, int KS, int KO, int w4, const void* bias, void* c, void* stream) {
+  return mmx::matmul(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mmx_gemm_debug_status(uint32_t* out, int n) {
+  if (!out || n <= 0) return MMX_ERR_INVALID;
+  uint32_t tmp[64];
+  cudaError_t e = cudaMemcpyFromSymbol(tmp, mmx::g_gemm_dbg, sizeof(tmp));
+  if (e != cudaSuccess) return mmx::cuda_fail(e, "cudaMemcpyFromSymbol");
+  for (int i = 0; i < n && i < 64; ++i) out[i] = tmp[i];
+  return MMX_OK;
+}

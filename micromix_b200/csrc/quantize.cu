@@ -1,0 +1,403 @@
+// quantize.cu -- fused reorder (gather) + per-32 absmax + E8M0 scale + FP4/FP6/FP8 convert + pack, for sm_100a.
+//
+// Replaces /root/reference/mgemm/src/reorder.cu:94-269 (reorder_quantize_mixed_kernel) and :271-432
+// (reorder_quantize_mxfp4_kernel) behind mmx_reorder_quantize_{x,w,w4}; results are bit-identical
+// (codes, packing, scale bytes, scale-factor swizzle) -- see oracle/mmx_oracle.c for the restated semantics.
+//
+// Design (HBM-bound, nothing GEMM-shaped here):
+//   * Persistent CTAs.  A work item is R rows {rb*128 + l + 32*(R*h+j), j<R}: the R rows whose scale bytes share
+//     one 16-byte line of the 512-byte scale-factor atom, so scales leave the SM as 16-byte (R=4) / 8-byte (R=2)
+//     stores instead of 1-byte scatters.
+//   * The R rows are read with coalesced 32-bit loads and stored to shared memory channel-major, row-interleaved
+//     (xs[c][j]); the permuted gather x[r, idx[c]] then costs ONE 8-byte (R=4) shared load per channel for all R
+//     rows, i.e. R times fewer bank-conflicted gathers than a row-at-a-time kernel.  reorder_index is staged in
+//     shared memory once per CTA (the reference re-reads it from global memory for every row).
+//   * A thread owns 8 consecutive permuted channels (a quarter of a 32-group) of all R rows: absmax over packed
+//     bf16x2 (two rows per instruction), two warp shuffles finish the group reduction.
+//   * Scale: integer exponent arithmetic on the bf16 absmax -- byte = exp(amax) - log2floor(QMAX) + (mant > mant(QMAX)),
+//     0x7E for an all-zero group -- provably equal to the reference's ceil(log2(amax/QMAX)) for every bf16 amax
+//     (tests/test_oracle_pin.py::test_scale_rule_exhaustive).  Elements: x * 2^-e is exact in fp32, then the
+//     hardware cvt.rn.satfinite.{e2m1x2,e3m2x2,e4m3x2}.f32 (RNE, saturating == the reference's clamp + software RNE).
+//   * Packed codes are staged in shared memory per pass and leave as fully coalesced 16-byte stores.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace mmx {
+
+struct QuantParams {
+  const uint16_t* x;
+  const int16_t* idx;
+  int64_t rows;
+  int64_t num_items;
+  int K;
+  int kseg[3];      // channels per segment
+  int fmt[3];       // bits per code: 4 | 6 | 8
+  int cend[3];      // cumulative channel ends
+  int vend[3];      // cumulative packed-byte ends of the "virtual packed row" (all three segments back to back)
+  int katoms[3];    // kseg / 128
+  int64_t rowbytes[3];
+  uint8_t* q[3];
+  uint8_t* sf[3];
+};
+
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void st_stream_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+// 8 floats -> 8 E2M1 codes, element 0 in the low nibble of byte 0 (reorder.cu:30-33 PackFp4).
+__device__ __forceinline__ uint32_t cvt8_e2m1(const float (&f)[8]) {
+  uint32_t r;
+  asm("{\n"
+      ".reg .b8 b0, b1, b2, b3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b0, %2, %1;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b1, %4, %3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b2, %6, %5;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b3, %8, %7;\n"
+      "mov.b32 %0, {b0, b1, b2, b3};\n"
+      "}"
+      : "=r"(r)
+      : "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]));
+  return r;
+}
+
+// 2 floats -> two 6-bit E3M2 codes, each in the low 6 bits of a byte (a low byte, b high byte).
+__device__ __forceinline__ uint32_t cvt2_e3m2(float a, float b) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.e3m2x2.f32 %0, %2, %1;" : "=h"(h) : "f"(a), "f"(b));
+  return h;
+}
+
+__device__ __forceinline__ uint32_t cvt2_e4m3(float a, float b) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(h) : "f"(a), "f"(b));
+  return h;
+}
+
+// four 6-bit codes (c0|c1<<8 in h01, c2|c3<<8 in h23) -> 24 bits, little-endian bit-contiguous (reorder.cu:54-63)
+__device__ __forceinline__ uint32_t pack4_fp6(uint32_t h01, uint32_t h23) {
+  return (h01 & 0x3fu) | ((h01 >> 2) & 0xfc0u) | ((h23 & 0x3fu) << 12) | ((h23 & 0x3f00u) << 10);
+}
+
+__device__ __forceinline__ int voff(const QuantParams& p, int c) {
+  int v = 0;
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    int n = min(max(c, 0), p.kseg[s]);
+    v += (n * p.fmt[s]) >> 3;
+    c -= p.kseg[s];
+  }
+  return v;
+}
+
+template <int R, int T>
+__global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
+  static_assert(R == 4 || R == 2, "rows per item");
+  constexpr int HS = 4 / R;        // items per (128-row block, lane row l)
+  constexpr int RW = R / 2;        // 32-bit words per gathered channel
+  constexpr int PASS_CH = 8 * T;   // channels per pass
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int K = p.K;
+  int16_t* idx_s = reinterpret_cast<int16_t*>(smem);
+  uint8_t* xs = smem + ((K * 2 + 15) & ~15);
+  uint8_t* stage = xs + (size_t)K * R * 2;
+  uint8_t* sfs = stage + 2 * R * PASS_CH;
+  const int t = threadIdx.x;
+
+  for (int i = t; i < K / 8; i += T) reinterpret_cast<uint4*>(idx_s)[i] = reinterpret_cast<const uint4*>(p.idx)[i];
+
+  const int npass = (K + PASS_CH - 1) / PASS_CH;
+
+  for (int64_t item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    const int l = (int)(item & 31);
+    const int64_t it2 = item >> 5;
+    const int h = (int)(it2 % HS);
+    const int64_t rb = it2 / HS;
+    int64_t row[R];
+    bool valid[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      row[j] = rb * 128 + l + 32 * (R * h + j);
+      valid[j] = row[j] < p.rows;
+    }
+    if (!valid[0]) continue;  // block-uniform
+
+    // ---- load R rows, coalesced 4-byte loads, store channel-major / row-interleaved
+    {
+      const uint16_t* xr[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) xr[j] = p.x + (valid[j] ? row[j] : row[0]) * (int64_t)K;
+#pragma unroll 4
+      for (int c2 = t; c2 < K / 2; c2 += T) {
+        uint32_t w[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) w[j] = ld_stream_u32(xr[j] + 2 * c2);
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (!valid[j]) w[j] = 0u;
+        if constexpr (R == 4) {
+          uint4 o;
+          o.x = __byte_perm(w[0], w[1], 0x5410);
+          o.y = __byte_perm(w[2], w[3], 0x5410);
+          o.z = __byte_perm(w[0], w[1], 0x7632);
+          o.w = __byte_perm(w[2], w[3], 0x7632);
+          *reinterpret_cast<uint4*>(xs + (size_t)c2 * 16) = o;
+        } else {
+          uint2 o;
+          o.x = __byte_perm(w[0], w[1], 0x5410);
+          o.y = __byte_perm(w[0], w[1], 0x7632);
+          *reinterpret_cast<uint2*>(xs + (size_t)c2 * 8) = o;
+        }
+      }
+    }
+    __syncthreads();
+
+    for (int ps = 0; ps < npass; ++ps) {
+      const int C0 = ps * PASS_CH;
+      const int c0 = C0 + 8 * t;
+      const bool active = c0 < K;
+      const int cc = active ? c0 : 0;
+      const int s = (cc >= p.cend[1]) ? 2 : (cc >= p.cend[0] ? 1 : 0);
+      const int fmt = p.fmt[s];
+      uint8_t* stagebuf = stage + (ps & 1) * (R * PASS_CH);
+
+      // ---- gather 8 permuted channels x R rows
+      const uint4 iv = *reinterpret_cast<const uint4*>(idx_s + cc);
+      const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
+      uint32_t g[8][RW];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t ch = (ivw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        if constexpr (R == 4) {
+          const uint2 v = *reinterpret_cast<const uint2*>(xs + (size_t)ch * 8);
+          g[e][0] = v.x;
+          g[e][1] = v.y;
+        } else {
+          g[e][0] = *reinterpret_cast<const uint32_t*>(xs + (size_t)ch * 4);
+        }
+      }
+
+      // ---- absmax per row over the 32-group (8 local channels, then 4 lanes)
+      uint32_t am[RW];
+#pragma unroll
+      for (int k = 0; k < RW; ++k) {
+        __nv_bfloat162 m = __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[0][k]));
+#pragma unroll
+        for (int e = 1; e < 8; ++e) m = __hmax2(m, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[e][k])));
+        uint32_t u = *reinterpret_cast<uint32_t*>(&m);
+#pragma unroll
+        for (int d = 1; d <= 2; d <<= 1) {
+          uint32_t o = __shfl_xor_sync(0xffffffffu, u, d);
+          __nv_bfloat162 mm = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), *reinterpret_cast<__nv_bfloat162*>(&o));
+          u = *reinterpret_cast<uint32_t*>(&mm);
+        }
+        am[k] = u;
+      }
+
+      // ---- scale byte and multiplier per row; convert; stage
+      const int qexp = (fmt == 4) ? 2 : ((fmt == 6) ? 4 : 8);  // QMAX = (1 + thr/128) * 2^qexp : 6, 28, 448
+      const int thr = (fmt == 4) ? 64 : 96;
+      const int vrel = voff(p, cc) - voff(p, C0);
+      uint32_t sfbytes = 0;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint32_t a = (j & 1) ? (am[j >> 1] >> 16) : (am[j >> 1] & 0xffffu);
+        int byte = (int)(a >> 7) - qexp + (((int)(a & 0x7f) > thr) ? 1 : 0);
+        byte = max(byte, 0);
+        if (a == 0) byte = 126;  // all-zero group: scale 0.5 (reorder.cu:179,191,203)
+        sfbytes |= (uint32_t)(byte & 0xff) << (8 * j);
+        const float rs = __uint_as_float((uint32_t)(254 - byte) << 23);  // 2^(127-byte) = 1/scale
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t w = g[e][j >> 1];
+          f[e] = __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16)) * rs;
+        }
+        uint8_t* dst = stagebuf + j * PASS_CH + vrel;
+        if (active) {
+          if (fmt == 4) {
+            *reinterpret_cast<uint32_t*>(dst) = cvt8_e2m1(f);
+          } else if (fmt == 6) {
+            const uint32_t lo = pack4_fp6(cvt2_e3m2(f[0], f[1]), cvt2_e3m2(f[2], f[3]));
+            const uint32_t hi = pack4_fp6(cvt2_e3m2(f[4], f[5]), cvt2_e3m2(f[6], f[7]));
+            uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);
+            d16[0] = (uint16_t)lo;
+            d16[1] = (uint16_t)((lo >> 16) | (hi << 8));
+            d16[2] = (uint16_t)(hi >> 8);
+          } else {
+            uint2 o;
+            o.x = cvt2_e4m3(f[0], f[1]) | (cvt2_e4m3(f[2], f[3]) << 16);
+            o.y = cvt2_e4m3(f[4], f[5]) | (cvt2_e4m3(f[6], f[7]) << 16);
+            *reinterpret_cast<uint2*>(dst) = o;
+          }
+        }
+      }
+      if (active && (t & 3) == 0) {
+        const int G = c0 >> 5;
+        uint8_t* d = sfs + (G >> 2) * 16 + (R * h) * 4 + (G & 3);
+#pragma unroll
+        for (int j = 0; j < R; ++j) d[4 * j] = (uint8_t)(sfbytes >> (8 * j));
+      }
+      __syncthreads();
+
+      // ---- coalesced 16-byte copy-out of this pass' packed codes
+      {
+        const int C1 = min(C0 + PASS_CH, K);
+        const int vs = voff(p, C0);
+        const int n16 = (voff(p, C1) - vs) >> 4;
+        for (int i = t; i < R * n16; i += T) {
+          const int j = i / n16;
+          const int ch = i - j * n16;
+          const int64_t rj = row[0] + 32 * j;
+          if (rj >= p.rows) continue;
+          const int v = vs + 16 * ch;
+          const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
+          const int vb = (sg == 0) ? 0 : p.vend[sg - 1];
+          const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + j * PASS_CH + 16 * ch);
+          st_stream_v4(p.q[sg] + rj * p.rowbytes[sg] + (v - vb), val);
+        }
+      }
+    }
+
+    // ---- scale factors: one 16-byte (R=4) / 8-byte (R=2) store per 128 channels
+    for (int ch = t; ch < K / 128; ch += T) {
+      const int c = ch * 128;
+      const int sg = (c >= p.cend[1]) ? 2 : (c >= p.cend[0] ? 1 : 0);
+      const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
+      const int ka = (c - cb) >> 7;
+      uint8_t* dst = p.sf[sg] + (rb * p.katoms[sg] + ka) * 512 + l * 16;
+      if constexpr (R == 4) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sfs + ch * 16);
+      } else {
+        *reinterpret_cast<uint2*>(dst + 8 * h) = *reinterpret_cast<const uint2*>(sfs + ch * 16 + 8 * h);
+      }
+    }
+    // the next item's first __syncthreads (after its load phase) orders these reads before sfs/stage/xs reuse
+  }
+}
+
+template <int R, int T>
+static size_t quant_smem_bytes(int K) {
+  return ((size_t)(K * 2 + 15) & ~(size_t)15) + (size_t)K * R * 2 + (size_t)2 * R * 8 * T + (size_t)(K / 128) * 16;
+}
+
+template <int R, int T>
+static int launch_quant(const QuantParams& p, cudaStream_t stream) {
+  static int occ_cached[2] = {-1, -1};  // keyed on smem size below/above 48K is not enough; recompute per K cheaply
+  const size_t smem = quant_smem_bytes<R, T>(p.K);
+  if (smem > 227 * 1024) {
+    set_error("reorder_quantize: K=%d needs %zu bytes of shared memory", p.K, smem);
+    return MMX_ERR_INVALID;
+  }
+  auto kern = reorder_quantize_kernel<R, T>;
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  (void)occ_cached;
+  int occ = 0;
+  MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+  if (occ < 1) occ = 1;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > p.num_items) grid = p.num_items;
+  if (grid < 1) return MMX_OK;
+  kern<<<(unsigned)grid, T, smem, stream>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  MMX_CUDA_TRY(cudaGetLastError());
+  return MMX_OK;
+}
+
+static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO,
+                            const int fmt[3], uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1,
+                            uint8_t* s2, void* stream) {
+  if (rows < 0 || K <= 0 || KN < 0 || KS < 0 || KO < 0 || KN + KS + KO != K) {
+    set_error("reorder_quantize: bad shape rows=%lld K=%d (KN,KS,KO)=(%d,%d,%d)", (long long)rows, K, KN, KS, KO);
+    return MMX_ERR_INVALID;
+  }
+  if ((KN % 128) || (KS % 128) || (KO % 128)) {
+    set_error("reorder_quantize: KN, KS, KO must be multiples of 128, got (%d,%d,%d)", KN, KS, KO);
+    return MMX_ERR_INVALID;
+  }
+  if (K > 32767) {
+    set_error("reorder_quantize: K=%d exceeds the int16 reorder_index range", K);
+    return MMX_ERR_INVALID;
+  }
+  uint8_t* q[3] = {q0, q1, q2};
+  uint8_t* s[3] = {s0, s1, s2};
+  const int ks[3] = {KN, KS, KO};
+  if (!x || !idx) {
+    set_error("reorder_quantize: null input pointer");
+    return MMX_ERR_INVALID;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (ks[i] && (!q[i] || !s[i])) {
+      set_error("reorder_quantize: null output pointer for non-empty segment %d", i);
+      return MMX_ERR_INVALID;
+    }
+  if (((uintptr_t)x | (uintptr_t)idx | (uintptr_t)q0 | (uintptr_t)q1 | (uintptr_t)q2 | (uintptr_t)s0 | (uintptr_t)s1 |
+       (uintptr_t)s2) & 15) {
+    set_error("reorder_quantize: pointers must be 16-byte aligned");
+    return MMX_ERR_INVALID;
+  }
+  if (rows == 0) return MMX_OK;
+  QuantParams p;
+  p.x = static_cast<const uint16_t*>(x);
+  p.idx = idx;
+  p.rows = rows;
+  p.K = K;
+  int cacc = 0, vacc = 0;
+  for (int i = 0; i < 3; ++i) {
+    p.kseg[i] = ks[i];
+    p.fmt[i] = fmt[i];
+    cacc += ks[i];
+    vacc += ks[i] * fmt[i] / 8;
+    p.cend[i] = cacc;
+    p.vend[i] = vacc;
+    p.katoms[i] = ks[i] / 128;
+    p.rowbytes[i] = (int64_t)ks[i] * fmt[i] / 8;
+    p.q[i] = q[i];
+    p.sf[i] = s[i];
+  }
+  const int64_t rblocks = (rows + 127) / 128;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int force = (int)options().quant_rows;
+  const bool r4_fits = quant_smem_bytes<4, 256>(K) <= 110 * 1024;  // keep >= 2 CTAs per SM
+  if ((force == 4) || (force == 0 && r4_fits)) {
+    p.num_items = rblocks * 32;
+    return launch_quant<4, 256>(p, st);
+  }
+  p.num_items = rblocks * 64;
+  return launch_quant<2, 512>(p, st);
+}
+
+}  // namespace mmx
+
+extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_x(const void* x, int64_t M, int K, const int16_t* idx, int KN, int KS, int KO,
+                                      uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
+                                      void* stream) {
+  const int fmt[3] = {4, 6, 8};
+  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_w(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO,
+                                      uint8_t* wn, uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
+                                      void* stream) {
+  const int fmt[3] = {4, 6, 8};
+  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_w4(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO,
+                                       uint8_t* wn, uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
+                                       void* stream) {
+  const int fmt[3] = {4, 4, 4};
+  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream);
+}

@@ -1,0 +1,173 @@
+"""`mixedgemm` -- drop-in for the reference's pybind module (/root/reference/mgemm/src/bindings.cpp:682-742).
+
+Same op names, positional/keyword argument names, return tuples, shapes and dtypes.  PyTorch is used only to
+allocate the outputs and to find the current CUDA stream; all compute is in libmicromix_b200.so (hand-written
+sm_100a kernels) reached through the C ABI of include/micromix_b200.h.  There is no CPU or eager fallback: inputs
+that are not CUDA tensors raise, and a missing library raises at first use.
+
+    import micromix_b200.mixedgemm as mixedgemm          # instead of sys.path.append('./mgemm/build/')
+
+Differences from the reference, all deliberate:
+  * any K = KN+KS+KO with KN, KS, KO multiples of 128 and K <= 32767 (the reference: 10 hard-coded K, :134-147);
+  * inputs are validated (device, dtype, contiguity, shapes) -> ValueError/RuntimeError instead of UB;
+  * kernels run on torch's current stream (the reference: legacy default stream) and are graph-capturable;
+  * matmul: one launch, fp32 accumulation across all three segments, one bf16 rounding; C is not pre-zeroed;
+  * ops that are not on the hot path yet raise NotImplementedError (see DESIGN.md "next rows").
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+__all__ = ["matmul", "reorder_quantize_x", "reorder_quantize_w", "reorder_quantize_w4", "rmsnorm_quantize_x",
+           "activate_quantize_x", "downproj_quantize_w", "downproj_quantize_w4", "test_function", "launch_count"]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else None
+
+
+def _check_cuda(name, t, dtype, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (micromix_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must be {ndim}-D, got shape {tuple(t.shape)}")
+
+
+def _check_split(K, KN, KS, KO):
+    KN, KS, KO = int(KN), int(KS), int(KO)
+    if min(KN, KS, KO) < 0 or KN + KS + KO != K:
+        raise ValueError(f"KN+KS+KO must equal K={K}, got ({KN},{KS},{KO})")
+    if KN % 128 or KS % 128 or KO % 128:
+        raise ValueError(f"KN, KS, KO must be multiples of 128, got ({KN},{KS},{KO})")
+    if K > 32767:
+        raise ValueError(f"K={K} exceeds the int16 reorder_index range")
+    return KN, KS, KO
+
+
+def _reorder_quantize(fn_name, T, reorder_index, KN, KS, KO, widths, is_act):
+    lib = _lib.load()
+    _check_cuda("X" if is_act else "W", T, torch.bfloat16, 2)
+    _check_cuda("reorder_index", reorder_index, torch.int16, 1)
+    rows, K = T.shape
+    KN, KS, KO = _check_split(K, KN, KS, KO)
+    if reorder_index.numel() != K:
+        raise ValueError(f"reorder_index must have K={K} entries, got {reorder_index.numel()}")
+    if reorder_index.device != T.device:
+        raise ValueError("reorder_index must live on the same device as the input")
+    opts = dict(dtype=torch.uint8, device=T.device)
+    with torch.cuda.device(T.device):
+        q = [torch.empty((rows, w), **opts) for w in widths(KN, KS, KO)]
+        if is_act:  # bindings.cpp:120-123
+            sf = [torch.empty((int(lib.mmx_sf_bytes_act(rows, k)),), **opts) for k in (KN, KS, KO)]
+        else:       # bindings.cpp:170-172 (rounded up to whole 128-row blocks so N % 128 != 0 stays in bounds)
+            sf = [torch.empty((int(lib.mmx_sf_bytes_wgt(rows, k)),), **opts) for k in (KN, KS, KO)]
+        rc = getattr(lib, fn_name)(_ptr(T), rows, K, _ptr(reorder_index), KN, KS, KO, _ptr(q[0]), _ptr(q[1]),
+                                   _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
+    _lib.check(rc, fn_name)
+    return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
+
+
+def reorder_quantize_x(X, reorder_index, KN, KS, KO):
+    """Reorder and quantize activation (bindings.cpp:104-151): -> (XN, XS, XO, SFXN, SFXS, SFXO), all uint8."""
+    return _reorder_quantize("mmx_reorder_quantize_x", X, reorder_index, KN, KS, KO,
+                             lambda kn, ks, ko: (kn // 2, ks // 4 * 3, ko), True)
+
+
+def reorder_quantize_w(W, reorder_index, KN, KS, KO):
+    """Reorder and quantize weight, FP4|FP6|FP8 (bindings.cpp:155-202)."""
+    return _reorder_quantize("mmx_reorder_quantize_w", W, reorder_index, KN, KS, KO,
+                             lambda kn, ks, ko: (kn // 2, ks // 4 * 3, ko), False)
+
+
+def reorder_quantize_w4(W, reorder_index, KN, KS, KO):
+    """Reorder and quantize weight to MXFP4 in all three segments (bindings.cpp:206-253)."""
+    return _reorder_quantize("mmx_reorder_quantize_w4", W, reorder_index, KN, KS, KO,
+                             lambda kn, ks, ko: (kn // 2, ks // 2, ko // 2), False)
+
+
+def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None, out=None):
+    """output = A @ B^T over the three mixed-MX segments (bindings.cpp:50-102) -> bf16 [M, N].
+
+    `bias` (bf16 [N]) and `out` are extensions: bias is added in the epilogue with the rounding of the reference's
+    separate `y + self.bias` (model/qLinearLayer.py:70-71).
+    """
+    lib = _lib.load()
+    names = ("AN", "BN", "AS", "BS", "AO", "BO", "SFAN", "SFBN", "SFAS", "SFBS", "SFAO", "SFBO")
+    tensors = (AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO)
+    for n, t in zip(names[:6], tensors[:6]):
+        _check_cuda(n, t, torch.uint8, 2)
+    for n, t in zip(names[6:], tensors[6:]):
+        _check_cuda(n, t, torch.uint8)
+    M, N = AN.size(0), BN.size(0)
+    KN, KS, KO = AN.size(1) * 2, AS.size(1) * 4 // 3, AO.size(1)  # bindings.cpp:68-70
+    sym = AS.size(1) == BS.size(1) and AO.size(1) == BO.size(1)    # bindings.cpp:74
+    w4 = 0 if sym else 1
+    if KS == 0 and KO == 0:
+        w4 = 1  # both branches coincide when only the FP4 segment exists
+    exp_b = (KN // 2, KS // 2 if w4 else KS // 4 * 3, KO // 2 if w4 else KO)
+    for n, t, w in zip(("BN", "BS", "BO"), (BN, BS, BO), exp_b):
+        if t.size(0) != N or t.size(1) != w:
+            raise ValueError(f"{n} must be [{N}, {w}], got {tuple(t.shape)}")
+    for n, t in zip(("AS", "AO"), (AS, AO)):
+        if t.size(0) != M:
+            raise ValueError(f"{n} must have M={M} rows, got {tuple(t.shape)}")
+    for n, t, k in zip(("SFAN", "SFAS", "SFAO"), (SFAN, SFAS, SFAO), (KN, KS, KO)):
+        if t.numel() < -(-M // 128) * 128 * k // 32:
+            raise ValueError(f"{n} has {t.numel()} bytes, too small for M={M}, K={k}")
+    for n, t, k in zip(("SFBN", "SFBS", "SFBO"), (SFBN, SFBS, SFBO), (KN, KS, KO)):
+        if t.numel() < N * k // 32:
+            raise ValueError(f"{n} has {t.numel()} bytes, too small for N={N}, K={k}")
+    if bias is not None:
+        _check_cuda("bias", bias, torch.bfloat16, 1)
+        if bias.numel() != N:
+            raise ValueError(f"bias must have N={N} entries")
+    with torch.cuda.device(AN.device):
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=AN.device)
+        else:
+            _check_cuda("out", out, torch.bfloat16, 2)
+            if tuple(out.shape) != (M, N):
+                raise ValueError(f"out must be [{M}, {N}]")
+        rc = 0
+        if M > 0:
+            rc = lib.mmx_matmul(_ptr(AN), _ptr(BN), _ptr(AS), _ptr(BS), _ptr(AO), _ptr(BO), _ptr(SFAN), _ptr(SFBN),
+                                _ptr(SFAS), _ptr(SFBS), _ptr(SFAO), _ptr(SFBO), M, N, KN, KS, KO, w4, _ptr(bias),
+                                _ptr(out), _stream())
+    _lib.check(rc, "mmx_matmul")
+    return out
+
+
+def _not_yet(name, where):
+    def f(*args, **kwargs):
+        raise NotImplementedError(
+            f"mixedgemm.{name} ({where}) is not called by any Python code of the reference and is a 'next' row of "
+            "the hot-path scope (SURVEY.md section 8f); it is not implemented yet.")
+    f.__name__ = name
+    return f
+
+
+rmsnorm_quantize_x = _not_yet("rmsnorm_quantize_x", "bindings.cpp:257-303")
+activate_quantize_x = _not_yet("activate_quantize_x", "bindings.cpp:307-334")
+downproj_quantize_w = _not_yet("downproj_quantize_w", "bindings.cpp:336-360")
+downproj_quantize_w4 = _not_yet("downproj_quantize_w4", "bindings.cpp:362-387")
+
+
+def test_function():
+    return "Hello from test_function!"
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far (bench.py's gpu_launches)."""
+    return int(_lib.load().mmx_launch_count())
