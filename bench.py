@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of MicroMix on B200: reorder+quantize -> three-segment mixed-MX GEMM.
+
+Workload (BASELINE.json configs[1]): the four linears of one Llama-3-8B decoder layer
+(qkv 6144x4096, o 4096x4096, gate_up 28672x4096, down 4096x14336) over M tokens, 5-bit average split
+(p4,p6,p8) = K*(5/8, 2/8, 1/8), synthetic activations / random-init weights / synthetic reorder_index.
+A "step" = one pass of the hot path over that batch: for each linear, mmx_reorder_quantize_x then mmx_matmul
+(8 kernel launches), weights pre-quantized to MXFP4 offline exactly as QLinearLayer.__init__ does.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--tokens M] [--impl ours|reference]
+
+N > 1 (launched by torchrun, one rank per GPU over NCCL): tensor parallel as in BASELINE north_star --
+qkv/gate_up column-parallel (no collective), o/down row-parallel with an all-reduce of the bf16 [M,4096] partials.
+Total work is fixed as N grows ("scaling": "strong"); value = whole-job TFLOP/s = 2*M*sum(N*K) / max-over-ranks time.
+
+`--impl reference` times the reference's algorithm on the host cores (the CPU oracle port: the reference has no CPU
+implementation of its own and its GEMM cannot run on sm_100) on a bounded token sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mixed-MX GEMM TFLOPS & prefill tokens/s, Llama-3-8B linears, 1/2/4/8 B200"
+# (name, N, K, parallel mode)
+LINEARS = [("qkv", 6144, 4096, "col"), ("o", 4096, 4096, "row"), ("gate_up", 28672, 4096, "col"),
+           ("down", 4096, 14336, "row")]
+
+
+def split_for(K):
+    """5.0 average bits: p4 = 5/8 K, p6 = 2/8 K, p8 = 1/8 K, multiples of 128."""
+    p8 = (K // 8) // 128 * 128
+    p6 = (K // 4) // 128 * 128
+    return K - p6 - p8, p6, p8
+
+
+def flops_per_token():
+    return sum(2 * n * k for _, n, k, _ in LINEARS)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.active = threading.Event()
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.004)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's algorithm on the host cores (oracle port; `kind`: "port").  Rank 0 only."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as H
+    O = H.O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ms = args.cpu_tokens
+    prep = []
+    for name, N, K, _ in LINEARS:
+        sp = split_for(K)
+        idx = H.make_index(K, seed=0)
+        x = H.make_activations(Ms, K, idx)
+        w = H.make_weights(N, K)
+        b = O.reorder_quantize(H.bits(w), idx.numpy(), *sp, "w4")  # offline, like QLinearLayer.__init__
+        wd = [torch.from_numpy(O.dequant(b[i], b[3 + i], N, sp[i], 4)) for i in range(3)]
+        prep.append((H.bits(x), idx.numpy(), sp, wd, N))
+
+    def step():
+        for xb, idx, sp, wd, N in prep:
+            a = O.reorder_quantize(xb, idx, *sp, "x")
+            acc = None
+            for i, f in enumerate((4, 6, 8)):
+                if sp[i] == 0:
+                    continue
+                ad = torch.from_numpy(O.dequant(a[i], a[3 + i], Ms, sp[i], f))
+                part = ad @ wd[i].T
+                acc = part if acc is None else acc + part
+            acc.to(torch.bfloat16)
+
+    for _ in range(args.warmup_ref):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps_ref):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps_ref
+    tflops = Ms * flops_per_token() / dt / 1e12
+    sample = f"{Ms} of {args.tokens} tokens per step through all four linears, weights pre-dequantised"
+    line = {"impl": "reference", "metric": METRIC, "value": tflops, "unit": "TFLOP/s", "n_gpus": args.gpus,
+            "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/6/8 (fake-quant in fp32)", "data": "synthetic",
+            "tokens_per_s": Ms / dt,
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"Llama-3-8B decoder-layer linears qkv(6144x4096) o(4096x4096) gate_up(28672x4096) "
+                        f"down(4096x14336), M={args.tokens} tokens, split p4:p6:p8 = 5:2:1 (5.0 avg bits), "
+                        f"quantize + mixed GEMM per linear",
+            "tokens": args.tokens, "split_4096": list(split_for(4096)), "split_14336": list(split_for(14336)),
+            "parallelism": f"tp{world}" if world > 1 else "single",
+            "l2": "inputs+weights+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+class HotLinear:
+    """One (possibly TP-sharded) linear with every buffer preallocated; calls the C ABI directly."""
+
+    def __init__(self, name, N, K, mode, M, rank, world, dev, lib, seed):
+        import torch
+        from micromix_b200 import mixedgemm
+        from micromix_b200.parallel_utils import column_shard_range, row_shard_plan
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        self.name, self.mode, self.lib, self.M, self.world = name, mode, lib, M, world
+        idx = H.make_index(K, seed=seed)
+        g = torch.Generator(device=dev).manual_seed(1234 + seed)
+        w = (torch.randn(N, K, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+        p4, p6, p8 = split_for(K)
+        if world > 1 and mode == "col":
+            n0, n1 = column_shard_range(N, world, rank)
+            w = w[n0:n1].contiguous()
+        elif world > 1 and mode == "row":
+            k0, k1, idx, p4, p6, p8 = row_shard_plan(idx, p6, p8, world, rank)
+            w = w[:, k0:k1].contiguous()
+        self.N, self.K = w.shape
+        self.split = (p4, p6, p8)
+        self.idx = idx.to(dev)
+        self.W = mixedgemm.reorder_quantize_w4(w, self.idx, p4, p6, p8)
+        del w
+        gx = torch.Generator(device=dev).manual_seed(721 + seed + 97 * rank * (mode == "row"))
+        gain = 1.0 + 31.0 * (torch.arange(self.K, device=dev, dtype=torch.float32) / self.K) ** 8
+        x = torch.randn(M, self.K, generator=gx, device=dev, dtype=torch.float32)
+        xg = torch.empty_like(x)
+        xg[:, self.idx.long()] = x * gain
+        self.x = xg.to(torch.bfloat16)
+        del x, xg
+        u8 = dict(dtype=torch.uint8, device=dev)
+        self.A = [torch.empty((M, w_), **u8) for w_ in (p4 // 2, p6 // 4 * 3, p8)]
+        self.SFA = [torch.empty((int(lib.mmx_sf_bytes_act(M, k)),), **u8) for k in (p4, p6, p8)]
+        self.out = torch.empty((M, self.N), dtype=torch.bfloat16, device=dev)
+        self.flops = 2.0 * M * self.N * self.K
+        self.qbytes = 2.0 * M * self.K + M * (p4 / 2 + p6 * 3 / 4 + p8) + M * self.K / 32
+        p = lambda t: t.data_ptr() if t.numel() else None
+        self._qargs = (p(self.x), M, self.K, p(self.idx), p4, p6, p8, p(self.A[0]), p(self.A[1]), p(self.A[2]),
+                       p(self.SFA[0]), p(self.SFA[1]), p(self.SFA[2]))
+        W = self.W
+        self._margs = (p(self.A[0]), p(W[0]), p(self.A[1]), p(W[1]), p(self.A[2]), p(W[2]), p(self.SFA[0]), p(W[3]),
+                       p(self.SFA[1]), p(W[4]), p(self.SFA[2]), p(W[5]), M, self.N, p4, p6, p8, 1, None, p(self.out))
+
+    def run(self, stream, events=None):
+        import torch
+        import torch.distributed as dist
+        if events is not None:
+            events[0].record()
+        rc = self.lib.mmx_reorder_quantize_x(*self._qargs, stream)
+        if events is not None:
+            events[1].record()
+        rc |= self.lib.mmx_matmul(*self._margs, stream)
+        if events is not None:
+            events[2].record()
+        if rc:
+            raise RuntimeError(self.lib.mmx_last_error().decode())
+        if self.world > 1 and self.mode == "row":
+            dist.all_reduce(self.out)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from micromix_b200 import _lib, mixedgemm
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: micromix_b200 has no CPU path (use --impl reference for "
+                           "the host-core baseline)")
+    lib = _lib.load()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    M = args.tokens
+    peaks = load_peaks()
+    lins = [HotLinear(n, N, K, mode, M, rank, world, dev, lib, seed=i) for i, (n, N, K, mode) in enumerate(LINEARS)]
+    stream = torch.cuda.current_stream().cuda_stream
+    total_flops = M * flops_per_token()  # whole job, all ranks together
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        for l in lins:
+            l.run(stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in lins] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = mixedgemm.launch_count()
+    barrier()
+    sampler.active.set()
+    t_start.record()
+    for s in range(args.steps):
+        for li, l in enumerate(lins):
+            l.run(stream, ev[s][li])
+    t_end.record()
+    barrier()
+    sampler.active.clear()
+    launches = mixedgemm.launch_count() - launches0
+    ms_total = t_start.elapsed_time(t_end)
+    ms_step = ms_total / args.steps
+    if world > 1:
+        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    # per-kernel device time from the events inside the timed region
+    q_ms = sum(ev[s][li][0].elapsed_time(ev[s][li][1]) for s in range(args.steps) for li in range(len(lins)))
+    g_ms = sum(ev[s][li][1].elapsed_time(ev[s][li][2]) for s in range(args.steps) for li in range(len(lins)))
+    per_lin = {}
+    for li, l in enumerate(lins):
+        gq = sum(ev[s][li][0].elapsed_time(ev[s][li][1]) for s in range(args.steps)) / args.steps
+        gg = sum(ev[s][li][1].elapsed_time(ev[s][li][2]) for s in range(args.steps)) / args.steps
+        per_lin[l.name] = {"N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
+                           "quant_gbs": l.qbytes / gq / 1e6, "gemm_tflops": l.flops / gg / 1e9}
+    rank_flops = sum(l.flops for l in lins)
+    gemm_tflops = rank_flops * args.steps / g_ms / 1e9
+    # split-weighted tensor peak: FP4xFP4 at 4x, the FP6/FP8 segments at 2x the MEASURED dense bf16 rate
+    p_bf16 = peaks["bf16_tflops"]
+    tmin = sum(2.0 * M * l.N * (l.split[0] / (4 * p_bf16) + (l.split[1] + l.split[2]) / (2 * p_bf16)) for l in lins)
+    peak_eff = rank_flops / tmin  # TFLOP/s
+    quant_gbs = sum(l.qbytes for l in lins) * args.steps / q_ms / 1e6
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- e2e: the plugin call a user makes (QLinearLayer.forward) with HOST buffers, copies inside the timed region
+    e2e = measure_e2e(args, rank, world, dev, lins, total_flops)
+
+    clocks = sampler.summary()
+    sampler.stop_flag.set()
+    line = {"metric": METRIC, "value": total_flops / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/mxfp6/mxfp8 x mxfp4 -> fp32 acc -> bf16",
+            "data": "synthetic", "tokens_per_s": M / ms_step * 1e3, "config": workload_config(args, world),
+            "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks,
+            "roofline": {"kernel": "mixed_gemm_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_eff,
+                         "unit": "TFLOP/s", "frac": gemm_tflops / peak_eff, "traffic": traffic,
+                         "peak_note": f"split-weighted: 4x (kind::mxf4) and 2x (kind::mxf8f6f4) the {peaks['source']} "
+                                      f"dense bf16 burst peak {p_bf16} TFLOP/s"},
+            "roofline_quantize": {"kernel": "reorder_quantize_kernel", "bound": "hbm", "achieved": quant_gbs,
+                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": quant_gbs / peaks["hbm_gbs"],
+                                  "traffic": None, "peak_note": f"{peaks['source']} copy bandwidth"},
+            "share": {"gemm": g_ms / ms_total if world == 1 else None, "quantize": q_ms / ms_total if world == 1 else None},
+            "per_linear": per_lin}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def measure_e2e(args, rank, world, dev, lins, total_flops):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    from micromix_b200.qLinearLayer import QLinearLayer
+    M = args.tokens
+    layers, xin, yout = [], [], []
+    for l in lins:
+        q = QLinearLayer.__new__(QLinearLayer)  # reuse the already-quantized shard instead of re-quantizing
+        nn.Module.__init__(q)
+        q.in_features, q.out_features, q.bias = l.K, l.N, None
+        q.p4_num, q.p6_num, q.p8_num = l.split
+        q.register_buffer("reorder_index", l.idx, persistent=False)
+        q.BN, q.BS, q.BO, q.SFBN, q.SFBS, q.SFBO = l.W
+        layers.append(q)
+        xin.append(l.x.cpu().pin_memory())
+        yout.append(torch.empty((M, l.N), dtype=torch.bfloat16).pin_memory())
+    h2d = sum(x.numel() * 2 for x in xin)
+    d2h = sum(y.numel() * 2 for y in yout)
+
+    def step():
+        for q, x, y, l in zip(layers, xin, yout, lins):
+            xd = x.to(dev, non_blocking=True)
+            yd = q(xd.view(1, M, -1))
+            if world > 1 and l.mode == "row":
+                dist.all_reduce(yd)
+            y.copy_(yd.view(M, -1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    n = max(3, min(args.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {"value": total_flops / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "tokens_per_s": M / dt,
+            "api": "QLinearLayer.forward on pinned host tensors (H2D copy, quantize, GEMM, D2H copy per linear)"}
+
+
+def cpu_baseline(args):
+    import io
+    import contextlib
+    a = argparse.Namespace(**vars(args))
+    a.steps_ref, a.warmup_ref = 2, 1
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run_reference(a, 0, 1)
+    return json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--tokens", type=int, default=8192)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-tokens", type=int, default=2048, help="token sample for the host-core baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.steps_ref = max(1, min(args.steps, 3))
+    args.warmup_ref = max(1, min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and args.impl == "ours":
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        from micromix_b200.parallel_utils import init_tensor_parallel
+        init_tensor_parallel("nccl")
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

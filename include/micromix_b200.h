@@ -100,7 +100,8 @@ int mmx_matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const ui
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
 int64_t mmx_launch_count(void);
 
-/* Debug/bring-up knobs (tests only): key in {"gemm_watchdog","gemm_tx_mode","quant_rows","gemm_ctas"}. */
+/* Debug/bring-up knobs (tests only): key in {"gemm_watchdog","gemm_tx_mode","quant_rows",
+ * "gemm_ctas","gemm_cta_group"}. */
 int mmx_set_option(const char* key, int64_t value);
 
 /* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n). */

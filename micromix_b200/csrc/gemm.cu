@@ -31,46 +31,60 @@
 
 namespace mmx {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
-constexpr int kStages = 4;
-constexpr int kStageA = BM * 128;            // 16 KB
-constexpr int kStageB = BN * 128;            // 32 KB
-constexpr int kStageSFA = 2 * 512;           // up to two 128-K atoms per stage
-constexpr int kStageSFB = (BN / 128) * 2 * 512;
-constexpr int kStageBytes = kStageA + kStageB + kStageSFA + kStageSFB;  // 52224
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// Tile geometry.  CG = CTAs cooperating on one MMA (tcgen05 cta_group): 1 -> 128x256 tile per CTA,
+// 2 -> 256x256 tile per CTA pair (each CTA holds its own 128 A rows and HALF of the B rows, so L2->SM operand
+// traffic per flop drops by a third; the kernel is bound by that traffic, see DESIGN.md / profiles/).
+constexpr int BM = 128;   // A rows per CTA
+constexpr int BN = 256;   // N per tile
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColSFA = 256;            // 8 columns  (2 atoms x 4)
-constexpr uint32_t kColSFB = 264;            // 16 columns (2 atoms x 2 n-blocks x 4)
+constexpr uint32_t kColSF = 256;   // scale factors: one 24-column slot per smem stage (SFA 8 = 2 atoms x 4, SFB 16)
+constexpr uint32_t kSFSlot = 24;   // per-stage slots, so a stage's tcgen05.cp never overwrites scales that MMAs
+                                   // still in flight are reading (a single slot costs a ~300-cycle bubble per stage)
+constexpr int kEpiStage = 4096;    // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled, source of the TMA store
+
+template <int CG>
+struct Geo {
+  static constexpr int kStages = (CG == 1) ? 4 : 5;
+  static constexpr int kBRows = BN / CG;          // B rows this CTA stages
+  static constexpr int kStageA = BM * 128;        // 16 KB
+  static constexpr int kStageB = kBRows * 128;    // 32 | 16 KB
+  static constexpr int kStageSFA = 2 * 512;       // [atom][512]
+  static constexpr int kStageSFB = 2 * 2 * 512;   // [n-block][atom][512], all 256 N columns in every CTA
+  static constexpr int kStageBytes = kStageA + kStageB + kStageSFA + kStageSFB;
+  static constexpr int kEpiOff = kStages * kStageBytes;        // 4 x kEpiStage, 1024-aligned
+  static constexpr int kBarOff = kEpiOff + 4 * kEpiStage;
+  static constexpr int kSmemBytes = kBarOff + 1024 /*align slack*/ + 256 /*barriers*/;
+};
 
 struct GemmSeg {
-  const uint8_t* sfa;
-  const uint8_t* sfb;
   int ktiles;          // pipeline stages this segment contributes per output tile
   int kind;            // 0: kind::mxf4 (256 K per stage)   1: kind::mxf8f6f4 (128 K per stage)
   int kelems;          // K elements per stage
-  int katoms;          // Kseg / 128
   int atoms_per_tile;  // 128-K scale atoms per stage: 2 (mxf4) or 1
   int last_atoms;      // atoms in the last stage (1 when an mxf4 segment has Kseg % 256 == 128)
   uint32_t idesc;      // instruction descriptor, sf ids zero
-  uint32_t tx_bytes;   // bytes the two TMA tile loads complete on the stage barrier
+  uint32_t tx_a;       // bytes one CTA's A tile load completes on the stage barrier
+  uint32_t tx_b;       // ... B tile load (per CTA)
 };
 
 struct GemmParams {
   GemmSeg seg[3];
   int nseg;
-  int m_tiles, n_tiles;
+  int m_tiles, n_tiles;  // in units of (CG*128) x 256
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
   uint32_t* dbg;
+  uint32_t flags;  // watchdog build only: 1 = skip SF copies, 2 = skip MMAs, 4 = skip C stores, 8 = one SF copy set per tile
 };
 
 struct alignas(64) TmapSet {
   CUtensorMap a[3];
   CUtensorMap b[3];
+  CUtensorMap sfa[3];  // 3-D [row-block][k-atom][128 x u32] views of the 512-byte scale atoms
+  CUtensorMap sfb[3];
+  CUtensorMap c;       // bf16 [M, N], box 64 x 32, 128B swizzle: epilogue TMA stores
 };
 
 __device__ uint32_t g_gemm_dbg[64];
@@ -86,6 +100,19 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n.reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(bar), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -123,16 +150,64 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+// true in exactly one lane of the (converged) warp; ptxas knows an elect.sync region is single-lane, so the
+// uniform-register operands of tcgen05 / TMA instructions inside it need no per-lane "waterfall" loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
+      "{\n.reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(pred));
+  return pred != 0;
 }
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
+__device__ __forceinline__ long long clk() {
+  long long c;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+  return c;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// TMA tile loads.  CG == 2: the .cta_group::2 form lets the transaction bytes land on the LEADER CTA's barrier
+// (`bar` is then a shared::cluster address produced by mapa).
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -141,34 +216,76 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+// MMA-completion arrive; CG == 2 multicasts the arrive to the barrier at the same offset in both CTAs of the pair
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tc_cp_sf(uint32_t tmem_dst, uint64_t desc) {
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
+  else
+    asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void mma_mxf4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa,
                                          uint32_t sfb, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void mma_mxf8f6f4(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa,
                                              uint32_t sfb, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
-      "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}" ::"r"(d),
+        "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+  }
 }
 
 // K-major, 128B-swizzled operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart).
@@ -200,13 +317,56 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 32 fp32 accumulator columns of one row -> bf16 (+bias) -> four 16-byte chunks of the warp's swizzled staging tile.
+// Row r of the tile is 128 bytes; chunk c lives at ((c ^ (r & 7)) << 4), the 128B-swizzle pattern of the C tensor map.
+__device__ __forceinline__ void stage_chunk(const uint32_t (&r)[32], uint32_t srow, int lane, int half,
+                                            const __nv_bfloat16* bias) {
+  uint32_t o[16];
+  if (bias != nullptr) {
+    const uint4* bp = reinterpret_cast<const uint4*>(bias);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint4 bv = __ldg(bp + v);
+      const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = v * 8 + u * 2;
+        // y = bf16(acc); y = bf16(y + bias): the reference's matmul followed by `y + self.bias`
+        const uint32_t y = pack_bf16(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+        const float y0 = __uint_as_float(y << 16) + __uint_as_float(bw[u] << 16);
+        const float y1 = __uint_as_float(y & 0xffff0000u) + __uint_as_float(bw[u] & 0xffff0000u);
+        o[v * 4 + u] = pack_bf16(y0, y1);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const uint32_t chunk = (uint32_t)(half * 4 + v) ^ (uint32_t)(lane & 7);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (chunk << 4)), "r"(o[4 * v]), "r"(o[4 * v + 1]),
+                 "r"(o[4 * v + 2]), "r"(o[4 * v + 3])
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
-template <bool WD>
+template <int CG, bool WD>
 __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p) {
+  using G = Geo<CG>;
+  constexpr int kStages = G::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = smem_base + G::kBarOff;
   // barriers: full[kStages] | empty[kStages] | tmem_full | tmem_empty | tmem_ptr(u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -216,60 +376,69 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int group = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int ngroups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);   // the leader's producer arrives once (with the expected bytes of the whole pair)
+      mbar_init(empty_bar(s), 1);  // one (multicast) tcgen05.commit
     }
     mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 128);
+    mbar_init(tmem_empty_bar, 4 * CG);  // one elected lane per epilogue warp, both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  if (warp == 1) tmem_alloc<CG>(tmem_ptr_smem, kTmemCols);
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
       prefetch_tmap(&tmaps.a[s]);
       prefetch_tmap(&tmaps.b[s]);
+      prefetch_tmap(&tmaps.sfa[s]);
+      prefetch_tmap(&tmaps.sfb[s]);
     }
+    prefetch_tmap(&tmaps.c);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
 
   if (warp == 0) {
-    // ======================================================================== TMA producer (one lane)
-    if (lane == 0) {
+    // ======================================================================== TMA producer (one lane per CTA)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+      long long t_wait = 0, t_begin = WD ? clk() : 0;
+      for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
         const int m_blk = tile % p.m_tiles;
         const int n_blk = tile / p.m_tiles;
-        const int nb_valid = ((int64_t)(n_blk * 2 + 1) * 128 < p.N) ? 2 : 1;
+        const int a_row = (m_blk * CG + (int)rank) * BM;          // this CTA's A rows
+        const int b_row = n_blk * BN + (int)rank * G::kBRows;      // this CTA's share of the B rows
         for (int s = 0; s < p.nseg && ok; ++s) {
           const GemmSeg& sg = p.seg[s];
+          const uint32_t sf_bytes = (uint32_t)sg.atoms_per_tile * 512u * 3u;  // SFA + two SFB row blocks
           for (int kt = 0; kt < sg.ktiles; ++kt) {
+            const long long tw0 = WD ? clk() : 0;
             if (!mbar_wait<WD>(empty_bar(stage), phase ^ 1)) {
-              if (WD) atomicOr(&p.dbg[0], 0x1u | (uint32_t)(stage << 8) | (uint32_t)(s << 16));
+              if (WD) atomicOr(&p.dbg[0], 0x1u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (rank << 24));
               ok = false;
               break;
             }
-            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : sg.atoms_per_tile;
-            const uint32_t sf_chunk = (uint32_t)natoms * 512u;
-            const uint32_t sbase = smem_base + stage * kStageBytes;
-            mbar_arrive_expect_tx(full_bar(stage), sg.tx_bytes + sf_chunk * (1 + nb_valid));
-            tma_load_2d(sbase, &tmaps.a[s], full_bar(stage), kt * sg.kelems, m_blk * BM);
-            tma_load_2d(sbase + kStageA, &tmaps.b[s], full_bar(stage), kt * sg.kelems, n_blk * BN);
-            const int64_t ka = (int64_t)kt * sg.atoms_per_tile;
-            bulk_load(sbase + kStageA + kStageB, sg.sfa + ((int64_t)m_blk * sg.katoms + ka) * 512, sf_chunk,
-                      full_bar(stage));
-            for (int nb = 0; nb < nb_valid; ++nb)
-              bulk_load(sbase + kStageA + kStageB + kStageSFA + nb * 1024,
-                        sg.sfb + ((int64_t)(n_blk * 2 + nb) * sg.katoms + ka) * 512, sf_chunk, full_bar(stage));
+            if (WD) t_wait += clk() - tw0;
+            const uint32_t sbase = smem_base + stage * G::kStageBytes;
+            uint32_t bar = full_bar(stage);
+            if (rank == 0) mbar_arrive_expect_tx(bar, (sg.tx_a + sg.tx_b + sf_bytes) * CG);
+            if constexpr (CG == 2) bar = mapa_rank(bar, 0);  // every byte of the pair is counted on the leader
+            tma_load_2d<CG>(sbase, &tmaps.a[s], bar, kt * sg.kelems, a_row);
+            tma_load_2d<CG>(sbase + G::kStageA, &tmaps.b[s], bar, kt * sg.kelems, b_row);
+            const int ka = kt * sg.atoms_per_tile;
+            tma_load_3d<CG>(sbase + G::kStageA + G::kStageB, &tmaps.sfa[s], bar, 0, ka, m_blk * CG + (int)rank);
+            tma_load_3d<CG>(sbase + G::kStageA + G::kStageB + G::kStageSFA, &tmaps.sfb[s], bar, 0, ka, n_blk * 2);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -277,130 +446,164 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           }
         }
       }
+      if (WD && blockIdx.x == 0) {
+        p.dbg[16] = (uint32_t)((clk() - t_begin) >> 4);  // producer: total cycles / 16
+        p.dbg[17] = (uint32_t)(t_wait >> 4);             // producer: cycles waiting for a free slot / 16
+      }
     }
   } else if (warp == 1) {
-    // ======================================================================== MMA issuer (one lane)
-    if (lane == 0) {
+    // ======================================================================== MMA issuer (leader CTA)
+    // The whole warp walks the loop (converged control flow, warp-uniform operands); one elected lane issues.
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tphase = 0;
       bool ok = true;
-      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+      long long t_full = 0, t_tmem = 0, t_begin = WD ? clk() : 0;
+      uint32_t n_stage = 0;
+      for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
+        const long long tt0 = WD ? clk() : 0;
         if (!mbar_wait<WD>(tmem_empty_bar, tphase ^ 1)) {
-          if (WD) atomicOr(&p.dbg[1], 0x2u);
+          if (WD && lane == 0) atomicOr(&p.dbg[1], 0x2u);
           ok = false;
           break;
         }
+        if (WD) t_tmem += clk() - tt0;
         tc_fence_after();
         uint32_t acc = 0;
         for (int s = 0; s < p.nseg && ok; ++s) {
           const GemmSeg& sg = p.seg[s];
+          const int apt = sg.atoms_per_tile;
           for (int kt = 0; kt < sg.ktiles; ++kt) {
+            const long long tf0 = WD ? clk() : 0;
             if (!mbar_wait<WD>(full_bar(stage), phase)) {
-              if (WD) atomicOr(&p.dbg[1], 0x4u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (uint32_t)(kt << 20));
+              if (WD && lane == 0)
+                atomicOr(&p.dbg[1], 0x4u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (uint32_t)(kt << 20));
               ok = false;
               break;
             }
+            if (WD) {
+              t_full += clk() - tf0;
+              ++n_stage;
+            }
             tc_fence_after();
-            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : sg.atoms_per_tile;
-            const uint32_t sbase = smem_base + stage * kStageBytes;
-            const uint32_t sfa_s = sbase + kStageA + kStageB;
-            const uint32_t sfb_s = sfa_s + kStageSFA;
-            for (int a = 0; a < natoms; ++a) {
-              tc_cp_sf(tmem_base + kColSFA + 4 * a, make_desc_sf(sfa_s + 512 * a));
-              tc_cp_sf(tmem_base + kColSFB + 8 * a, make_desc_sf(sfb_s + 512 * a));
-              tc_cp_sf(tmem_base + kColSFB + 8 * a + 4, make_desc_sf(sfb_s + 1024 + 512 * a));
-            }
-            const uint64_t da = make_desc_sw128(sbase);
-            const uint64_t db = make_desc_sw128(sbase + kStageA);
-            if (sg.kind == 0) {
-              const int nmma = 2 * natoms;  // K=64 each; two scales per row per MMA: sf id 0 or 2
+            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : apt;
+            const uint32_t sbase = smem_base + stage * G::kStageBytes;
+            const uint32_t sfa_s = sbase + G::kStageA + G::kStageB;
+            const uint32_t sfb_s = sfa_s + G::kStageSFA;
+            const uint32_t t_sfa = tmem_base + kColSF + kSFSlot * (uint32_t)stage;  // this stage's scale slot
+            const uint32_t t_sfb = t_sfa + 8;
+            const bool do_cp = !WD || !((p.flags & 1u) || ((p.flags & 8u) && (kt > 0)));
+            const bool do_mma = !WD || !(p.flags & 2u);
+            if (elect_one()) {
+              for (int a = 0; a < (do_cp ? natoms : 0); ++a) {
+                tc_cp_sf<CG>(t_sfa + 4 * a, make_desc_sf(sfa_s + 512 * a));
+                tc_cp_sf<CG>(t_sfb + 8 * a, make_desc_sf(sfb_s + 512 * a));              // n-block 0
+                tc_cp_sf<CG>(t_sfb + 8 * a + 4, make_desc_sf(sfb_s + 512 * (apt + a)));  // n-block 1
+              }
+              const uint64_t da = make_desc_sw128(sbase);
+              const uint64_t db = make_desc_sw128(sbase + G::kStageA);
+              if (!do_mma) {
+              } else if (sg.kind == 0) {
+                const int nmma = 2 * natoms;  // K=64 each; two scales per row per MMA: sf id 0 or 2
 #pragma unroll 4
-              for (int j = 0; j < nmma; ++j) {
-                const uint32_t a = (uint32_t)j >> 1, sid = ((uint32_t)j & 1u) * 2u;
-                const uint32_t idesc = sg.idesc | (sid << 29) | (sid << 4);
-                mma_mxf4(tmem_base, da + 2u * j, db + 2u * j, idesc, tmem_base + kColSFA + 4 * a,
-                         tmem_base + kColSFB + 8 * a, acc);
-                acc = 1;
-              }
-            } else {
+                for (int j = 0; j < nmma; ++j) {
+                  const uint32_t a = (uint32_t)j >> 1, sid = ((uint32_t)j & 1u) * 2u;
+                  const uint32_t idesc = sg.idesc | (sid << 29) | (sid << 4);
+                  mma_mxf4<CG>(tmem_base, da + 2u * j, db + 2u * j, idesc, t_sfa + 4 * a, t_sfb + 8 * a, acc);
+                  acc = 1;
+                }
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {  // K=32 each; sf id = k-block within the 128-K atom
-                const uint32_t idesc = sg.idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4);
-                mma_mxf8f6f4(tmem_base, da + 2u * j, db + 2u * j, idesc, tmem_base + kColSFA, tmem_base + kColSFB, acc);
-                acc = 1;
+                for (int j = 0; j < 4; ++j) {  // K=32 each; sf id = k-block within the 128-K atom
+                  const uint32_t idesc = sg.idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4);
+                  mma_mxf8f6f4<CG>(tmem_base, da + 2u * j, db + 2u * j, idesc, t_sfa, t_sfb, acc);
+                  acc = 1;
+                }
               }
+              tc_commit<CG>(empty_bar(stage));  // frees the smem slot (both CTAs) once MMAs and SF copies have read it
             }
-            tc_commit(empty_bar(stage));  // frees the smem slot once the MMAs (and SF copies) have read it
+            __syncwarp();
+            acc = 1;
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
             }
           }
         }
-        tc_commit(tmem_full_bar);
+        if (elect_one()) tc_commit<CG>(tmem_full_bar);
+        __syncwarp();
         tphase ^= 1;
+      }
+      if (WD && blockIdx.x == 0 && lane == 0) {
+        p.dbg[18] = (uint32_t)((clk() - t_begin) >> 4);  // MMA warp: total cycles / 16
+        p.dbg[19] = (uint32_t)(t_full >> 4);             // ... waiting for TMA data / 16
+        p.dbg[20] = (uint32_t)(t_tmem >> 4);             // ... waiting for the epilogue to drain TMEM / 16
+        p.dbg[21] = n_stage;
       }
     }
   } else {
-    // ======================================================================== epilogue warps 2..5
+    // ======================================================================== epilogue warps 2..5 (every CTA)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long t_ewait = 0, t_ework = 0;
+    uint32_t n_tiles_done = 0;
+    for (int tile = group; tile < num_tiles; tile += ngroups) {
       const int m_blk = tile % p.m_tiles;
       const int n_blk = tile / p.m_tiles;
+      const long long te0 = WD ? clk() : 0;
       if (!mbar_wait<WD>(tmem_full_bar, tphase)) {
-        if (WD && lane == 0) atomicOr(&p.dbg[2], 0x8u | (uint32_t)(q << 8));
+        if (WD && lane == 0) atomicOr(&p.dbg[2], 0x8u | (uint32_t)(q << 8) | (rank << 24));
         break;
       }
+      const long long te1 = WD ? clk() : 0;
       tc_fence_after();
-      const int64_t row = (int64_t)m_blk * BM + q * 32 + lane;
-      __nv_bfloat16* crow = p.c + row * p.N;
+      const int row0 = (m_blk * CG + (int)rank) * BM + q * 32;  // first C row of this warp's 32-row band
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
+      const uint32_t srow = sbuf + (uint32_t)lane * 128u;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int64_t col0 = (int64_t)n_blk * BN + ch * 32;
+      for (int ch = 0; ch < BN / 64; ++ch) {
+        const int col0 = n_blk * BN + ch * 64;
         if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tbase + (uint32_t)(ch * 64), r0);
+        tmem_ld32(tbase + (uint32_t)(ch * 64 + 32), r1);
         tmem_ld_wait();
-        if (row < p.M) {
-          uint32_t o[16];
-          if (p.bias != nullptr) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const uint4 bv = __ldg(bp + v);
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int e = v * 8 + u * 2;
-                // y = bf16(acc); y = bf16(y + bias): the reference's matmul followed by `y + self.bias`
-                const uint32_t y = pack_bf16(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-                const float y0 = __uint_as_float(y << 16) + __uint_as_float(bw[u] << 16);
-                const float y1 = __uint_as_float(y & 0xffff0000u) + __uint_as_float(bw[u] & 0xffff0000u);
-                o[v * 4 + u] = pack_bf16(y0, y1);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-          }
-          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-        }
+        // the previous TMA store must have finished READING the staging tile before it is overwritten
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        stage_chunk(r0, srow, lane, 0, p.bias ? p.bias + col0 : nullptr);
+        stage_chunk(r1, srow, lane, 1, p.bias ? p.bias + col0 + 32 : nullptr);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
+        __syncwarp();
+        if (lane == 0 && row0 < p.M && !(WD && (p.flags & 4u))) tma_store_2d(&tmaps.c, sbuf, col0, row0);  // clips at M, N
       }
       tc_fence_before();
-      mbar_arrive(tmem_empty_bar);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+      }
       tphase ^= 1;
+      if (WD) {
+        t_ewait += te1 - te0;
+        t_ework += clk() - te1;
+        ++n_tiles_done;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores done before smem goes away
+    if (WD && blockIdx.x == 0 && warp == 2 && lane == 0) {
+      p.dbg[22] = (uint32_t)(t_ewait >> 4);  // epilogue warp: cycles waiting for an accumulator / 16
+      p.dbg[23] = (uint32_t)(t_ework >> 4);  // ... draining TMEM and storing C / 16
+      p.dbg[24] = n_tiles_done;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 
@@ -486,7 +689,49 @@ static int get_tmap(const void* ptr, int64_t rows, int kseg, int bits, bool unpa
   return MMX_OK;
 }
 
-static uint32_t make_idesc(int kind, int a_bits, int b_bits) {
+// scale-factor map: the 512-byte atoms of one SF buffer viewed as u32[rblocks][katoms][128]; box = nrb x atoms x 128
+static int get_sf_tmap(const void* ptr, int64_t rblocks, int katoms, int box_atoms, int box_rblocks, CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MMX_ERR_CUDA;
+  }
+  const cuuint64_t gdim[3] = {128, (cuuint64_t)katoms, (cuuint64_t)rblocks};
+  const cuuint64_t gstride[2] = {512, (cuuint64_t)512 * katoms};
+  const cuuint32_t box[3] = {128, (cuuint32_t)box_atoms, (cuuint32_t)box_rblocks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (scale factors) failed (%d) ptr=%p rblocks=%lld katoms=%d", (int)r, ptr,
+              (long long)rblocks, katoms);
+    return MMX_ERR_CUDA;
+  }
+  return MMX_OK;
+}
+
+// output map: bf16 C[M, N] row-major, box = 64 columns x 32 rows, 128B swizzle (matches stage_chunk's layout)
+static int get_c_tmap(void* ptr, int64_t M, int64_t N, CUtensorMap* out) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return MMX_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)N * 2};
+  const cuuint32_t box[2] = {64, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (C) failed (%d) ptr=%p M=%lld N=%lld", (int)r, ptr, (long long)M, (long long)N);
+    return MMX_ERR_CUDA;
+  }
+  return MMX_OK;
+}
+
+static uint32_t make_idesc(int kind, int a_bits, int b_bits, int mma_m) {
   auto fmt_f8f6f4 = [](int bits) -> uint32_t { return bits == 8 ? 0u : (bits == 6 ? 4u : 5u); };  // E4M3, E3M2, E2M1
   const uint32_t afmt = kind == 0 ? 1u : fmt_f8f6f4(a_bits);  // MXF4Format::E2M1 = 1
   const uint32_t bfmt = kind == 0 ? 1u : fmt_f8f6f4(b_bits);
@@ -496,8 +741,42 @@ static uint32_t make_idesc(int kind, int a_bits, int b_bits) {
   // bits 13,14 negate = 0; bits 15,16 major = 0 (K-major)
   d |= (uint32_t)(BN >> 3) << 17;
   d |= 1u << 23;  // scale format UE8M0
-  d |= (uint32_t)(BM >> 4) << 24;
+  d |= (uint32_t)(mma_m >> 4) << 24;
   return d;
+}
+
+template <int CG>
+static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
+  using G = Geo<CG>;
+  p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
+  p.n_tiles = (int)((p.N + BN - 1) / BN);
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / CG : sm_count() / CG;
+  if (groups < 1) groups = 1;
+  if (groups > tiles) groups = tiles;
+  const bool wd = options().gemm_watchdog != 0;
+  auto kern = wd ? mixed_gemm_kernel<CG, true> : mixed_gemm_kernel<CG, false>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[wd]) {
+    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    attr_done[wd] = true;
+  }
+  if (wd) MMX_CUDA_TRY(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(uint32_t), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = G::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MMX_OK;
 }
 
 static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
@@ -512,8 +791,8 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
     set_error("matmul: N=%lld must be a multiple of 128", (long long)N);
     return MMX_ERR_INVALID;
   }
-  if (!c) {
-    set_error("matmul: null output");
+  if (!c || ((uintptr_t)c & 15)) {
+    set_error("matmul: output must be a non-null 16-byte aligned pointer");
     return MMX_ERR_INVALID;
   }
   if (M == 0) return MMX_OK;
@@ -521,6 +800,7 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
     set_error("matmul: this library only runs on sm_100 (B200) devices");
     return MMX_ERR_ARCH;
   }
+  const int cg = (M > 128 && options().gemm_cta_group != 1) ? 2 : 1;  // CTA pairs unless one 128-row tile covers M
   const uint8_t* A[3] = {an, as, ao};
   const uint8_t* B[3] = {bn, bs, bo};
   const uint8_t* SA[3] = {sfan, sfas, sfao};
@@ -546,13 +826,11 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
     GemmSeg& g = p.seg[ns];
     g.kind = (s == 0) ? 0 : 1;
     g.kelems = (s == 0) ? 256 : 128;
-    g.katoms = ks[s] / 128;
+    const int katoms = ks[s] / 128;
     g.atoms_per_tile = (s == 0) ? 2 : 1;
     g.ktiles = (ks[s] + g.kelems - 1) / g.kelems;
-    g.last_atoms = g.katoms - (g.ktiles - 1) * g.atoms_per_tile;
-    g.idesc = make_idesc(g.kind, abits[s], bbits[s]);
-    g.sfa = SA[s];
-    g.sfb = SB[s];
+    g.last_atoms = katoms - (g.ktiles - 1) * g.atoms_per_tile;
+    g.idesc = make_idesc(g.kind, abits[s], bbits[s], BM * cg);
     const bool unpack = g.kind == 1;
     // bytes TMA reports per row of 128 smem bytes: packed gmem bytes (mode 0) or the smem footprint (mode 1)
     auto row_tx = [&](int bits) -> uint32_t {
@@ -560,39 +838,31 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
       if (options().gemm_tx_mode == 1) return 128u;
       return (uint32_t)(128 * bits / 8);
     };
-    g.tx_bytes = (uint32_t)BM * row_tx(abits[s]) + (uint32_t)BN * row_tx(bbits[s]);
+    const int b_rows = BN / cg;
+    g.tx_a = (uint32_t)BM * row_tx(abits[s]);
+    g.tx_b = (uint32_t)b_rows * row_tx(bbits[s]);
     int rc = get_tmap(A[s], M, ks[s], abits[s], unpack, BM, &tm.a[ns]);
     if (rc) return rc;
-    rc = get_tmap(B[s], N, ks[s], bbits[s], unpack, BN, &tm.b[ns]);
+    rc = get_tmap(B[s], N, ks[s], bbits[s], unpack, b_rows, &tm.b[ns]);
+    if (rc) return rc;
+    rc = get_sf_tmap(SA[s], (M + 127) / 128, katoms, g.atoms_per_tile, 1, &tm.sfa[ns]);
+    if (rc) return rc;
+    rc = get_sf_tmap(SB[s], (N + 127) / 128, katoms, g.atoms_per_tile, 2, &tm.sfb[ns]);
     if (rc) return rc;
     ++ns;
   }
+  if (int rc = get_c_tmap(c, M, N, &tm.c)) return rc;
   p.nseg = ns;
   p.M = M;
   p.N = N;
-  p.m_tiles = (int)((M + BM - 1) / BM);
-  p.n_tiles = (int)((N + BN - 1) / BN);
   p.c = static_cast<__nv_bfloat16*>(c);
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   uint32_t* dbg = nullptr;
   MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&dbg), g_gemm_dbg));
   p.dbg = dbg;
-  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-  int64_t grid = options().gemm_ctas > 0 ? options().gemm_ctas : sm_count();
-  if (grid > tiles) grid = tiles;
+  p.flags = (uint32_t)options().gemm_debug_flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_done[2] = {false, false};
-  const bool wd = options().gemm_watchdog != 0;
-  auto kern = wd ? mixed_gemm_kernel<true> : mixed_gemm_kernel<false>;
-  if (!attr_done[wd]) {
-    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done[wd] = true;
-  }
-  if (wd) MMX_CUDA_TRY(cudaMemsetAsync(dbg, 0, 64 * sizeof(uint32_t), st));
-  kern<<<(unsigned)grid, kThreads, kSmemBytes, st>>>(tm, p);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  MMX_CUDA_TRY(cudaGetLastError());
-  return MMX_OK;
+  return cg == 2 ? launch_gemm<2>(tm, p, st) : launch_gemm<1>(tm, p, st);
 }
 
 }  // namespace mmx

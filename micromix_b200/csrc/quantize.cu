@@ -98,11 +98,59 @@ __device__ __forceinline__ int voff(const QuantParams& p, int c) {
   return v;
 }
 
-template <int R, int T>
-__global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
+// One pass-step of a thread: 8 permuted channels x R rows -> packed codes in the staging buffer.
+//   g[e][k]   : gathered data, channel e, row pair k (rows 2k | 2k+1 in the low | high half), bf16 bits
+//   mult[k]   : bf16x2 multiplier 2^(127-byte) per row -> x * mult is exact (power of two), so HMUL2.BF16 is bit-safe
+template <int FMT, int R>
+__device__ __forceinline__ void convert_and_stage(const uint32_t (&g)[8][R / 2], const uint32_t (&mult)[R / 2],
+                                                  uint8_t* dst, int row_stride) {
+#pragma unroll
+  for (int k = 0; k < R / 2; ++k) {
+    uint32_t h[8];
+    const __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&mult[k]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&g[e][k]), m2);
+      h[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(half ? (h[e] & 0xffff0000u) : (h[e] << 16));
+      uint8_t* d = dst + (2 * k + half) * row_stride;
+      if constexpr (FMT == 4) {
+        *reinterpret_cast<uint32_t*>(d) = cvt8_e2m1(f);
+      } else if constexpr (FMT == 6) {
+        const uint32_t lo = pack4_fp6(cvt2_e3m2(f[0], f[1]), cvt2_e3m2(f[2], f[3]));
+        const uint32_t hi = pack4_fp6(cvt2_e3m2(f[4], f[5]), cvt2_e3m2(f[6], f[7]));
+        uint16_t* d16 = reinterpret_cast<uint16_t*>(d);
+        d16[0] = (uint16_t)lo;
+        d16[1] = (uint16_t)((lo >> 16) | (hi << 8));
+        d16[2] = (uint16_t)(hi >> 8);
+      } else {
+        uint2 o;
+        o.x = cvt2_e4m3(f[0], f[1]) | (cvt2_e4m3(f[2], f[3]) << 16);
+        o.y = cvt2_e4m3(f[4], f[5]) | (cvt2_e4m3(f[6], f[7]) << 16);
+        *reinterpret_cast<uint2*>(d) = o;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint2 ld_stream_u64(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// R rows per item, T threads, NLD = register-prefetch depth (each thread holds NLD x R 8-byte loads of the NEXT item
+// while it computes the current one; needs NLD * T * 4 >= K).
+template <int R, int T, int NLD, int MINB>
+__global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
   constexpr int HS = 4 / R;        // items per (128-row block, lane row l)
-  constexpr int RW = R / 2;        // 32-bit words per gathered channel
+  constexpr int RW = R / 2;        // 32-bit words per gathered channel (two rows per word)
   constexpr int PASS_CH = 8 * T;   // channels per pass
   extern __shared__ __align__(16) uint8_t smem[];
   const int K = p.K;
@@ -111,54 +159,89 @@ __global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_consta
   uint8_t* stage = xs + (size_t)K * R * 2;
   uint8_t* sfs = stage + 2 * R * PASS_CH;
   const int t = threadIdx.x;
+  const int K4 = K >> 2;
 
   for (int i = t; i < K / 8; i += T) reinterpret_cast<uint4*>(idx_s)[i] = reinterpret_cast<const uint4*>(p.idx)[i];
 
   const int npass = (K + PASS_CH - 1) / PASS_CH;
+  uint2 pre[NLD][R];  // prefetched rows of the next item
 
-  for (int64_t item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-    const int l = (int)(item & 31);
+  auto item_rows = [&](int64_t item, int& l, int& h, int64_t& rb) -> int64_t {
+    l = (int)(item & 31);
     const int64_t it2 = item >> 5;
-    const int h = (int)(it2 % HS);
-    const int64_t rb = it2 / HS;
-    int64_t row[R];
-    bool valid[R];
+    h = (int)(it2 % HS);
+    rb = it2 / HS;
+    return rb * 128 + l + 32 * (R * h);  // first row; the others follow at +32 each
+  };
+  auto prefetch = [&](int64_t item) {
+    int l, h;
+    int64_t rb;
+    const int64_t row0 = item_rows(item, l, h, rb);
+    const uint16_t* base[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-      row[j] = rb * 128 + l + 32 * (R * h + j);
-      valid[j] = row[j] < p.rows;
+      const int64_t rj = row0 + 32 * j;
+      base[j] = p.x + (rj < p.rows ? rj : 0) * (int64_t)K + 4 * t;  // invalid rows re-read row 0, zeroed at the store
     }
-    if (!valid[0]) continue;  // block-uniform
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      if (i * T + t < K4) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) pre[i][j] = ld_stream_u64(base[j] + (size_t)i * T * 4);
+      }
+    }
+  };
 
-    // ---- load R rows, coalesced 4-byte loads, store channel-major / row-interleaved
+  int64_t item = blockIdx.x;
+  if (item < p.num_items) prefetch(item);
+
+  for (; item < p.num_items; item += gridDim.x) {
+    int l, h;
+    int64_t rb;
+    const int64_t row0 = item_rows(item, l, h, rb);
+    if (row0 >= p.rows) break;  // block-uniform; items are ordered by row, nothing valid follows for this CTA stride
+
+    // ---- prefetched registers -> shared memory, channel-major / row-interleaved
     {
-      const uint16_t* xr[R];
+      const bool full = row0 + 32 * (R - 1) < p.rows;
 #pragma unroll
-      for (int j = 0; j < R; ++j) xr[j] = p.x + (valid[j] ? row[j] : row[0]) * (int64_t)K;
-#pragma unroll 4
-      for (int c2 = t; c2 < K / 2; c2 += T) {
-        uint32_t w[R];
+      for (int i = 0; i < NLD; ++i) {
+        const int c4 = i * T + t;
+        if (c4 < K4) {
+          uint2 w[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) w[j] = ld_stream_u32(xr[j] + 2 * c2);
+          for (int j = 0; j < R; ++j) w[j] = pre[i][j];
+          if (!full) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if (!valid[j]) w[j] = 0u;
-        if constexpr (R == 4) {
-          uint4 o;
-          o.x = __byte_perm(w[0], w[1], 0x5410);
-          o.y = __byte_perm(w[2], w[3], 0x5410);
-          o.z = __byte_perm(w[0], w[1], 0x7632);
-          o.w = __byte_perm(w[2], w[3], 0x7632);
-          *reinterpret_cast<uint4*>(xs + (size_t)c2 * 16) = o;
-        } else {
-          uint2 o;
-          o.x = __byte_perm(w[0], w[1], 0x5410);
-          o.y = __byte_perm(w[0], w[1], 0x7632);
-          *reinterpret_cast<uint2*>(xs + (size_t)c2 * 8) = o;
+            for (int j = 1; j < R; ++j)
+              if (row0 + 32 * j >= p.rows) w[j] = make_uint2(0u, 0u);
+          }
+          if constexpr (R == 4) {
+            uint4 o0, o1;
+            o0.x = __byte_perm(w[0].x, w[1].x, 0x5410);
+            o0.y = __byte_perm(w[2].x, w[3].x, 0x5410);
+            o0.z = __byte_perm(w[0].x, w[1].x, 0x7632);
+            o0.w = __byte_perm(w[2].x, w[3].x, 0x7632);
+            o1.x = __byte_perm(w[0].y, w[1].y, 0x5410);
+            o1.y = __byte_perm(w[2].y, w[3].y, 0x5410);
+            o1.z = __byte_perm(w[0].y, w[1].y, 0x7632);
+            o1.w = __byte_perm(w[2].y, w[3].y, 0x7632);
+            uint4* d = reinterpret_cast<uint4*>(xs + (size_t)c4 * 32);
+            d[0] = o0;
+            d[1] = o1;
+          } else {
+            uint4 o;
+            o.x = __byte_perm(w[0].x, w[1].x, 0x5410);
+            o.y = __byte_perm(w[0].x, w[1].x, 0x7632);
+            o.z = __byte_perm(w[0].y, w[1].y, 0x5410);
+            o.w = __byte_perm(w[0].y, w[1].y, 0x7632);
+            *reinterpret_cast<uint4*>(xs + (size_t)c4 * 16) = o;
+          }
         }
       }
     }
     __syncthreads();
+    if (item + gridDim.x < p.num_items) prefetch(item + gridDim.x);  // in flight during the compute below
 
     for (int ps = 0; ps < npass; ++ps) {
       const int C0 = ps * PASS_CH;
@@ -168,6 +251,10 @@ __global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_consta
       const int s = (cc >= p.cend[1]) ? 2 : (cc >= p.cend[0] ? 1 : 0);
       const int fmt = p.fmt[s];
       uint8_t* stagebuf = stage + (ps & 1) * (R * PASS_CH);
+      // packed-byte offset of channel c inside the virtual packed row
+      const int s0 = (C0 >= p.cend[1]) ? 2 : (C0 >= p.cend[0] ? 1 : 0);
+      const int vs = (s0 ? p.vend[s0 - 1] : 0) + (((C0 - (s0 ? p.cend[s0 - 1] : 0)) * p.fmt[s0]) >> 3);
+      const int vrel = (s ? p.vend[s - 1] : 0) + (((cc - (s ? p.cend[s - 1] : 0)) * fmt) >> 3) - vs;
 
       // ---- gather 8 permuted channels x R rows
       const uint4 iv = *reinterpret_cast<const uint4*>(idx_s + cc);
@@ -175,94 +262,72 @@ __global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_consta
       uint32_t g[8][RW];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const uint32_t ch = (ivw[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+        const uint32_t ch = (e & 1) ? (ivw[e >> 1] >> 16) : (ivw[e >> 1] & 0xffffu);
         if constexpr (R == 4) {
-          const uint2 v = *reinterpret_cast<const uint2*>(xs + (size_t)ch * 8);
+          const uint2 v = *reinterpret_cast<const uint2*>(xs + ch * 8);
           g[e][0] = v.x;
           g[e][1] = v.y;
         } else {
-          g[e][0] = *reinterpret_cast<const uint32_t*>(xs + (size_t)ch * 4);
+          g[e][0] = *reinterpret_cast<const uint32_t*>(xs + ch * 4);
         }
       }
 
-      // ---- absmax per row over the 32-group (8 local channels, then 4 lanes)
-      uint32_t am[RW];
+      // ---- absmax per row over the 32-group: 8 local channels, then the 4 lanes of the team
+      const int qexp = (fmt == 4) ? 2 : ((fmt == 6) ? 4 : 8);  // QMAX = (1 + thr/128) * 2^qexp : 6, 28, 448
+      const uint32_t q2 = (uint32_t)qexp * 0x00010001u;
+      const uint32_t add2 = (fmt == 4) ? (63u * 0x00010001u) : (31u * 0x00010001u);  // 127 - thr, thr = 64 | 96
+      uint32_t mult[RW];
+      uint32_t sfb[RW];
 #pragma unroll
       for (int k = 0; k < RW; ++k) {
-        __nv_bfloat162 m = __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[0][k]));
+        uint32_t u = g[0][k] & 0x7fff7fffu;
 #pragma unroll
-        for (int e = 1; e < 8; ++e) m = __hmax2(m, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&g[e][k])));
-        uint32_t u = *reinterpret_cast<uint32_t*>(&m);
-#pragma unroll
-        for (int d = 1; d <= 2; d <<= 1) {
-          uint32_t o = __shfl_xor_sync(0xffffffffu, u, d);
-          __nv_bfloat162 mm = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), *reinterpret_cast<__nv_bfloat162*>(&o));
-          u = *reinterpret_cast<uint32_t*>(&mm);
-        }
-        am[k] = u;
+        for (int e = 1; e < 8; ++e) u = __vmaxu2(u, g[e][k] & 0x7fff7fffu);  // |bf16| orders like u16
+        u = __vmaxu2(u, __shfl_xor_sync(0xffffffffu, u, 1));
+        u = __vmaxu2(u, __shfl_xor_sync(0xffffffffu, u, 2));
+        // byte = max(exp - qexp, 0) + (mant > thr), both rows of the pair at once; 0x7E for an all-zero group
+        const uint32_t ex2 = (u >> 7) & 0x00ff00ffu;
+        const uint32_t gt2 = (((u & 0x007f007fu) + add2) >> 7) & 0x00010001u;
+        const uint32_t b2 = __vmaxu2(ex2, q2) - q2 + gt2;
+        mult[k] = (0x00fe00feu - b2) << 7;  // bf16x2 of 2^(127-byte)
+        const uint32_t z = __vcmpeq2(u, 0u);
+        sfb[k] = (b2 & ~z) | (0x007e007eu & z);
       }
 
-      // ---- scale byte and multiplier per row; convert; stage
-      const int qexp = (fmt == 4) ? 2 : ((fmt == 6) ? 4 : 8);  // QMAX = (1 + thr/128) * 2^qexp : 6, 28, 448
-      const int thr = (fmt == 4) ? 64 : 96;
-      const int vrel = voff(p, cc) - voff(p, C0);
-      uint32_t sfbytes = 0;
+      if (active) {
+        uint8_t* dst = stagebuf + vrel;
+        if (fmt == 4) convert_and_stage<4, R>(g, mult, dst, PASS_CH);
+        else if (fmt == 6) convert_and_stage<6, R>(g, mult, dst, PASS_CH);
+        else convert_and_stage<8, R>(g, mult, dst, PASS_CH);
+        if ((t & 3) == 0) {
+          const int G = c0 >> 5;
+          uint8_t* d = sfs + (G >> 2) * 16 + (R * h) * 4 + (G & 3);
 #pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const uint32_t a = (j & 1) ? (am[j >> 1] >> 16) : (am[j >> 1] & 0xffffu);
-        int byte = (int)(a >> 7) - qexp + (((int)(a & 0x7f) > thr) ? 1 : 0);
-        byte = max(byte, 0);
-        if (a == 0) byte = 126;  // all-zero group: scale 0.5 (reorder.cu:179,191,203)
-        sfbytes |= (uint32_t)(byte & 0xff) << (8 * j);
-        const float rs = __uint_as_float((uint32_t)(254 - byte) << 23);  // 2^(127-byte) = 1/scale
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t w = g[e][j >> 1];
-          f[e] = __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16)) * rs;
-        }
-        uint8_t* dst = stagebuf + j * PASS_CH + vrel;
-        if (active) {
-          if (fmt == 4) {
-            *reinterpret_cast<uint32_t*>(dst) = cvt8_e2m1(f);
-          } else if (fmt == 6) {
-            const uint32_t lo = pack4_fp6(cvt2_e3m2(f[0], f[1]), cvt2_e3m2(f[2], f[3]));
-            const uint32_t hi = pack4_fp6(cvt2_e3m2(f[4], f[5]), cvt2_e3m2(f[6], f[7]));
-            uint16_t* d16 = reinterpret_cast<uint16_t*>(dst);
-            d16[0] = (uint16_t)lo;
-            d16[1] = (uint16_t)((lo >> 16) | (hi << 8));
-            d16[2] = (uint16_t)(hi >> 8);
-          } else {
-            uint2 o;
-            o.x = cvt2_e4m3(f[0], f[1]) | (cvt2_e4m3(f[2], f[3]) << 16);
-            o.y = cvt2_e4m3(f[4], f[5]) | (cvt2_e4m3(f[6], f[7]) << 16);
-            *reinterpret_cast<uint2*>(dst) = o;
+          for (int k = 0; k < RW; ++k) {
+            d[8 * k] = (uint8_t)sfb[k];
+            d[8 * k + 4] = (uint8_t)(sfb[k] >> 16);
           }
         }
       }
-      if (active && (t & 3) == 0) {
-        const int G = c0 >> 5;
-        uint8_t* d = sfs + (G >> 2) * 16 + (R * h) * 4 + (G & 3);
-#pragma unroll
-        for (int j = 0; j < R; ++j) d[4 * j] = (uint8_t)(sfbytes >> (8 * j));
-      }
       __syncthreads();
 
-      // ---- coalesced 16-byte copy-out of this pass' packed codes
+      // ---- coalesced 16-byte copy-out of this pass' packed codes: T/R threads per row
       {
         const int C1 = min(C0 + PASS_CH, K);
-        const int vs = voff(p, C0);
-        const int n16 = (voff(p, C1) - vs) >> 4;
-        for (int i = t; i < R * n16; i += T) {
-          const int j = i / n16;
-          const int ch = i - j * n16;
-          const int64_t rj = row[0] + 32 * j;
-          if (rj >= p.rows) continue;
-          const int v = vs + 16 * ch;
-          const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
-          const int vb = (sg == 0) ? 0 : p.vend[sg - 1];
-          const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + j * PASS_CH + 16 * ch);
-          st_stream_v4(p.q[sg] + rj * p.rowbytes[sg] + (v - vb), val);
+        const int s1 = (C1 > p.cend[1]) ? 2 : (C1 > p.cend[0] ? 1 : 0);  // segment of channel C1-1
+        const int ve = (s1 ? p.vend[s1 - 1] : 0) + (((C1 - (s1 ? p.cend[s1 - 1] : 0)) * p.fmt[s1]) >> 3);
+        const int n16 = (ve - vs) >> 4;
+        constexpr int TPR = T / R;
+        const int j = t / TPR;
+        const int64_t rj = row0 + 32 * j;
+        if (rj < p.rows) {
+          for (int ch = t - j * TPR; ch < n16; ch += TPR) {
+            const int v = vs + 16 * ch;
+            const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
+            const int vb = (sg == 0) ? 0 : p.vend[sg - 1];
+            const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + j * PASS_CH + 16 * ch);
+            st_stream_v4(p.q[sg] + rj * p.rowbytes[sg] + (v - vb), val);
+          }
         }
       }
     }
@@ -280,7 +345,8 @@ __global__ void __launch_bounds__(T) reorder_quantize_kernel(const __grid_consta
         *reinterpret_cast<uint2*>(dst + 8 * h) = *reinterpret_cast<const uint2*>(sfs + ch * 16 + 8 * h);
       }
     }
-    // the next item's first __syncthreads (after its load phase) orders these reads before sfs/stage/xs reuse
+    // the next item's __syncthreads (after its xs stores) orders these reads before sfs/stage reuse; xs itself is
+    // only rewritten after the last pass' barrier, i.e. after every gather of this item
   }
 }
 
@@ -289,21 +355,20 @@ static size_t quant_smem_bytes(int K) {
   return ((size_t)(K * 2 + 15) & ~(size_t)15) + (size_t)K * R * 2 + (size_t)2 * R * 8 * T + (size_t)(K / 128) * 16;
 }
 
-template <int R, int T>
+template <int R, int T, int NLD, int MINB>
 static int launch_quant(const QuantParams& p, cudaStream_t stream) {
-  static int occ_cached[2] = {-1, -1};  // keyed on smem size below/above 48K is not enough; recompute per K cheaply
   const size_t smem = quant_smem_bytes<R, T>(p.K);
-  if (smem > 227 * 1024) {
-    set_error("reorder_quantize: K=%d needs %zu bytes of shared memory", p.K, smem);
+  if (smem > 227 * 1024 || (int64_t)NLD * T * 4 < p.K) {
+    set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, T, NLD,
+              smem);
     return MMX_ERR_INVALID;
   }
-  auto kern = reorder_quantize_kernel<R, T>;
+  auto kern = reorder_quantize_kernel<R, T, NLD, MINB>;
   static size_t attr_set = 0;
   if (smem > attr_set) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
   }
-  (void)occ_cached;
   int occ = 0;
   MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
   if (occ < 1) occ = 1;
@@ -369,14 +434,20 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   }
   const int64_t rblocks = (rows + 127) / 128;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int force = (int)options().quant_rows;
-  const bool r4_fits = quant_smem_bytes<4, 256>(K) <= 110 * 1024;  // keep >= 2 CTAs per SM
-  if ((force == 4) || (force == 0 && r4_fits)) {
+  const int force = (int)options().quant_rows;
+  // configuration by K: rows per item R, threads T, prefetch depth NLD (NLD*T*4 >= K); smem grows with K*R
+  if (force != 2 && K <= 4096) {
     p.num_items = rblocks * 32;
-    return launch_quant<4, 256>(p, st);
+    return launch_quant<4, 256, 4, 3>(p, st);
+  }
+  if (force != 2 && K <= 8192) {
+    p.num_items = rblocks * 32;
+    return launch_quant<4, 512, 4, 2>(p, st);
   }
   p.num_items = rblocks * 64;
-  return launch_quant<2, 512>(p, st);
+  if (K <= 4096) return launch_quant<2, 256, 4, 4>(p, st);
+  if (K <= 16384) return launch_quant<2, 512, 8, 2>(p, st);
+  return launch_quant<2, 512, 16, 1>(p, st);
 }
 
 }  // namespace mmx

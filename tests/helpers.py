@@ -74,3 +74,24 @@ def rel_err(got_bits: np.ndarray, ref_bits: np.ndarray):
     rms = np.sqrt(np.mean(r * r)) + 1e-30
     d = np.abs(g - r) / np.maximum(np.abs(r), rms)
     return float(d.max()), float(d.mean())
+
+
+# ---- cases whose reference-kernel outputs are committed in tests/golden/ref_reorder_golden.npz
+# (generated on a B200 by tools/make_golden_ref.py from the reference's own reorder.cu)
+GOLDEN_CASES = {
+    # /root/reference/mgemm/test.py:7-25 recipe: M=128, K=11008, identity index, boosted tail channels
+    "testpy": (128, 11008, (11008 - 1024, 1024 - 128, 128)),
+    "mixed": (300, 4096, (2560, 1024, 512)),
+    "thirds": (64, 3072, (1024, 1024, 1024)),
+}
+
+
+def golden_inputs(tag):
+    M, K, (KN, KS, KO) = GOLDEN_CASES[tag]
+    idx = make_index(K, seed=1, identity=(tag == "testpy"))
+    x = make_testpy_activations(M, K, KN, KS, KO) if tag == "testpy" else make_activations(M, K, idx)
+    return x, idx
+
+
+def load_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_reorder_golden.npz"))

@@ -1,0 +1,106 @@
+"""CPU tests of the N>1 path: shard planning + the reduce step under a world_size-2 gloo group.
+
+The per-rank compute stand-in is the oracle's fake-quant linear (the CUDA layers cannot run here); what is under
+test is the host logic of micromix_b200/parallel_utils.py: which rows/channels a rank owns, its rank-local
+permutation and split, and that summing the partials over the group reproduces the unsharded sharded-math result.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers as H
+
+O = H.O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_row_shard_plan_properties():
+    from micromix_b200.parallel_utils import row_shard_plan, column_shard_range
+    for K, (p4, p6, p8), tp in ((14336, (8960, 3584, 1792), 8), (4096, (2560, 1024, 512), 4), (27648, (17280, 6912, 3456), 2)):
+        idx = H.make_index(K, seed=K)
+        seen = []
+        for r in range(tp):
+            k0, k1, lidx, q4, q6, q8 = row_shard_plan(idx, p6, p8, tp, r)
+            assert (k0, k1) == (r * K // tp, (r + 1) * K // tp)
+            assert q4 + q6 + q8 == K // tp and min(q4, q6, q8) >= 0
+            assert q4 % 128 == 0 and q6 % 128 == 0 and q8 % 128 == 0
+            li = lidx.to(torch.int64)
+            assert sorted(li.tolist()) == list(range(K // tp))  # a permutation of the local slice
+            # importance order is preserved: local order is the global order filtered to the slice
+            glob = idx.to(torch.int64)
+            assert torch.equal(li + k0, glob[(glob >= k0) & (glob < k1)])
+            # the split follows the global assignment (random permutation -> close to p/tp)
+            assert abs(q8 - p8 / tp) <= 256 and abs(q6 - p6 / tp) <= 256
+            seen += (li + k0).tolist()
+        assert sorted(seen) == list(range(K))
+    assert column_shard_range(6144, 4, 1) == (1536, 3072)
+    with pytest.raises(ValueError):
+        column_shard_range(1024, 16, 0)
+    with pytest.raises(ValueError):
+        row_shard_plan(H.make_index(4096), 1024, 512, 64, 0)
+
+
+def _worker(rank, world, port, K, N, M, split, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from micromix_b200.parallel_utils import row_shard_plan, column_shard_range, all_reduce_sum
+        idx = H.make_index(K, seed=77)
+        x = H.make_activations(M, K, idx)
+        w = H.make_weights(N, K)
+        # ---- row parallel: local quantize + local mixed GEMM -> partial; partials summed over the group
+        k0, k1, lidx, p4, p6, p8 = row_shard_plan(idx, split[1], split[2], world, rank)
+        part = O.fake_quant_linear(H.bits(x[:, k0:k1].contiguous()), H.bits(w[:, k0:k1].contiguous()),
+                                   lidx.numpy(), p4, p6, p8, chain=False)
+        y = H.from_bits(part).clone()          # bf16 partial, as the GPU layer produces
+        all_reduce_sum(y)
+        # ---- column parallel: each rank's slice equals the slice of the unsharded result
+        n0, n1 = column_shard_range(N, world, rank)
+        col = O.fake_quant_linear(H.bits(x), H.bits(w[n0:n1].contiguous()), idx.numpy(), *split, chain=False)
+        gathered = [torch.empty(M, n1 - n0, dtype=torch.bfloat16) for _ in range(world)]
+        dist.all_gather(gathered, H.from_bits(col))
+        if rank == 0:
+            ret["row"] = H.bits(y)
+            ret["col"] = H.bits(torch.cat(gathered, dim=1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_row_and_column_parallel():
+    from micromix_b200.parallel_utils import row_shard_plan
+    K, N, M, split = 1024, 256, 24, (512, 256, 256)
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), K, N, M, split, ret), nprocs=world, join=True)
+    idx = H.make_index(K, seed=77)
+    x = H.make_activations(M, K, idx)
+    w = H.make_weights(N, K)
+    # expected row-parallel result: same sharded math in one process, partials rounded to bf16 then summed in bf16
+    acc = None
+    for r in range(world):
+        k0, k1, lidx, p4, p6, p8 = row_shard_plan(idx, split[1], split[2], world, r)
+        part = O.fake_quant_linear(H.bits(x[:, k0:k1].contiguous()), H.bits(w[:, k0:k1].contiguous()),
+                                   lidx.numpy(), p4, p6, p8, chain=False)
+        t = H.from_bits(part)
+        acc = t.clone() if acc is None else acc + t
+    assert np.array_equal(ret["row"], H.bits(acc))
+    # and it approximates the full-precision product as well as the unsharded quantized path does
+    full = O.fake_quant_linear(H.bits(x), H.bits(w), idx.numpy(), *split, chain=False)
+    exact = O.f32_to_bf16_bits((x.float() @ w.float().T).numpy())
+    e_tp, e_1 = H.rel_err(ret["row"], exact)[1], H.rel_err(full, exact)[1]
+    assert e_tp <= 1.5 * e_1 + 1e-3
+    assert np.array_equal(ret["col"], full)  # column parallel is exactly the unsharded result

@@ -131,8 +131,9 @@ def stage_gemm(tx_mode: int):
         L.mmx_gemm_debug_status(buf, 8)
         return [hex(v) for v in buf]
     cases = [(128, 256, (256, 0, 0)), (128, 256, (0, 0, 128)), (128, 256, (0, 128, 0)), (128, 256, (128, 0, 0)),
-             (128, 256, (512, 0, 0)), (128, 256, (0, 256, 0)), (128, 256, (0, 0, 256)),
-             (128, 256, (256, 128, 128)), (200, 384, (384, 256, 128)), (1, 128, (128, 128, 128)),
+             (256, 256, (256, 0, 0)), (256, 256, (0, 0, 128)), (256, 256, (0, 128, 0)), (256, 256, (128, 0, 0)),
+             (256, 256, (512, 0, 0)), (256, 256, (0, 256, 0)), (256, 256, (0, 0, 256)), (129, 128, (384, 0, 0)),
+             (256, 256, (256, 128, 128)), (200, 384, (384, 256, 128)), (1, 128, (128, 128, 128)),
              (300, 1024, (2560, 1024, 512)), (2048, 4096, (2560, 1024, 512))]
     allok = True
     for (M, N, (KN, KS, KO)) in cases:
@@ -179,6 +180,18 @@ def stage_gemm(tx_mode: int):
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 20 * 1e3
             print(f"gemm timing M={M} N={N} K={K}: {us:.1f} us  {2.0 * M * N * K / us / 1e6:.1f} TFLOPS", flush=True)
+            for (opt, val, tag) in ((b"gemm_cta_group", 1, "single-CTA kernel"), (b"gemm_ctas", 74, "74 CTAs")):
+                L.mmx_set_option(opt, val)
+                for _ in range(2):
+                    mixedgemm.matmul(a[0], b[0], a[1], b[1], a[2], b[2], a[3], b[3], a[4], b[4], a[5], b[5], out=out)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    mixedgemm.matmul(a[0], b[0], a[1], b[1], a[2], b[2], a[3], b[3], a[4], b[4], a[5], b[5], out=out)
+                e1.record(); torch.cuda.synchronize()
+                us2 = e0.elapsed_time(e1) / 10 * 1e3
+                print(f"     [{tag}] {us2:.1f} us  {2.0 * M * N * K / us2 / 1e6:.1f} TFLOPS", flush=True)
+                L.mmx_set_option(opt, 0)
 
 
 def run_stage(name, *args, timeout=600):
@@ -207,5 +220,3 @@ if __name__ == "__main__":
         subprocess.run(["nvidia-smi", "--query-gpu=name,clocks.sm,clocks.max.sm,memory.total", "--format=csv"])
         run_stage("quant")
         rc, out = run_stage("gemm", 0)
-        if "GEMM_ALL_OK" not in out:
-            run_stage("gemm", 1)
