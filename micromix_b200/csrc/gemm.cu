@@ -41,11 +41,12 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColSF = 256;   // scale factors: one 24-column slot per smem stage (SFA 8 = 2 atoms x 4, SFB 16)
 constexpr uint32_t kSFSlot = 24;   // per-stage slots, so a stage's tcgen05.cp never overwrites scales that MMAs
                                    // still in flight are reading (a single slot costs a ~300-cycle bubble per stage)
-constexpr int kEpiStage = 4096;    // per epilogue warp: 32 rows x 64 bf16, 128B-swizzled, source of the TMA store
+constexpr int kEpiBuf = 2048;      // 32 rows x 32 bf16 (64-byte rows, 64B swizzle): source of one TMA store
+constexpr int kEpiStage = 2 * kEpiBuf;  // two buffers per epilogue warp: stage chunk i+1 while chunk i is read
 
 template <int CG>
 struct Geo {
-  static constexpr int kStages = (CG == 1) ? 4 : 5;
+  static constexpr int kStages = (CG == 1) ? 4 : 6;
   static constexpr int kBRows = BN / CG;          // B rows this CTA stages
   static constexpr int kStageA = BM * 128;        // 16 KB
   static constexpr int kStageB = kBRows * 128;    // 32 | 16 KB
@@ -54,7 +55,7 @@ struct Geo {
   static constexpr int kStageBytes = kStageA + kStageB + kStageSFA + kStageSFB;
   static constexpr int kEpiOff = kStages * kStageBytes;        // 4 x kEpiStage, 1024-aligned
   static constexpr int kBarOff = kEpiOff + 4 * kEpiStage;
-  static constexpr int kSmemBytes = kBarOff + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kBarOff + 256 /*barriers*/;
 };
 
 struct GemmSeg {
@@ -84,7 +85,7 @@ struct alignas(64) TmapSet {
   CUtensorMap b[3];
   CUtensorMap sfa[3];  // 3-D [row-block][k-atom][128 x u32] views of the 512-byte scale atoms
   CUtensorMap sfb[3];
-  CUtensorMap c;       // bf16 [M, N], box 64 x 32, 128B swizzle: epilogue TMA stores
+  CUtensorMap c;       // bf16 [M, N], box 32 x 32, 64B swizzle: epilogue TMA stores
 };
 
 __device__ uint32_t g_gemm_dbg[64];
@@ -317,11 +318,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// 32 fp32 accumulator columns of one row -> bf16 (+bias) -> four 16-byte chunks of the warp's swizzled staging tile.
-// Row r of the tile is 128 bytes; chunk c lives at ((c ^ (r & 7)) << 4), the 128B-swizzle pattern of the C tensor map.
-__device__ __forceinline__ void stage_chunk(const uint32_t (&r)[32], uint32_t srow, int lane, int half,
-                                            const __nv_bfloat16* bias) {
-  uint32_t o[16];
+// 32 fp32 accumulator columns of one row -> 16 packed bf16x2 words (+bias, rounded like the reference's separate add)
+__device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t* o, const __nv_bfloat16* bias) {
   if (bias != nullptr) {
     const uint4* bp = reinterpret_cast<const uint4*>(bias);
 #pragma unroll
@@ -342,11 +340,17 @@ __device__ __forceinline__ void stage_chunk(const uint32_t (&r)[32], uint32_t sr
 #pragma unroll
     for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
   }
+}
+
+// 16 packed words (32 bf16 of one row) -> four 16-byte chunks of a 32x32 staging buffer.  Row r is 64 bytes; chunk c
+// lives at ((c ^ ((r >> 1) & 3)) << 4): the 64B-swizzle pattern of the C tensor map, conflict-free for the warp.
+__device__ __forceinline__ void stage_chunk(const uint32_t* o, uint32_t sbuf, int lane) {
+  const uint32_t srow = sbuf + (uint32_t)lane * 64u;
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
-    const uint32_t chunk = (uint32_t)(half * 4 + v) ^ (uint32_t)(lane & 7);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (chunk << 4)), "r"(o[4 * v]), "r"(o[4 * v + 1]),
-                 "r"(o[4 * v + 2]), "r"(o[4 * v + 3])
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((uint32_t)v ^ sw) << 4)), "r"(o[4 * v]),
+                 "r"(o[4 * v + 1]), "r"(o[4 * v + 2]), "r"(o[4 * v + 3])
                  : "memory");
   }
 }
@@ -364,8 +368,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p) {
   using G = Geo<CG>;
   constexpr int kStages = G::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
+  const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t bar_base = smem_base + G::kBarOff;
   // barriers: full[kStages] | empty[kStages] | tmem_full | tmem_empty | tmem_ptr(u32)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -561,28 +565,39 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       const int row0 = (m_blk * CG + (int)rank) * BM + q * 32;  // first C row of this warp's 32-row band
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
       const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
-      const uint32_t srow = sbuf + (uint32_t)lane * 128u;
-#pragma unroll 1
+      const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
+      // ---- phase 1: drain the whole 32 x 256 accumulator band into registers (packed bf16), then hand TMEM back
+      // to the MMA warp at once -- the next tile's MMAs overlap phase 2 although there is a single accumulator.
+      uint32_t packed[BN / 2];
+#pragma unroll
       for (int ch = 0; ch < BN / 64; ++ch) {
-        const int col0 = n_blk * BN + ch * 64;
-        if (col0 >= p.N) break;  // warp-uniform
         uint32_t r0[32], r1[32];
         tmem_ld32(tbase + (uint32_t)(ch * 64), r0);
         tmem_ld32(tbase + (uint32_t)(ch * 64 + 32), r1);
         tmem_ld_wait();
-        // the previous TMA store must have finished READING the staging tile before it is overwritten
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-        stage_chunk(r0, srow, lane, 0, p.bias ? p.bias + col0 : nullptr);
-        stage_chunk(r1, srow, lane, 1, p.bias ? p.bias + col0 + 32 : nullptr);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
-        __syncwarp();
-        if (lane == 0 && row0 < p.M && !(WD && (p.flags & 4u))) tma_store_2d(&tmaps.c, sbuf, col0, row0);  // clips at M, N
+        const int col0 = min(n_blk * BN + ch * 64, (int)p.N - 64);  // clamp keeps bias reads in bounds on an N tail
+        pack_chunk(r0, &packed[32 * ch], p.bias ? p.bias + col0 : nullptr);
+        pack_chunk(r1, &packed[32 * ch + 16], p.bias ? p.bias + col0 + 32 : nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+      }
+      // ---- phase 2: registers -> swizzled smem (two alternating 2 KB buffers) -> TMA stores
+#pragma unroll
+      for (int sc = 0; sc < BN / 32; ++sc) {
+        const int col0 = n_blk * BN + sc * 32;
+        if (col0 < p.N) {  // warp-uniform
+          const uint32_t buf = sbuf + (uint32_t)(sc & 1) * kEpiBuf;
+          // the store issued from this buffer two sub-chunks ago must have finished READING it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          stage_chunk(&packed[16 * sc], buf, lane);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
+          __syncwarp();
+          if (lane == 0 && do_store) tma_store_2d(&tmaps.c, buf, col0, row0);  // clipped at M and N by the map
+        }
       }
       tphase ^= 1;
       if (WD) {
@@ -711,7 +726,7 @@ static int get_sf_tmap(const void* ptr, int64_t rblocks, int katoms, int box_ato
   return MMX_OK;
 }
 
-// output map: bf16 C[M, N] row-major, box = 64 columns x 32 rows, 128B swizzle (matches stage_chunk's layout)
+// output map: bf16 C[M, N] row-major, box = 32 columns x 32 rows, 64B swizzle (matches stage_chunk's layout)
 static int get_c_tmap(void* ptr, int64_t M, int64_t N, CUtensorMap* out) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -720,10 +735,10 @@ static int get_c_tmap(void* ptr, int64_t M, int64_t N, CUtensorMap* out) {
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
   const cuuint64_t gstride[1] = {(cuuint64_t)N * 2};
-  const cuuint32_t box[2] = {64, 32};
+  const cuuint32_t box[2] = {32, 32};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (C) failed (%d) ptr=%p M=%lld N=%lld", (int)r, ptr, (long long)M, (long long)N);
     return MMX_ERR_CUDA;

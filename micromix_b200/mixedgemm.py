@@ -73,8 +73,10 @@ def _reorder_quantize(fn_name, T, reorder_index, KN, KS, KO, widths, is_act):
             sf = [torch.empty((int(lib.mmx_sf_bytes_act(rows, k)),), **opts) for k in (KN, KS, KO)]
         else:       # bindings.cpp:170-172 (rounded up to whole 128-row blocks so N % 128 != 0 stays in bounds)
             sf = [torch.empty((int(lib.mmx_sf_bytes_wgt(rows, k)),), **opts) for k in (KN, KS, KO)]
-        rc = getattr(lib, fn_name)(_ptr(T), rows, K, _ptr(reorder_index), KN, KS, KO, _ptr(q[0]), _ptr(q[1]),
-                                   _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
+        rc = 0
+        if rows > 0:
+            rc = getattr(lib, fn_name)(_ptr(T), rows, K, _ptr(reorder_index), KN, KS, KO, _ptr(q[0]), _ptr(q[1]),
+                                       _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
     _lib.check(rc, fn_name)
     return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
 
