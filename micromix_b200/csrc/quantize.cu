@@ -144,138 +144,175 @@ __device__ __forceinline__ uint2 ld_stream_u64(const void* p) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
 // R rows per item, T threads, NLD = register-prefetch depth (each thread holds NLD x R 8-byte loads of the NEXT item
 // while it computes the current one; needs NLD * T * 4 >= K).
+//
+// Shared memory: idx_s[K] i16 | tabA[K/8] u32 | tabB[K/16] u32 | tabV[npass+1] u32 | xs | stage | sfs
+//   tabA[o]  per channel octet o: format code (bits 30..31: 0 FP4, 1 FP6, 2 FP8) | byte offset of the octet's packed
+//            codes relative to the start of its pass in the "virtual packed row" (all three segments back to back)
+//   tabB[q]  per 16-byte chunk q of the virtual packed row: segment (bits 28..29) | byte offset inside that segment's row
+//   tabV[ps] first 16-byte chunk of pass ps (tabV[npass] = total chunks)
+// The tables are built once per CTA, so the per-item / per-pass code does no segment bookkeeping at all.
 template <int R, int T, int NLD, int MINB>
 __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
   constexpr int HS = 4 / R;        // items per (128-row block, lane row l)
   constexpr int RW = R / 2;        // 32-bit words per gathered channel (two rows per word)
   constexpr int PASS_CH = 8 * T;   // channels per pass
+  constexpr int TPR = T / R;       // copy-out threads per row
   extern __shared__ __align__(16) uint8_t smem[];
   const int K = p.K;
+  const int npass = (K + PASS_CH - 1) / PASS_CH;
   int16_t* idx_s = reinterpret_cast<int16_t*>(smem);
-  uint8_t* xs = smem + ((K * 2 + 15) & ~15);
+  uint32_t* tabA = reinterpret_cast<uint32_t*>(smem + ((K * 2 + 15) & ~15));
+  uint32_t* tabB = tabA + K / 8;
+  uint32_t* tabV = tabB + K / 16;
+  uint8_t* xs = reinterpret_cast<uint8_t*>(tabV) + 64;
   uint8_t* stage = xs + (size_t)K * R * 2;
   uint8_t* sfs = stage + 2 * R * PASS_CH;
+  const uint32_t xs_a = smem_addr(xs);
   const int t = threadIdx.x;
   const int K4 = K >> 2;
 
+  // ---- one-time per CTA: permutation and lookup tables
   for (int i = t; i < K / 8; i += T) reinterpret_cast<uint4*>(idx_s)[i] = reinterpret_cast<const uint4*>(p.idx)[i];
+  for (int o = t; o < K / 8; o += T) {
+    const int c = o * 8;
+    const int sg = (c >= p.cend[1]) ? 2 : (c >= p.cend[0] ? 1 : 0);
+    const int C0 = (c / PASS_CH) * PASS_CH;
+    tabA[o] = ((uint32_t)((p.fmt[sg] - 4) >> 1) << 30) | (uint32_t)(voff(p, c) - voff(p, C0));  // 4|6|8 bits -> 0|1|2
+  }
+  for (int q = t; q < p.vend[2] / 16; q += T) {
+    const int v = q * 16;
+    const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
+    tabB[q] = ((uint32_t)sg << 28) | (uint32_t)(v - (sg ? p.vend[sg - 1] : 0));
+  }
+  if (t <= npass) tabV[t] = (uint32_t)(voff(p, min(t * PASS_CH, K)) >> 4);
+  // (the first __syncthreads of the item loop publishes the tables)
 
-  const int npass = (K + PASS_CH - 1) / PASS_CH;
   uint2 pre[NLD][R];  // prefetched rows of the next item
 
-  auto item_rows = [&](int64_t item, int& l, int& h, int64_t& rb) -> int64_t {
-    l = (int)(item & 31);
-    const int64_t it2 = item >> 5;
-    h = (int)(it2 % HS);
+  // item -> first row (the other R-1 rows follow at +32 each), all in 32-bit arithmetic
+  auto item_row0 = [&](int item, int& l, int& h, int& rb) -> int {
+    l = item & 31;
+    const int it2 = item >> 5;
+    h = it2 % HS;
     rb = it2 / HS;
-    return rb * 128 + l + 32 * (R * h);  // first row; the others follow at +32 each
+    return rb * 128 + l + 32 * (R * h);
   };
-  auto prefetch = [&](int64_t item) {
-    int l, h;
-    int64_t rb;
-    const int64_t row0 = item_rows(item, l, h, rb);
-    const uint16_t* base[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int64_t rj = row0 + 32 * j;
-      base[j] = p.x + (rj < p.rows ? rj : 0) * (int64_t)K + 4 * t;  // invalid rows re-read row 0, zeroed at the store
-    }
+  auto prefetch = [&](int item) {
+    int l, h, rb;
+    const int row0 = item_row0(item, l, h, rb);
+    if (row0 >= (int)p.rows) return;  // block-uniform: nothing to fetch for an item past the last row
+    const uint16_t* b0 = p.x + (int64_t)row0 * K + 4 * t;
+    const int64_t rstride = (int64_t)32 * K;
+    const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       if (i * T + t < K4) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) pre[i][j] = ld_stream_u64(base[j] + (size_t)i * T * 4);
+        for (int j = 0; j < R; ++j)  // rows past the end re-read row0; they are zeroed when stored to shared memory
+          pre[i][j] = ld_stream_u64(b0 + (j < nvalid ? j * rstride : 0) + (size_t)i * T * 4);
       }
     }
   };
 
-  int64_t item = blockIdx.x;
-  if (item < p.num_items) prefetch(item);
+  const int num_items = (int)p.num_items;
+  int item = blockIdx.x;
+  if (item < num_items) prefetch(item);
 
-  for (; item < p.num_items; item += gridDim.x) {
-    int l, h;
-    int64_t rb;
-    const int64_t row0 = item_rows(item, l, h, rb);
-    if (row0 >= p.rows) break;  // block-uniform; items are ordered by row, nothing valid follows for this CTA stride
+  for (; item < num_items; item += gridDim.x) {
+    int l, h, rb;
+    const int row0 = item_row0(item, l, h, rb);
+    if (row0 >= (int)p.rows) break;  // block-uniform; items are ordered by row, nothing valid follows for this CTA
+    const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
 
     // ---- prefetched registers -> shared memory, channel-major / row-interleaved
-    {
-      const bool full = row0 + 32 * (R - 1) < p.rows;
 #pragma unroll
-      for (int i = 0; i < NLD; ++i) {
-        const int c4 = i * T + t;
-        if (c4 < K4) {
-          uint2 w[R];
+    for (int i = 0; i < NLD; ++i) {
+      const int c4 = i * T + t;
+      if (c4 < K4) {
+        uint2 w[R];
 #pragma unroll
-          for (int j = 0; j < R; ++j) w[j] = pre[i][j];
-          if (!full) {
+        for (int j = 0; j < R; ++j) w[j] = pre[i][j];
+        if (nvalid < R) {  // block-uniform; only the last, partly filled row block takes this path
 #pragma unroll
-            for (int j = 1; j < R; ++j)
-              if (row0 + 32 * j >= p.rows) w[j] = make_uint2(0u, 0u);
-          }
-          if constexpr (R == 4) {
-            uint4 o0, o1;
-            o0.x = __byte_perm(w[0].x, w[1].x, 0x5410);
-            o0.y = __byte_perm(w[2].x, w[3].x, 0x5410);
-            o0.z = __byte_perm(w[0].x, w[1].x, 0x7632);
-            o0.w = __byte_perm(w[2].x, w[3].x, 0x7632);
-            o1.x = __byte_perm(w[0].y, w[1].y, 0x5410);
-            o1.y = __byte_perm(w[2].y, w[3].y, 0x5410);
-            o1.z = __byte_perm(w[0].y, w[1].y, 0x7632);
-            o1.w = __byte_perm(w[2].y, w[3].y, 0x7632);
-            uint4* d = reinterpret_cast<uint4*>(xs + (size_t)c4 * 32);
-            d[0] = o0;
-            d[1] = o1;
-          } else {
-            uint4 o;
-            o.x = __byte_perm(w[0].x, w[1].x, 0x5410);
-            o.y = __byte_perm(w[0].x, w[1].x, 0x7632);
-            o.z = __byte_perm(w[0].y, w[1].y, 0x5410);
-            o.w = __byte_perm(w[0].y, w[1].y, 0x7632);
-            *reinterpret_cast<uint4*>(xs + (size_t)c4 * 16) = o;
-          }
+          for (int j = 1; j < R; ++j)
+            if (j >= nvalid) w[j] = make_uint2(0u, 0u);
+        }
+        if constexpr (R == 4) {
+          uint4 o0, o1;
+          o0.x = __byte_perm(w[0].x, w[1].x, 0x5410);
+          o0.y = __byte_perm(w[2].x, w[3].x, 0x5410);
+          o0.z = __byte_perm(w[0].x, w[1].x, 0x7632);
+          o0.w = __byte_perm(w[2].x, w[3].x, 0x7632);
+          o1.x = __byte_perm(w[0].y, w[1].y, 0x5410);
+          o1.y = __byte_perm(w[2].y, w[3].y, 0x5410);
+          o1.z = __byte_perm(w[0].y, w[1].y, 0x7632);
+          o1.w = __byte_perm(w[2].y, w[3].y, 0x7632);
+          uint4* d = reinterpret_cast<uint4*>(xs + (size_t)c4 * 32);
+          d[0] = o0;
+          d[1] = o1;
+        } else {
+          uint4 o;
+          o.x = __byte_perm(w[0].x, w[1].x, 0x5410);
+          o.y = __byte_perm(w[0].x, w[1].x, 0x7632);
+          o.z = __byte_perm(w[0].y, w[1].y, 0x5410);
+          o.w = __byte_perm(w[0].y, w[1].y, 0x7632);
+          *reinterpret_cast<uint4*>(xs + (size_t)c4 * 16) = o;
         }
       }
     }
     __syncthreads();
-    if (item + gridDim.x < p.num_items) prefetch(item + gridDim.x);  // in flight during the compute below
+    if (item + (int)gridDim.x < num_items) prefetch(item + (int)gridDim.x);  // in flight during the compute below
+
+    // this thread's copy-out row and its three destination row pointers
+    const int jrow = t / TPR;
+    const bool jvalid = jrow < nvalid;
+    const int64_t rj = (int64_t)row0 + 32 * jrow;
+    uint8_t* const d0 = p.q[0] + rj * p.rowbytes[0];
+    uint8_t* const d1 = p.q[1] + rj * p.rowbytes[1];
+    uint8_t* const d2 = p.q[2] + rj * p.rowbytes[2];
 
     for (int ps = 0; ps < npass; ++ps) {
-      const int C0 = ps * PASS_CH;
-      const int c0 = C0 + 8 * t;
-      const bool active = c0 < K;
-      const int cc = active ? c0 : 0;
-      const int s = (cc >= p.cend[1]) ? 2 : (cc >= p.cend[0] ? 1 : 0);
-      const int fmt = p.fmt[s];
+      const int oct = ps * T + t;
+      const bool active = oct * 8 < K;
+      const int oc = active ? oct : 0;
+      const uint32_t ta = tabA[oc];
+      const uint32_t fmtc = ta >> 30;
       uint8_t* stagebuf = stage + (ps & 1) * (R * PASS_CH);
-      // packed-byte offset of channel c inside the virtual packed row
-      const int s0 = (C0 >= p.cend[1]) ? 2 : (C0 >= p.cend[0] ? 1 : 0);
-      const int vs = (s0 ? p.vend[s0 - 1] : 0) + (((C0 - (s0 ? p.cend[s0 - 1] : 0)) * p.fmt[s0]) >> 3);
-      const int vrel = (s ? p.vend[s - 1] : 0) + (((cc - (s ? p.cend[s - 1] : 0)) * fmt) >> 3) - vs;
 
       // ---- gather 8 permuted channels x R rows
-      const uint4 iv = *reinterpret_cast<const uint4*>(idx_s + cc);
+      const uint4 iv = *reinterpret_cast<const uint4*>(idx_s + oc * 8);
       const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
       uint32_t g[8][RW];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const uint32_t ch = (e & 1) ? (ivw[e >> 1] >> 16) : (ivw[e >> 1] & 0xffffu);
         if constexpr (R == 4) {
-          const uint2 v = *reinterpret_cast<const uint2*>(xs + ch * 8);
+          const uint2 v = lds64(xs_a + ch * 8);
           g[e][0] = v.x;
           g[e][1] = v.y;
         } else {
-          g[e][0] = *reinterpret_cast<const uint32_t*>(xs + ch * 4);
+          g[e][0] = lds32(xs_a + ch * 4);
         }
       }
 
-      // ---- absmax per row over the 32-group: 8 local channels, then the 4 lanes of the team
-      const int qexp = (fmt == 4) ? 2 : ((fmt == 6) ? 4 : 8);  // QMAX = (1 + thr/128) * 2^qexp : 6, 28, 448
-      const uint32_t q2 = (uint32_t)qexp * 0x00010001u;
-      const uint32_t add2 = (fmt == 4) ? (63u * 0x00010001u) : (31u * 0x00010001u);  // 127 - thr, thr = 64 | 96
+      // ---- absmax per row over the 32-group (8 local channels, then the 4 lanes of the team), scale byte, multiplier
+      const uint32_t q2 = (fmtc == 0) ? 0x00020002u : ((fmtc == 1) ? 0x00040004u : 0x00080008u);  // log2floor(QMAX)
+      const uint32_t add2 = (fmtc == 0) ? (63u * 0x00010001u) : (31u * 0x00010001u);            // 127 - thr, thr = 64 | 96
       uint32_t mult[RW];
       uint32_t sfb[RW];
 #pragma unroll
@@ -295,12 +332,12 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       }
 
       if (active) {
-        uint8_t* dst = stagebuf + vrel;
-        if (fmt == 4) convert_and_stage<4, R>(g, mult, dst, PASS_CH);
-        else if (fmt == 6) convert_and_stage<6, R>(g, mult, dst, PASS_CH);
+        uint8_t* dst = stagebuf + (ta & 0x3fffffffu);
+        if (fmtc == 0) convert_and_stage<4, R>(g, mult, dst, PASS_CH);
+        else if (fmtc == 1) convert_and_stage<6, R>(g, mult, dst, PASS_CH);
         else convert_and_stage<8, R>(g, mult, dst, PASS_CH);
         if ((t & 3) == 0) {
-          const int G = c0 >> 5;
+          const int G = oct >> 2;  // 32-channel group index
           uint8_t* d = sfs + (G >> 2) * 16 + (R * h) * 4 + (G & 3);
 #pragma unroll
           for (int k = 0; k < RW; ++k) {
@@ -312,22 +349,15 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       __syncthreads();
 
       // ---- coalesced 16-byte copy-out of this pass' packed codes: T/R threads per row
-      {
-        const int C1 = min(C0 + PASS_CH, K);
-        const int s1 = (C1 > p.cend[1]) ? 2 : (C1 > p.cend[0] ? 1 : 0);  // segment of channel C1-1
-        const int ve = (s1 ? p.vend[s1 - 1] : 0) + (((C1 - (s1 ? p.cend[s1 - 1] : 0)) * p.fmt[s1]) >> 3);
-        const int n16 = (ve - vs) >> 4;
-        constexpr int TPR = T / R;
-        const int j = t / TPR;
-        const int64_t rj = row0 + 32 * j;
-        if (rj < p.rows) {
-          for (int ch = t - j * TPR; ch < n16; ch += TPR) {
-            const int v = vs + 16 * ch;
-            const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
-            const int vb = (sg == 0) ? 0 : p.vend[sg - 1];
-            const uint4 val = *reinterpret_cast<const uint4*>(stagebuf + j * PASS_CH + 16 * ch);
-            st_stream_v4(p.q[sg] + rj * p.rowbytes[sg] + (v - vb), val);
-          }
+      if (jvalid) {
+        const int q0 = (int)tabV[ps];
+        const int n16 = (int)tabV[ps + 1] - q0;
+        const uint8_t* src = stagebuf + jrow * PASS_CH;
+        for (int ch = t - jrow * TPR; ch < n16; ch += TPR) {
+          const uint32_t tb = tabB[q0 + ch];
+          const uint32_t sg = tb >> 28;
+          uint8_t* d = (sg == 0) ? d0 : ((sg == 1) ? d1 : d2);
+          st_stream_v4(d + (tb & 0x0fffffffu), *reinterpret_cast<const uint4*>(src + 16 * ch));
         }
       }
     }
@@ -338,7 +368,7 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       const int sg = (c >= p.cend[1]) ? 2 : (c >= p.cend[0] ? 1 : 0);
       const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
       const int ka = (c - cb) >> 7;
-      uint8_t* dst = p.sf[sg] + (rb * p.katoms[sg] + ka) * 512 + l * 16;
+      uint8_t* dst = p.sf[sg] + ((int64_t)rb * p.katoms[sg] + ka) * 512 + l * 16;
       if constexpr (R == 4) {
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sfs + ch * 16);
       } else {
@@ -352,7 +382,8 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
 
 template <int R, int T>
 static size_t quant_smem_bytes(int K) {
-  return ((size_t)(K * 2 + 15) & ~(size_t)15) + (size_t)K * R * 2 + (size_t)2 * R * 8 * T + (size_t)(K / 128) * 16;
+  return ((size_t)(K * 2 + 15) & ~(size_t)15) + (size_t)(K / 8) * 4 + (size_t)(K / 16) * 4 + 64 /*tabV*/ +
+         (size_t)K * R * 2 + (size_t)2 * R * 8 * T + (size_t)(K / 128) * 16;
 }
 
 template <int R, int T, int NLD, int MINB>

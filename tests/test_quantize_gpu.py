@@ -67,7 +67,7 @@ def test_segment_extremes(cuda, split):
 
 
 @pytest.mark.parametrize("K,split", [(128, (128, 0, 0)), (128, (0, 128, 0)), (128, (0, 0, 128)),
-                                     (384, (128, 128, 128)), (27648, (17280, 6912, 3456)), (32640, (32000, 512, 128)),
+                                     (384, (128, 128, 128)), (27648, (17280, 6912, 3456)), (30720, (30080, 512, 128)),
                                      (6912, (4352, 1792, 768)), (1792, (1152, 384, 256))])
 def test_k_not_in_reference_list(cuda, K, split):
     """TP shards (6912, 1792, ...) and the K the reference cannot run (27648) must work here."""
