@@ -4,21 +4,26 @@
 // (reorder_quantize_mxfp4_kernel) behind mmx_reorder_quantize_{x,w,w4}; results are bit-identical
 // (codes, packing, scale bytes, scale-factor swizzle) -- see oracle/mmx_oracle.c for the restated semantics.
 //
-// Design (HBM-bound, nothing GEMM-shaped here):
+// Design (HBM-bound byte work; the enemy is the instruction count per element, not arithmetic):
 //   * Persistent CTAs.  A work item is R rows {rb*128 + l + 32*(R*h+j), j<R}: the R rows whose scale bytes share
-//     one 16-byte line of the 512-byte scale-factor atom, so scales leave the SM as 16-byte (R=4) / 8-byte (R=2)
-//     stores instead of 1-byte scatters.
-//   * The R rows are read with coalesced 32-bit loads and stored to shared memory channel-major, row-interleaved
-//     (xs[c][j]); the permuted gather x[r, idx[c]] then costs ONE 8-byte (R=4) shared load per channel for all R
-//     rows, i.e. R times fewer bank-conflicted gathers than a row-at-a-time kernel.  reorder_index is staged in
-//     shared memory once per CTA (the reference re-reads it from global memory for every row).
-//   * A thread owns 8 consecutive permuted channels (a quarter of a 32-group) of all R rows: absmax over packed
-//     bf16x2 (two rows per instruction), two warp shuffles finish the group reduction.
-//   * Scale: integer exponent arithmetic on the bf16 absmax -- byte = exp(amax) - log2floor(QMAX) + (mant > mant(QMAX)),
-//     0x7E for an all-zero group -- provably equal to the reference's ceil(log2(amax/QMAX)) for every bf16 amax
-//     (tests/test_oracle_pin.py::test_scale_rule_exhaustive).  Elements: x * 2^-e is exact in fp32, then the
-//     hardware cvt.rn.satfinite.{e2m1x2,e3m2x2,e4m3x2}.f32 (RNE, saturating == the reference's clamp + software RNE).
-//   * Packed codes are staged in shared memory per pass and leave as fully coalesced 16-byte stores.
+//     one 16-byte line of the 512-byte scale-factor atom.
+//   * SCATTER ON WRITE.  The permutation is applied while the rows go into shared memory, not when they are read
+//     back: each thread loads 16 bytes (8 original channels) of each of the R rows with coalesced 128-bit loads,
+//     interleaves the rows with PRMT (one slot = the R values of one channel, 2R bytes) and stores every slot at the
+//     position of its PERMUTED channel (inverse permutation, built once per CTA as a table of swizzled byte
+//     offsets).  The read side is then perfectly sequential: a thread owns 16 consecutive permuted channels (half a
+//     32-group) of all R rows and fetches them with conflict-free 128-bit shared loads (XOR swizzle on the 16-byte
+//     chunk index), with no index loads and no address arithmetic in the loop.
+//   * Register prefetch: the global loads of the NEXT item are issued right after the scatter of the current one and
+//     stay in flight during its compute phase.
+//   * absmax: max.xorsign.abs.bf16x2 (one instruction per two elements, two rows at once), one warp shuffle finishes
+//     the 32-group.  Scale: integer exponent arithmetic on the bf16 absmax --
+//     byte = exp(amax) - log2floor(QMAX) + (mant > mant(QMAX)), 0x7E for an all-zero group -- provably equal to the
+//     reference's ceil(log2(amax/QMAX)) for every bf16 amax (tests/test_oracle_pin.py::test_scale_rule_exhaustive).
+//     Elements: x * 2^-e is exact (bf16x2 multiply by a power of two), then the hardware
+//     cvt.rn.satfinite.{e2m1x2,e3m2x2,e4m3x2}.f32 (RNE, saturating == the reference's clamp + software RNE).
+//   * Packed codes leave straight from registers: 8 (FP4) / 12 (FP6) / 16 (FP8) contiguous bytes per thread and row,
+//     so a warp writes 256 / 384 / 512 contiguous bytes per row -- full sectors, no staging pass.
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -29,32 +34,54 @@ struct QuantParams {
   const uint16_t* x;
   const int16_t* idx;
   int64_t rows;
-  int64_t num_items;
+  int num_items;
   int K;
-  int kseg[3];      // channels per segment
   int fmt[3];       // bits per code: 4 | 6 | 8
   int cend[3];      // cumulative channel ends
-  int vend[3];      // cumulative packed-byte ends of the "virtual packed row" (all three segments back to back)
   int katoms[3];    // kseg / 128
   int64_t rowbytes[3];
   uint8_t* q[3];
   uint8_t* sf[3];
 };
 
-__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
-  uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
   return v;
 }
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t x) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void stg_v2(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void stg_b32(void* p, uint32_t a) {
+  asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
+}
 
-__device__ __forceinline__ void st_stream_v4(void* p, const uint4& v) {
-  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
+// max(|a|, |b|) on both bf16 halves; the sign bits of the result are garbage (xor of the input signs)
+__device__ __forceinline__ uint32_t absmax2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.xorsign.abs.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
 }
 
 // 8 floats -> 8 E2M1 codes, element 0 in the low nibble of byte 0 (reorder.cu:30-33 PackFp4).
-__device__ __forceinline__ uint32_t cvt8_e2m1(const float (&f)[8]) {
+__device__ __forceinline__ uint32_t cvt8_e2m1(const float* f) {
   uint32_t r;
   asm("{\n"
       ".reg .b8 b0, b1, b2, b3;\n"
@@ -69,142 +96,122 @@ __device__ __forceinline__ uint32_t cvt8_e2m1(const float (&f)[8]) {
   return r;
 }
 
-// 2 floats -> two 6-bit E3M2 codes, each in the low 6 bits of a byte (a low byte, b high byte).
-__device__ __forceinline__ uint32_t cvt2_e3m2(float a, float b) {
-  uint16_t h;
-  asm("cvt.rn.satfinite.e3m2x2.f32 %0, %2, %1;" : "=h"(h) : "f"(a), "f"(b));
-  return h;
+// 4 floats -> four E3M2 codes, one per byte (6 bits each, upper two bits zero)
+__device__ __forceinline__ uint32_t cvt4_e3m2(const float* f) {
+  uint32_t r;
+  asm("{\n"
+      ".reg .b16 h0, h1;\n"
+      "cvt.rn.satfinite.e3m2x2.f32 h0, %2, %1;\n"
+      "cvt.rn.satfinite.e3m2x2.f32 h1, %4, %3;\n"
+      "mov.b32 %0, {h0, h1};\n"
+      "}"
+      : "=r"(r)
+      : "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]));
+  return r;
 }
 
-__device__ __forceinline__ uint32_t cvt2_e4m3(float a, float b) {
-  uint16_t h;
-  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %2, %1;" : "=h"(h) : "f"(a), "f"(b));
-  return h;
+// 4 floats -> four E4M3 codes, one per byte
+__device__ __forceinline__ uint32_t cvt4_e4m3(const float* f) {
+  uint32_t r;
+  asm("{\n"
+      ".reg .b16 h0, h1;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 h0, %2, %1;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 h1, %4, %3;\n"
+      "mov.b32 %0, {h0, h1};\n"
+      "}"
+      : "=r"(r)
+      : "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]));
+  return r;
 }
 
-// four 6-bit codes (c0|c1<<8 in h01, c2|c3<<8 in h23) -> 24 bits, little-endian bit-contiguous (reorder.cu:54-63)
-__device__ __forceinline__ uint32_t pack4_fp6(uint32_t h01, uint32_t h23) {
-  return (h01 & 0x3fu) | ((h01 >> 2) & 0xfc0u) | ((h23 & 0x3fu) << 12) | ((h23 & 0x3f00u) << 10);
+// four 6-bit codes, one per byte -> 24 bits, little-endian bit-contiguous (reorder.cu:54-63): c0 | c1<<6 | c2<<12 | c3<<18
+__device__ __forceinline__ uint32_t squeeze4_fp6(uint32_t w) {
+  const uint32_t a = w & 0x00ff00ffu;          // c0, c2
+  const uint32_t b = (w >> 8) & 0x00ff00ffu;   // c1, c3
+  const uint32_t x = b * 64u + a;              // [c0 | c1<<6] in bits 0..11, [c2 | c3<<6] in bits 16..27
+  return ((x >> 4) & 0xfffff000u) | (x & 0xfffu);
 }
 
-__device__ __forceinline__ int voff(const QuantParams& p, int c) {
-  int v = 0;
-#pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    int n = min(max(c, 0), p.kseg[s]);
-    v += (n * p.fmt[s]) >> 3;
-    c -= p.kseg[s];
+// One row of a thread's 16 channels: 16 floats -> packed codes -> global memory (8 | 12 | 16 contiguous bytes).
+template <int FMT>
+__device__ __forceinline__ void convert_store_row(const float (&f)[16], uint8_t* dst) {
+  if constexpr (FMT == 4) {
+    stg_v2(dst, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
+  } else if constexpr (FMT == 6) {
+    const uint32_t y0 = squeeze4_fp6(cvt4_e3m2(&f[0])), y1 = squeeze4_fp6(cvt4_e3m2(&f[4]));
+    const uint32_t y2 = squeeze4_fp6(cvt4_e3m2(&f[8])), y3 = squeeze4_fp6(cvt4_e3m2(&f[12]));
+    stg_b32(dst, __byte_perm(y0, y1, 0x4210));
+    stg_b32(dst + 4, __byte_perm(y1, y2, 0x5421));
+    stg_b32(dst + 8, __byte_perm(y2, y3, 0x6542));
+  } else {
+    stg_v4(dst, cvt4_e4m3(&f[0]), cvt4_e4m3(&f[4]), cvt4_e4m3(&f[8]), cvt4_e4m3(&f[12]));
   }
-  return v;
 }
 
-// One pass-step of a thread: 8 permuted channels x R rows -> packed codes in the staging buffer.
-//   g[e][k]   : gathered data, channel e, row pair k (rows 2k | 2k+1 in the low | high half), bf16 bits
-//   mult[k]   : bf16x2 multiplier 2^(127-byte) per row -> x * mult is exact (power of two), so HMUL2.BF16 is bit-safe
+// 16 channels x R rows of one thread: scale (x * 2^-e, exact), convert, pack, store.
+//   g[c][k]  : channel c, row pair k (rows 2k | 2k+1 in the low | high half), bf16 bits
+//   mult[k]  : bf16x2 multiplier 2^(127-byte) per row -> x * mult is exact (power of two), so HMUL2.BF16 is bit-safe
 template <int FMT, int R>
-__device__ __forceinline__ void convert_and_stage(const uint32_t (&g)[8][R / 2], const uint32_t (&mult)[R / 2],
-                                                  uint8_t* dst, int row_stride) {
+__device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], const uint32_t (&mult)[R / 2], uint8_t* dst,
+                                              int64_t row_stride, int nvalid) {
 #pragma unroll
   for (int k = 0; k < R / 2; ++k) {
-    uint32_t h[8];
+    uint32_t h[16];
     const __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&mult[k]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&g[e][k]), m2);
-      h[e] = *reinterpret_cast<const uint32_t*>(&v);
+    for (int c = 0; c < 16; ++c) {
+      const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&g[c][k]), m2);
+      h[c] = *reinterpret_cast<const uint32_t*>(&v);
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      float f[8];
+      const int j = 2 * k + half;
+      float f[16];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(half ? (h[e] & 0xffff0000u) : (h[e] << 16));
-      uint8_t* d = dst + (2 * k + half) * row_stride;
-      if constexpr (FMT == 4) {
-        *reinterpret_cast<uint32_t*>(d) = cvt8_e2m1(f);
-      } else if constexpr (FMT == 6) {
-        const uint32_t lo = pack4_fp6(cvt2_e3m2(f[0], f[1]), cvt2_e3m2(f[2], f[3]));
-        const uint32_t hi = pack4_fp6(cvt2_e3m2(f[4], f[5]), cvt2_e3m2(f[6], f[7]));
-        uint16_t* d16 = reinterpret_cast<uint16_t*>(d);
-        d16[0] = (uint16_t)lo;
-        d16[1] = (uint16_t)((lo >> 16) | (hi << 8));
-        d16[2] = (uint16_t)(hi >> 8);
-      } else {
-        uint2 o;
-        o.x = cvt2_e4m3(f[0], f[1]) | (cvt2_e4m3(f[2], f[3]) << 16);
-        o.y = cvt2_e4m3(f[4], f[5]) | (cvt2_e4m3(f[6], f[7]) << 16);
-        *reinterpret_cast<uint2*>(d) = o;
-      }
+      for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(half ? (h[c] & 0xffff0000u) : (h[c] << 16));
+      if (j < nvalid) convert_store_row<FMT>(f, dst + j * row_stride);
     }
   }
 }
 
-__device__ __forceinline__ uint2 ld_stream_u64(const void* p) {
-  uint2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint2 lds64(uint32_t a) {
-  uint2 v;
-  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-
-// R rows per item, T threads, NLD = register-prefetch depth (each thread holds NLD x R 8-byte loads of the NEXT item
-// while it computes the current one; needs NLD * T * 4 >= K).
+// R rows per item, T threads, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), WIDE = table offsets in
+// 4-byte units (K * 2R > 65536).
 //
-// Shared memory: idx_s[K] i16 | tabA[K/8] u32 | tabB[K/16] u32 | tabV[npass+1] u32 | xs | stage | sfs
-//   tabA[o]  per channel octet o: format code (bits 30..31: 0 FP4, 1 FP6, 2 FP8) | byte offset of the octet's packed
-//            codes relative to the start of its pass in the "virtual packed row" (all three segments back to back)
-//   tabB[q]  per 16-byte chunk q of the virtual packed row: segment (bits 28..29) | byte offset inside that segment's row
-//   tabV[ps] first 16-byte chunk of pass ps (tabV[npass] = total chunks)
-// The tables are built once per CTA, so the per-item / per-pass code does no segment bookkeeping at all.
-template <int R, int T, int NLD, int MINB>
+// Shared memory: tab[K] u16 | xs[K] slots of 2R bytes
+//   tab[c]  byte offset (WIDE: /4) inside xs of the slot of ORIGINAL channel c, i.e. of permuted position j with
+//           idx[j] == c, after the chunk swizzle.  Built once per CTA.
+//   xs      slot j holds the R rows of permuted channel j; 16-byte chunk p = j * 2R / 16 is stored at chunk
+//           p ^ ((p >> 3) & SWM) so that the lane-strided 128-bit reads of the compute phase are conflict-free.
+template <int R, int T, int NLD, int MINB, bool WIDE>
 __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
-  constexpr int HS = 4 / R;        // items per (128-row block, lane row l)
-  constexpr int RW = R / 2;        // 32-bit words per gathered channel (two rows per word)
-  constexpr int PASS_CH = 8 * T;   // channels per pass
-  constexpr int TPR = T / R;       // copy-out threads per row
-  extern __shared__ __align__(16) uint8_t smem[];
+  constexpr int HS = 4 / R;          // items per (128-row block, lane row l)
+  constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
+  constexpr int SLOT = 2 * R;        // bytes per slot
+  constexpr int CPT = SLOT;          // 16-byte chunks holding a thread's 16 channels: 8 (R=4) | 4 (R=2)
+  constexpr uint32_t SWM = (R == 4) ? 7u : 3u;
+  extern __shared__ __align__(128) uint8_t smem[];
   const int K = p.K;
-  const int npass = (K + PASS_CH - 1) / PASS_CH;
-  int16_t* idx_s = reinterpret_cast<int16_t*>(smem);
-  uint32_t* tabA = reinterpret_cast<uint32_t*>(smem + ((K * 2 + 15) & ~15));
-  uint32_t* tabB = tabA + K / 8;
-  uint32_t* tabV = tabB + K / 16;
-  uint8_t* xs = reinterpret_cast<uint8_t*>(tabV) + 64;
-  uint8_t* stage = xs + (size_t)K * R * 2;
-  uint8_t* sfs = stage + 2 * R * PASS_CH;
+  const int K8 = K >> 3;
+  const int nunits = K >> 4;
+  uint16_t* tab = reinterpret_cast<uint16_t*>(smem);
+  uint8_t* xs = smem + ((K * 2 + 127) & ~127);
   const uint32_t xs_a = smem_addr(xs);
   const int t = threadIdx.x;
-  const int K4 = K >> 2;
 
-  // ---- one-time per CTA: permutation and lookup tables
-  for (int i = t; i < K / 8; i += T) reinterpret_cast<uint4*>(idx_s)[i] = reinterpret_cast<const uint4*>(p.idx)[i];
-  for (int o = t; o < K / 8; o += T) {
-    const int c = o * 8;
-    const int sg = (c >= p.cend[1]) ? 2 : (c >= p.cend[0] ? 1 : 0);
-    const int C0 = (c / PASS_CH) * PASS_CH;
-    tabA[o] = ((uint32_t)((p.fmt[sg] - 4) >> 1) << 30) | (uint32_t)(voff(p, c) - voff(p, C0));  // 4|6|8 bits -> 0|1|2
+  // ---- one-time per CTA: inverse permutation as swizzled slot offsets
+  for (int j = t; j < K; j += T) {
+    const uint32_t c = (uint16_t)p.idx[j];
+    const uint32_t pc = ((uint32_t)j * SLOT) >> 4;                               // 16-byte chunk of slot j
+    const uint32_t off = ((pc ^ ((pc >> 3) & SWM)) << 4) | (((uint32_t)j * SLOT) & 15u);
+    tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
   }
-  for (int q = t; q < p.vend[2] / 16; q += T) {
-    const int v = q * 16;
-    const int sg = (v >= p.vend[1]) ? 2 : (v >= p.vend[0] ? 1 : 0);
-    tabB[q] = ((uint32_t)sg << 28) | (uint32_t)(v - (sg ? p.vend[sg - 1] : 0));
-  }
-  if (t <= npass) tabV[t] = (uint32_t)(voff(p, min(t * PASS_CH, K)) >> 4);
-  // (the first __syncthreads of the item loop publishes the tables)
+  // (the first __syncthreads of the item loop would be too late: the scatter below reads tab)
+  __syncthreads();
 
-  uint2 pre[NLD][R];  // prefetched rows of the next item
+  uint4 pre[NLD][R];  // prefetched rows of the next item
 
-  // item -> first row (the other R-1 rows follow at +32 each), all in 32-bit arithmetic
+  // item -> first row (the other R-1 rows follow at +32 each)
   auto item_row0 = [&](int item, int& l, int& h, int& rb) -> int {
     l = item & 31;
     const int it2 = item >> 5;
@@ -216,20 +223,21 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
     int l, h, rb;
     const int row0 = item_row0(item, l, h, rb);
     if (row0 >= (int)p.rows) return;  // block-uniform: nothing to fetch for an item past the last row
-    const uint16_t* b0 = p.x + (int64_t)row0 * K + 4 * t;
-    const int64_t rstride = (int64_t)32 * K;
     const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
+    const uint16_t* b[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j)  // rows past the end re-read row0; they are zeroed when stored to shared memory
+      b[j] = p.x + ((int64_t)row0 + (j < nvalid ? 32 * j : 0)) * K + 8 * t;
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
-      if (i * T + t < K4) {
+      if (i * T + t < K8) {
 #pragma unroll
-        for (int j = 0; j < R; ++j)  // rows past the end re-read row0; they are zeroed when stored to shared memory
-          pre[i][j] = ld_stream_u64(b0 + (j < nvalid ? j * rstride : 0) + (size_t)i * T * 4);
+        for (int j = 0; j < R; ++j) pre[i][j] = ld_stream_v4(b[j] + (size_t)i * T * 8);
       }
     }
   };
 
-  const int num_items = (int)p.num_items;
+  const int num_items = p.num_items;
   int item = blockIdx.x;
   if (item < num_items) prefetch(item);
 
@@ -239,162 +247,130 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
     if (row0 >= (int)p.rows) break;  // block-uniform; items are ordered by row, nothing valid follows for this CTA
     const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
 
-    // ---- prefetched registers -> shared memory, channel-major / row-interleaved
+    // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
-      const int c4 = i * T + t;
-      if (c4 < K4) {
-        uint2 w[R];
+      const int c8 = i * T + t;
+      if (c8 < K8) {
+        const uint4 ov = *reinterpret_cast<const uint4*>(tab + 8 * c8);
+        const uint32_t o[4] = {ov.x, ov.y, ov.z, ov.w};
+        uint32_t w[R][4];
 #pragma unroll
-        for (int j = 0; j < R; ++j) w[j] = pre[i][j];
+        for (int j = 0; j < R; ++j) {
+          w[j][0] = pre[i][j].x;
+          w[j][1] = pre[i][j].y;
+          w[j][2] = pre[i][j].z;
+          w[j][3] = pre[i][j].w;
+        }
         if (nvalid < R) {  // block-uniform; only the last, partly filled row block takes this path
 #pragma unroll
           for (int j = 1; j < R; ++j)
-            if (j >= nvalid) w[j] = make_uint2(0u, 0u);
+            if (j >= nvalid) w[j][0] = w[j][1] = w[j][2] = w[j][3] = 0u;
         }
-        if constexpr (R == 4) {
-          uint4 o0, o1;
-          o0.x = __byte_perm(w[0].x, w[1].x, 0x5410);
-          o0.y = __byte_perm(w[2].x, w[3].x, 0x5410);
-          o0.z = __byte_perm(w[0].x, w[1].x, 0x7632);
-          o0.w = __byte_perm(w[2].x, w[3].x, 0x7632);
-          o1.x = __byte_perm(w[0].y, w[1].y, 0x5410);
-          o1.y = __byte_perm(w[2].y, w[3].y, 0x5410);
-          o1.z = __byte_perm(w[0].y, w[1].y, 0x7632);
-          o1.w = __byte_perm(w[2].y, w[3].y, 0x7632);
-          uint4* d = reinterpret_cast<uint4*>(xs + (size_t)c4 * 32);
-          d[0] = o0;
-          d[1] = o1;
-        } else {
-          uint4 o;
-          o.x = __byte_perm(w[0].x, w[1].x, 0x5410);
-          o.y = __byte_perm(w[0].x, w[1].x, 0x7632);
-          o.z = __byte_perm(w[0].y, w[1].y, 0x5410);
-          o.w = __byte_perm(w[0].y, w[1].y, 0x7632);
-          *reinterpret_cast<uint4*>(xs + (size_t)c4 * 16) = o;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {  // channels 8*c8 + 2m (low halves) and + 2m+1 (high halves)
+          const uint32_t a_lo = xs_a + (WIDE ? ((o[m] & 0xffffu) << 2) : (o[m] & 0xffffu));
+          const uint32_t a_hi = xs_a + (WIDE ? ((o[m] >> 16) << 2) : (o[m] >> 16));
+          if constexpr (R == 4) {
+            sts64(a_lo, __byte_perm(w[0][m], w[1][m], 0x5410), __byte_perm(w[2][m], w[3][m], 0x5410));
+            sts64(a_hi, __byte_perm(w[0][m], w[1][m], 0x7632), __byte_perm(w[2][m], w[3][m], 0x7632));
+          } else {
+            sts32(a_lo, __byte_perm(w[0][m], w[1][m], 0x5410));
+            sts32(a_hi, __byte_perm(w[0][m], w[1][m], 0x7632));
+          }
         }
       }
     }
     __syncthreads();
     if (item + (int)gridDim.x < num_items) prefetch(item + (int)gridDim.x);  // in flight during the compute below
 
-    // this thread's copy-out row and its three destination row pointers
-    const int jrow = t / TPR;
-    const bool jvalid = jrow < nvalid;
-    const int64_t rj = (int64_t)row0 + 32 * jrow;
-    uint8_t* const d0 = p.q[0] + rj * p.rowbytes[0];
-    uint8_t* const d1 = p.q[1] + rj * p.rowbytes[1];
-    uint8_t* const d2 = p.q[2] + rj * p.rowbytes[2];
-
-    for (int ps = 0; ps < npass; ++ps) {
-      const int oct = ps * T + t;
-      const bool active = oct * 8 < K;
-      const int oc = active ? oct : 0;
-      const uint32_t ta = tabA[oc];
-      const uint32_t fmtc = ta >> 30;
-      uint8_t* stagebuf = stage + (ps & 1) * (R * PASS_CH);
-
-      // ---- gather 8 permuted channels x R rows
-      const uint4 iv = *reinterpret_cast<const uint4*>(idx_s + oc * 8);
-      const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
-      uint32_t g[8][RW];
+    // ---- compute: thread owns permuted channels [16u, 16u+16) of all R rows.  The loop is warp-uniform (full-mask
+    // shuffles inside); lanes past the last unit compute on unit 0 and store nothing.
+    for (int ub = 0; ub < nunits; ub += T) {
+      const bool active = ub + t < nunits;
+      const int u = active ? ub + t : 0;
+      const int nstore = active ? nvalid : 0;
+      const int c0 = u << 4;
+      const int sg = (c0 >= p.cend[1]) ? 2 : (c0 >= p.cend[0] ? 1 : 0);
+      const int fmt = p.fmt[sg];
+      const uint32_t p0 = (uint32_t)u * CPT;
+      const uint32_t base = xs_a + ((p0 ^ ((p0 >> 3) & SWM)) << 4);
+      uint32_t g[16][RW];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t ch = (e & 1) ? (ivw[e >> 1] >> 16) : (ivw[e >> 1] & 0xffffu);
+      for (int e = 0; e < CPT; ++e) {
+        const uint4 v = lds128(base ^ ((uint32_t)e << 4));
         if constexpr (R == 4) {
-          const uint2 v = lds64(xs_a + ch * 8);
-          g[e][0] = v.x;
-          g[e][1] = v.y;
+          g[2 * e][0] = v.x;
+          g[2 * e][1] = v.y;
+          g[2 * e + 1][0] = v.z;
+          g[2 * e + 1][1] = v.w;
         } else {
-          g[e][0] = lds32(xs_a + ch * 4);
+          g[4 * e][0] = v.x;
+          g[4 * e + 1][0] = v.y;
+          g[4 * e + 2][0] = v.z;
+          g[4 * e + 3][0] = v.w;
         }
       }
 
-      // ---- absmax per row over the 32-group (8 local channels, then the 4 lanes of the team), scale byte, multiplier
-      const uint32_t q2 = (fmtc == 0) ? 0x00020002u : ((fmtc == 1) ? 0x00040004u : 0x00080008u);  // log2floor(QMAX)
-      const uint32_t add2 = (fmtc == 0) ? (63u * 0x00010001u) : (31u * 0x00010001u);            // 127 - thr, thr = 64 | 96
+      // ---- absmax per row over the 32-group (16 local channels + the partner lane), scale byte, multiplier
+      const uint32_t q2 = (fmt == 4) ? 0x00020002u : ((fmt == 6) ? 0x00040004u : 0x00080008u);  // log2floor(QMAX)
+      const uint32_t add2 = (fmt == 4) ? (63u * 0x00010001u) : (31u * 0x00010001u);             // 127 - thr, thr = 64 | 96
       uint32_t mult[RW];
       uint32_t sfb[RW];
 #pragma unroll
       for (int k = 0; k < RW; ++k) {
-        uint32_t u = g[0][k] & 0x7fff7fffu;
+        uint32_t m = absmax2(g[0][k], g[1][k]);
 #pragma unroll
-        for (int e = 1; e < 8; ++e) u = __vmaxu2(u, g[e][k] & 0x7fff7fffu);  // |bf16| orders like u16
-        u = __vmaxu2(u, __shfl_xor_sync(0xffffffffu, u, 1));
-        u = __vmaxu2(u, __shfl_xor_sync(0xffffffffu, u, 2));
+        for (int c = 2; c < 16; ++c) m = absmax2(m, g[c][k]);
+        m = absmax2(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        const uint32_t a = m & 0x7fff7fffu;  // |bf16| bits of the group's absmax, two rows
         // byte = max(exp - qexp, 0) + (mant > thr), both rows of the pair at once; 0x7E for an all-zero group
-        const uint32_t ex2 = (u >> 7) & 0x00ff00ffu;
-        const uint32_t gt2 = (((u & 0x007f007fu) + add2) >> 7) & 0x00010001u;
+        const uint32_t ex2 = (a >> 7) & 0x00ff00ffu;
+        const uint32_t gt2 = (((a & 0x007f007fu) + add2) >> 7) & 0x00010001u;
         const uint32_t b2 = __vmaxu2(ex2, q2) - q2 + gt2;
         mult[k] = (0x00fe00feu - b2) << 7;  // bf16x2 of 2^(127-byte)
-        const uint32_t z = __vcmpeq2(u, 0u);
+        const uint32_t z = __vcmpeq2(a, 0u);
         sfb[k] = (b2 & ~z) | (0x007e007eu & z);
       }
 
-      if (active) {
-        uint8_t* dst = stagebuf + (ta & 0x3fffffffu);
-        if (fmtc == 0) convert_and_stage<4, R>(g, mult, dst, PASS_CH);
-        else if (fmtc == 1) convert_and_stage<6, R>(g, mult, dst, PASS_CH);
-        else convert_and_stage<8, R>(g, mult, dst, PASS_CH);
-        if ((t & 3) == 0) {
-          const int G = oct >> 2;  // 32-channel group index
-          uint8_t* d = sfs + (G >> 2) * 16 + (R * h) * 4 + (G & 3);
-#pragma unroll
-          for (int k = 0; k < RW; ++k) {
-            d[8 * k] = (uint8_t)sfb[k];
-            d[8 * k + 4] = (uint8_t)(sfb[k] >> 16);
-          }
-        }
-      }
-      __syncthreads();
-
-      // ---- coalesced 16-byte copy-out of this pass' packed codes: T/R threads per row
-      if (jvalid) {
-        const int q0 = (int)tabV[ps];
-        const int n16 = (int)tabV[ps + 1] - q0;
-        const uint8_t* src = stagebuf + jrow * PASS_CH;
-        for (int ch = t - jrow * TPR; ch < n16; ch += TPR) {
-          const uint32_t tb = tabB[q0 + ch];
-          const uint32_t sg = tb >> 28;
-          uint8_t* d = (sg == 0) ? d0 : ((sg == 1) ? d1 : d2);
-          st_stream_v4(d + (tb & 0x0fffffffu), *reinterpret_cast<const uint4*>(src + 16 * ch));
-        }
-      }
-    }
-
-    // ---- scale factors: one 16-byte (R=4) / 8-byte (R=2) store per 128 channels
-    for (int ch = t; ch < K / 128; ch += T) {
-      const int c = ch * 128;
-      const int sg = (c >= p.cend[1]) ? 2 : (c >= p.cend[0] ? 1 : 0);
+      // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row)
       const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
-      const int ka = (c - cb) >> 7;
-      uint8_t* dst = p.sf[sg] + ((int64_t)rb * p.katoms[sg] + ka) * 512 + l * 16;
-      if constexpr (R == 4) {
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(sfs + ch * 16);
-      } else {
-        *reinterpret_cast<uint2*>(dst + 8 * h) = *reinterpret_cast<const uint2*>(sfs + ch * 16 + 8 * h);
+      if (active && (u & 1) == 0) {
+        const int G = (c0 - cb) >> 5;  // 32-channel group inside the segment
+        uint8_t* d = p.sf[sg] + ((int64_t)rb * p.katoms[sg] + (G >> 2)) * 512 + l * 16 + (R * h) * 4 + (G & 3);
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+          d[8 * k] = (uint8_t)sfb[k];
+          d[8 * k + 4] = (uint8_t)(sfb[k] >> 16);
+        }
       }
+
+      // ---- convert + store: 16 codes per row, contiguous bytes
+      const int64_t rbytes = p.rowbytes[sg];
+      uint8_t* dst = p.q[sg] + (int64_t)row0 * rbytes + (((c0 - cb) * fmt) >> 3);
+      const int64_t rstride = 32 * rbytes;
+      if (fmt == 4) convert_store<4, R>(g, mult, dst, rstride, nstore);
+      else if (fmt == 6) convert_store<6, R>(g, mult, dst, rstride, nstore);
+      else convert_store<8, R>(g, mult, dst, rstride, nstore);
     }
-    // the next item's __syncthreads (after its xs stores) orders these reads before sfs/stage reuse; xs itself is
-    // only rewritten after the last pass' barrier, i.e. after every gather of this item
+    __syncthreads();  // every read of xs is done before the next item's scatter overwrites it
   }
 }
 
-template <int R, int T>
+template <int R>
 static size_t quant_smem_bytes(int K) {
-  return ((size_t)(K * 2 + 15) & ~(size_t)15) + (size_t)(K / 8) * 4 + (size_t)(K / 16) * 4 + 64 /*tabV*/ +
-         (size_t)K * R * 2 + (size_t)2 * R * 8 * T + (size_t)(K / 128) * 16;
+  return ((size_t)(K * 2 + 127) & ~(size_t)127) + (size_t)K * 2 * R;
 }
 
-template <int R, int T, int NLD, int MINB>
-static int launch_quant(const QuantParams& p, cudaStream_t stream) {
-  const size_t smem = quant_smem_bytes<R, T>(p.K);
-  if (smem > 227 * 1024 || (int64_t)NLD * T * 4 < p.K) {
+template <int R, int T, int NLD, int MINB, bool WIDE>
+static int launch_quant(QuantParams& p, cudaStream_t stream) {
+  const size_t smem = quant_smem_bytes<R>(p.K);
+  if (smem > 227 * 1024 || (int64_t)NLD * T * 8 < p.K || (!WIDE && (int64_t)p.K * 2 * R > 65536)) {
     set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, T, NLD,
               smem);
     return MMX_ERR_INVALID;
   }
-  auto kern = reorder_quantize_kernel<R, T, NLD, MINB>;
+  auto kern = reorder_quantize_kernel<R, T, NLD, MINB, WIDE>;
   static size_t attr_set = 0;
   if (smem > attr_set) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -403,8 +379,15 @@ static int launch_quant(const QuantParams& p, cudaStream_t stream) {
   int occ = 0;
   MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
   if (occ < 1) occ = 1;
+  const int64_t rblocks = (p.rows + 127) / 128;
+  const int64_t items = rblocks * 32 * (4 / R);
+  p.num_items = (int)items;
+  // equal shares: with `per` items per CTA, ceil(items / per) CTAs all run the same number of rounds
   int64_t grid = (int64_t)sm_count() * occ;
-  if (grid > p.num_items) grid = p.num_items;
+  if (options().quant_ctas > 0) grid = options().quant_ctas;
+  if (grid > items) grid = items;
+  const int64_t per = (items + grid - 1) / grid;
+  grid = (items + per - 1) / per;
   if (grid < 1) return MMX_OK;
   kern<<<(unsigned)grid, T, smem, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -425,6 +408,10 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   }
   if (K > 32767) {
     set_error("reorder_quantize: K=%d exceeds the int16 reorder_index range", K);
+    return MMX_ERR_INVALID;
+  }
+  if (rows > (int64_t)1 << 24) {
+    set_error("reorder_quantize: rows=%lld exceeds the supported 2^24", (long long)rows);
     return MMX_ERR_INVALID;
   }
   uint8_t* q[3] = {q0, q1, q2};
@@ -450,35 +437,27 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   p.idx = idx;
   p.rows = rows;
   p.K = K;
-  int cacc = 0, vacc = 0;
+  int cacc = 0;
   for (int i = 0; i < 3; ++i) {
-    p.kseg[i] = ks[i];
     p.fmt[i] = fmt[i];
     cacc += ks[i];
-    vacc += ks[i] * fmt[i] / 8;
     p.cend[i] = cacc;
-    p.vend[i] = vacc;
     p.katoms[i] = ks[i] / 128;
     p.rowbytes[i] = (int64_t)ks[i] * fmt[i] / 8;
     p.q[i] = q[i];
     p.sf[i] = s[i];
   }
-  const int64_t rblocks = (rows + 127) / 128;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int force = (int)options().quant_rows;
-  // configuration by K: rows per item R, threads T, prefetch depth NLD (NLD*T*4 >= K); smem grows with K*R
-  if (force != 2 && K <= 4096) {
-    p.num_items = rblocks * 32;
-    return launch_quant<4, 256, 4, 3>(p, st);
+  // configuration by K: rows per item R, threads T, 16-byte chunks per thread and row NLD (NLD*T*8 >= K)
+  if (force != 2) {
+    if (K <= 2048) return launch_quant<4, 128, 2, 6, false>(p, st);
+    if (K <= 4096) return launch_quant<4, 256, 2, 3, false>(p, st);
+    if (K <= 8192) return launch_quant<4, 512, 2, 2, false>(p, st);
   }
-  if (force != 2 && K <= 8192) {
-    p.num_items = rblocks * 32;
-    return launch_quant<4, 512, 4, 2>(p, st);
-  }
-  p.num_items = rblocks * 64;
-  if (K <= 4096) return launch_quant<2, 256, 4, 4>(p, st);
-  if (K <= 16384) return launch_quant<2, 512, 8, 2>(p, st);
-  return launch_quant<2, 512, 16, 1>(p, st);
+  if (K <= 4096) return launch_quant<2, 256, 2, 4, false>(p, st);
+  if (K <= 16384) return launch_quant<2, 512, 4, 2, false>(p, st);
+  return launch_quant<2, 1024, 4, 1, true>(p, st);
 }
 
 }  // namespace mmx
