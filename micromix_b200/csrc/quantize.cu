@@ -36,6 +36,7 @@ struct QuantParams {
   int64_t rows;
   int num_items;
   int K;
+  unsigned int* sched;  // {next dynamic item, finished CTAs}: both zero at launch, reset by the last CTA to finish
   int fmt[3];       // bits per code: 4 | 6 | 8
   int cend[3];      // cumulative channel ends
   int katoms[3];    // kseg / 128
@@ -151,9 +152,10 @@ __device__ __forceinline__ void convert_store_row(const float (&f)[16], uint8_t*
 // 16 channels x R rows of one thread: scale (x * 2^-e, exact), convert, pack, store.
 //   g[c][k]  : channel c, row pair k (rows 2k | 2k+1 in the low | high half), bf16 bits
 //   mult[k]  : bf16x2 multiplier 2^(127-byte) per row -> x * mult is exact (power of two), so HMUL2.BF16 is bit-safe
-template <int FMT, int R>
+//   dst      : first row's destination; row j lives at dst + j * row_stride; rows >= nstore are not stored
+template <int FMT, int R, bool FULL>
 __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], const uint32_t (&mult)[R / 2], uint8_t* dst,
-                                              int64_t row_stride, int nvalid) {
+                                              int64_t row_stride, int nstore) {
 #pragma unroll
   for (int k = 0; k < R / 2; ++k) {
     uint32_t h[16];
@@ -165,88 +167,54 @@ __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], co
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const int j = 2 * k + half;
       float f[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(half ? (h[c] & 0xffff0000u) : (h[c] << 16));
-      if (j < nvalid) convert_store_row<FMT>(f, dst + j * row_stride);
+      if (FULL || 2 * k + half < nstore) convert_store_row<FMT>(f, dst);
+      dst += row_stride;
     }
   }
 }
 
-// R rows per item, T threads, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), WIDE = table offsets in
-// 4-byte units (K * 2R > 65536).
+// R rows per item, T threads, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), NP = compute passes
+// (NP * T * 16 >= K), WIDE = table offsets in 4-byte units (K * 2R > 65536).
 //
 // Shared memory: tab[K] u16 | xs[K] slots of 2R bytes
 //   tab[c]  byte offset (WIDE: /4) inside xs of the slot of ORIGINAL channel c, i.e. of permuted position j with
 //           idx[j] == c, after the chunk swizzle.  Built once per CTA.
 //   xs      slot j holds the R rows of permuted channel j; 16-byte chunk p = j * 2R / 16 is stored at chunk
 //           p ^ ((p >> 3) & SWM) so that the lane-strided 128-bit reads of the compute phase are conflict-free.
-template <int R, int T, int NLD, int MINB, bool WIDE>
-__global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
-  static_assert(R == 4 || R == 2, "rows per item");
-  constexpr int HS = 4 / R;          // items per (128-row block, lane row l)
-  constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
-  constexpr int SLOT = 2 * R;        // bytes per slot
-  constexpr int CPT = SLOT;          // 16-byte chunks holding a thread's 16 channels: 8 (R=4) | 4 (R=2)
-  constexpr uint32_t SWM = (R == 4) ? 7u : 3u;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int K = p.K;
-  const int K8 = K >> 3;
-  const int nunits = K >> 4;
-  uint16_t* tab = reinterpret_cast<uint16_t*>(smem);
-  uint8_t* xs = smem + ((K * 2 + 127) & ~127);
-  const uint32_t xs_a = smem_addr(xs);
-  const int t = threadIdx.x;
+template <int R, int NLD, int NP, bool WIDE>
+struct QuantKernel {
+  static constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
+  static constexpr int SLOT = 2 * R;        // bytes per slot
+  static constexpr int CPT = SLOT;          // 16-byte chunks holding a thread's 16 channels: 8 (R=4) | 4 (R=2)
+  static constexpr uint32_t SWM = (R == 4) ? 7u : 3u;
 
-  // ---- one-time per CTA: inverse permutation as swizzled slot offsets
-  for (int j = t; j < K; j += T) {
-    const uint32_t c = (uint16_t)p.idx[j];
-    const uint32_t pc = ((uint32_t)j * SLOT) >> 4;                               // 16-byte chunk of slot j
-    const uint32_t off = ((pc ^ ((pc >> 3) & SWM)) << 4) | (((uint32_t)j * SLOT) & 15u);
-    tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
-  }
-  // (the first __syncthreads of the item loop would be too late: the scatter below reads tab)
-  __syncthreads();
+  // item -> first row: 32 consecutive items share a block of 32R rows, item i takes rows row0 + 32j, j < R
+  static __device__ __forceinline__ int item_row0(int item) { return (item >> 5) * (32 * R) + (item & 31); }
 
-  uint4 pre[NLD][R];  // prefetched rows of the next item
-
-  // item -> first row (the other R-1 rows follow at +32 each)
-  auto item_row0 = [&](int item, int& l, int& h, int& rb) -> int {
-    l = item & 31;
-    const int it2 = item >> 5;
-    h = it2 % HS;
-    rb = it2 / HS;
-    return rb * 128 + l + 32 * (R * h);
-  };
-  auto prefetch = [&](int item) {
-    int l, h, rb;
-    const int row0 = item_row0(item, l, h, rb);
-    if (row0 >= (int)p.rows) return;  // block-uniform: nothing to fetch for an item past the last row
-    const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
-    const uint16_t* b[R];
+  template <bool FULL>
+  static __device__ __forceinline__ void prefetch(const QuantParams& p, int row0, int t, int T, int K8,
+                                                  uint4 (&pre)[NLD][R]) {
+    const int K = p.K;
+    const uint16_t* b0 = p.x + (int64_t)row0 * K + 8 * t;
+    const int64_t rs = (int64_t)32 * K;  // elements between two rows of the item
+    const int nvalid = FULL ? R : min(R, ((int)p.rows - 1 - row0) / 32 + 1);
 #pragma unroll
-    for (int j = 0; j < R; ++j)  // rows past the end re-read row0; they are zeroed when stored to shared memory
-      b[j] = p.x + ((int64_t)row0 + (j < nvalid ? 32 * j : 0)) * K + 8 * t;
+    for (int j = 0; j < R; ++j) {
+      // rows past the end re-read row0; they are zeroed when stored to shared memory
+      const uint16_t* bj = (FULL || j < nvalid) ? b0 + j * rs : b0;
 #pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-      if (i * T + t < K8) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) pre[i][j] = ld_stream_v4(b[j] + (size_t)i * T * 8);
-      }
+      for (int i = 0; i < NLD; ++i)
+        if (i * T + t < K8) pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
     }
-  };
+  }
 
-  const int num_items = p.num_items;
-  int item = blockIdx.x;
-  if (item < num_items) prefetch(item);
-
-  for (; item < num_items; item += gridDim.x) {
-    int l, h, rb;
-    const int row0 = item_row0(item, l, h, rb);
-    if (row0 >= (int)p.rows) break;  // block-uniform; items are ordered by row, nothing valid follows for this CTA
-    const int nvalid = min(R, ((int)p.rows - 1 - row0) / 32 + 1);
-
+  template <bool FULL>
+  static __device__ __forceinline__ void process(const QuantParams& p, int row0, int t, int T, int K8, int nunits, uint32_t xs_a,
+                                                 const uint16_t* tab, uint4 (&pre)[NLD][R], int next_row0, int* s_next) {
+    const int nvalid = FULL ? R : min(R, ((int)p.rows - 1 - row0) / 32 + 1);
     // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
@@ -257,15 +225,11 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
         uint32_t w[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          w[j][0] = pre[i][j].x;
-          w[j][1] = pre[i][j].y;
-          w[j][2] = pre[i][j].z;
-          w[j][3] = pre[i][j].w;
-        }
-        if (nvalid < R) {  // block-uniform; only the last, partly filled row block takes this path
-#pragma unroll
-          for (int j = 1; j < R; ++j)
-            if (j >= nvalid) w[j][0] = w[j][1] = w[j][2] = w[j][3] = 0u;
+          const bool keep = FULL || j < nvalid;
+          w[j][0] = keep ? pre[i][j].x : 0u;
+          w[j][1] = keep ? pre[i][j].y : 0u;
+          w[j][2] = keep ? pre[i][j].z : 0u;
+          w[j][3] = keep ? pre[i][j].w : 0u;
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {  // channels 8*c8 + 2m (low halves) and + 2m+1 (high halves)
@@ -282,14 +246,26 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       }
     }
     __syncthreads();
-    if (item + (int)gridDim.x < num_items) prefetch(item + (int)gridDim.x);  // in flight during the compute below
+    // the next item's rows: in flight during the compute below
+    if (next_row0 >= 0) {
+      if (next_row0 + 32 * (R - 1) < (int)p.rows) prefetch<true>(p, next_row0, t, T, K8, pre);
+      else prefetch<false>(p, next_row0, t, T, K8, pre);
+    }
+
+    // dynamic schedule: claim the item after next now; the answer is only needed one whole item later
+    unsigned int claimed = 0;
+    if (t == 0) claimed = atomicAdd(p.sched, 1u);
 
     // ---- compute: thread owns permuted channels [16u, 16u+16) of all R rows.  The loop is warp-uniform (full-mask
     // shuffles inside); lanes past the last unit compute on unit 0 and store nothing.
-    for (int ub = 0; ub < nunits; ub += T) {
-      const bool active = ub + t < nunits;
-      const int u = active ? ub + t : 0;
-      const int nstore = active ? nvalid : 0;
+    const int l = row0 & 31;
+    const int64_t sfrow = (int64_t)(row0 >> 7) * 512;             // x katoms: the row block's first atom
+    const int sfin = l * 16 + ((row0 >> 5) & 3) * 4;               // byte of (row0, group 0) inside an atom
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps) {
+      if (ps * T >= nunits) break;
+      const bool active = ps * T + t < nunits;
+      const int u = active ? ps * T + t : 0;
       const int c0 = u << 4;
       const int sg = (c0 >= p.cend[1]) ? 2 : (c0 >= p.cend[0] ? 1 : 0);
       const int fmt = p.fmt[sg];
@@ -337,7 +313,7 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
       if (active && (u & 1) == 0) {
         const int G = (c0 - cb) >> 5;  // 32-channel group inside the segment
-        uint8_t* d = p.sf[sg] + ((int64_t)rb * p.katoms[sg] + (G >> 2)) * 512 + l * 16 + (R * h) * 4 + (G & 3);
+        uint8_t* d = p.sf[sg] + sfrow * p.katoms[sg] + ((G >> 2) * 512 + (G & 3) + sfin);
 #pragma unroll
         for (int k = 0; k < RW; ++k) {
           d[8 * k] = (uint8_t)sfb[k];
@@ -349,46 +325,115 @@ __global__ void __launch_bounds__(T, MINB) reorder_quantize_kernel(const __grid_
       const int64_t rbytes = p.rowbytes[sg];
       uint8_t* dst = p.q[sg] + (int64_t)row0 * rbytes + (((c0 - cb) * fmt) >> 3);
       const int64_t rstride = 32 * rbytes;
-      if (fmt == 4) convert_store<4, R>(g, mult, dst, rstride, nstore);
-      else if (fmt == 6) convert_store<6, R>(g, mult, dst, rstride, nstore);
-      else convert_store<8, R>(g, mult, dst, rstride, nstore);
+      const int nstore = active ? nvalid : 0;
+      if (FULL && !active) {
+      } else if (fmt == 4) convert_store<4, R, FULL>(g, mult, dst, rstride, nstore);
+      else if (fmt == 6) convert_store<6, R, FULL>(g, mult, dst, rstride, nstore);
+      else convert_store<8, R, FULL>(g, mult, dst, rstride, nstore);
     }
-    __syncthreads();  // every read of xs is done before the next item's scatter overwrites it
+    if (t == 0) *s_next = (int)(claimed + 2u * gridDim.x);
+    __syncthreads();  // every read of xs is done before the next item's scatter overwrites it; publishes *s_next
+  }
+};
+
+template <int R, int TMAX, int NLD, int NP, int MINB, bool WIDE>
+__global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
+  static_assert(R == 4 || R == 2, "rows per item");
+  using QK = QuantKernel<R, NLD, NP, WIDE>;
+  const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int K = p.K;
+  const int K8 = K >> 3;
+  const int nunits = K >> 4;
+  uint16_t* tab = reinterpret_cast<uint16_t*>(smem);
+  uint8_t* xs = smem + ((K * 2 + 127) & ~127);
+  const uint32_t xs_a = smem_addr(xs);
+  const int t = threadIdx.x;
+  const int rows = (int)p.rows;
+
+  uint4 pre[NLD][R];  // prefetched rows of the next item
+  __shared__ int s_next;
+  const int num_items = p.num_items;
+  // schedule: the first two rounds are static (item = blockIdx.x, blockIdx.x + gridDim.x), later items are claimed
+  // from a global counter one item ahead of their prefetch, so SMs that run ahead simply take more items
+  int item = blockIdx.x;
+  int row0 = item < num_items ? QK::item_row0(item) : rows;
+  if (row0 < rows) {  // first loads go out before the table is built
+    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true>(p, row0, t, T, K8, pre);
+    else QK::template prefetch<false>(p, row0, t, T, K8, pre);
+  }
+
+  // ---- one-time per CTA: inverse permutation as swizzled slot offsets
+  for (int j = t; j < K; j += T) {
+    const uint32_t c = (uint16_t)p.idx[j];
+    const uint32_t pc = ((uint32_t)j * QK::SLOT) >> 4;  // 16-byte chunk of slot j
+    const uint32_t off = ((pc ^ ((pc >> 3) & QK::SWM)) << 4) | (((uint32_t)j * QK::SLOT) & 15u);
+    tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
+  }
+  __syncthreads();
+
+  // items are ordered by row: the first item past the last row ends this CTA's work (block-uniform)
+  int nitem = item + (int)gridDim.x;
+  while (row0 < rows) {
+    int nrow0 = nitem < num_items ? QK::item_row0(nitem) : rows;
+    if (nrow0 >= rows) nrow0 = -1;
+    if (row0 + 32 * (R - 1) < rows) QK::template process<true>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next);
+    else QK::template process<false>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next);
+    if (nrow0 < 0) break;
+    row0 = nrow0;
+    nitem = s_next;
+  }
+  // the last CTA to leave resets the schedule for the next launch that uses this slot
+  if (t == 0) {
+    const unsigned int done = atomicInc(p.sched + 1, gridDim.x - 1);  // wraps to 0 by itself
+    if (done == gridDim.x - 1) atomicExch(p.sched, 0u);
   }
 }
+
+__device__ unsigned int g_quant_sched[64][2];  // rotating schedule slots (zero-initialised, self-resetting)
 
 template <int R>
 static size_t quant_smem_bytes(int K) {
   return ((size_t)(K * 2 + 127) & ~(size_t)127) + (size_t)K * 2 * R;
 }
 
-template <int R, int T, int NLD, int MINB, bool WIDE>
+template <int R, int TMAX, int NLD, int NP, int MINB, bool WIDE>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
   const size_t smem = quant_smem_bytes<R>(p.K);
-  if (smem > 227 * 1024 || (int64_t)NLD * T * 8 < p.K || (!WIDE && (int64_t)p.K * 2 * R > 65536)) {
-    set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, T, NLD,
-              smem);
+  // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
+  const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
+  if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (!WIDE && (int64_t)p.K * 2 * R > 65536)) {
+    set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, TMAX,
+              NLD, NP, smem);
     return MMX_ERR_INVALID;
   }
-  auto kern = reorder_quantize_kernel<R, T, NLD, MINB, WIDE>;
+  auto kern = reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, WIDE>;
   static size_t attr_set = 0;
   if (smem > attr_set) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
   }
-  int occ = 0;
-  MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
-  if (occ < 1) occ = 1;
+  static int occ_cached = 0;
+  static size_t occ_smem = 0;
+  static int occ_T = 0;
+  if (occ_cached == 0 || occ_smem != smem || occ_T != T) {
+    occ_T = T;
+    int occ = 0;
+    MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+    occ_cached = occ < 1 ? 1 : occ;
+    occ_smem = smem;
+  }
   const int64_t rblocks = (p.rows + 127) / 128;
   const int64_t items = rblocks * 32 * (4 / R);
   p.num_items = (int)items;
-  // equal shares: with `per` items per CTA, ceil(items / per) CTAs all run the same number of rounds
-  int64_t grid = (int64_t)sm_count() * occ;
+  int64_t grid = (int64_t)sm_count() * occ_cached;  // every SM full; items beyond two rounds are claimed dynamically
   if (options().quant_ctas > 0) grid = options().quant_ctas;
   if (grid > items) grid = items;
-  const int64_t per = (items + grid - 1) / grid;
-  grid = (items + per - 1) / per;
   if (grid < 1) return MMX_OK;
+  static unsigned int* sched_base = nullptr;
+  if (!sched_base) MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base), g_quant_sched));
+  static std::atomic<unsigned int> seq{0};
+  p.sched = sched_base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) & 63u);
   kern<<<(unsigned)grid, T, smem, stream>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   MMX_CUDA_TRY(cudaGetLastError());
@@ -449,15 +494,13 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int force = (int)options().quant_rows;
-  // configuration by K: rows per item R, threads T, 16-byte chunks per thread and row NLD (NLD*T*8 >= K)
-  if (force != 2) {
-    if (K <= 2048) return launch_quant<4, 128, 2, 6, false>(p, st);
-    if (K <= 4096) return launch_quant<4, 256, 2, 3, false>(p, st);
-    if (K <= 8192) return launch_quant<4, 512, 2, 2, false>(p, st);
-  }
-  if (K <= 4096) return launch_quant<2, 256, 2, 4, false>(p, st);
-  if (K <= 16384) return launch_quant<2, 512, 4, 2, false>(p, st);
-  return launch_quant<2, 1024, 4, 1, true>(p, st);
+  // configuration by K: rows per item R, thread bound, 16-byte chunks per thread and row NLD, compute passes NP
+  if (force == 4 && K <= 4096) return launch_quant<4, 256, 2, 1, 3, false>(p, st);
+  if (K <= 4096) return launch_quant<2, 256, 2, 1, 4, false>(p, st);
+  if (K <= 8192) return launch_quant<2, 512, 2, 1, 2, false>(p, st);
+  if (K <= 14336) return launch_quant<2, 448, 4, 2, 2, false>(p, st);  // 72 registers at two CTAs per SM
+  if (K <= 16384) return launch_quant<2, 512, 4, 2, 2, false>(p, st);
+  return launch_quant<2, 1024, 4, 2, 1, true>(p, st);
 }
 
 }  // namespace mmx
