@@ -176,6 +176,15 @@ __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], co
   }
 }
 
+// What a thread needs to know about one of its compute units (16 permuted channels); item-invariant, so it is
+// computed once per CTA and kept in three registers per pass.
+struct UnitCtx {
+  uint32_t meta;  // bits 0..3 fmt (4|6|8), bits 4..5 segment, bit 6 active, bit 7 writes the group's scale bytes
+  uint32_t qoff;  // byte offset of the unit's codes inside a packed row of its segment
+  uint32_t sfo;   // byte offset of the unit's group inside the row block's scale atoms: (G/4)*512 + G%4
+  uint32_t xoff;  // byte offset of the unit's first (swizzled) 16-byte chunk inside xs
+};
+
 // R rows per item, T threads, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), NP = compute passes
 // (NP * T * 16 >= K), WIDE = table offsets in 4-byte units (K * 2R > 65536).
 //
@@ -193,6 +202,23 @@ struct QuantKernel {
 
   // item -> first row: 32 consecutive items share a block of 32R rows, item i takes rows row0 + 32j, j < R
   static __device__ __forceinline__ int item_row0(int item) { return (item >> 5) * (32 * R) + (item & 31); }
+
+  static __device__ __forceinline__ UnitCtx make_ctx(const QuantParams& p, int ps, int t, int T, int nunits) {
+    const bool active = ps * T + t < nunits;
+    const int u = active ? ps * T + t : 0;
+    const int c0 = u << 4;
+    const int sg = (c0 >= p.cend[1]) ? 2 : (c0 >= p.cend[0] ? 1 : 0);
+    const int fmt = p.fmt[sg];
+    const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
+    const int G = (c0 - cb) >> 5;  // 32-channel group inside the segment
+    const uint32_t p0 = (uint32_t)u * CPT;
+    UnitCtx cx;
+    cx.meta = (uint32_t)fmt | ((uint32_t)sg << 4) | (active ? 64u : 0u) | ((active && !(u & 1)) ? 128u : 0u);
+    cx.qoff = (uint32_t)(((c0 - cb) * fmt) >> 3);
+    cx.sfo = (uint32_t)((G >> 2) * 512 + (G & 3));
+    cx.xoff = (p0 ^ ((p0 >> 3) & SWM)) << 4;
+    return cx;
+  }
 
   template <bool FULL>
   static __device__ __forceinline__ void prefetch(const QuantParams& p, int row0, int t, int T, int K8,
@@ -213,7 +239,8 @@ struct QuantKernel {
 
   template <bool FULL>
   static __device__ __forceinline__ void process(const QuantParams& p, int row0, int t, int T, int K8, int nunits, uint32_t xs_a,
-                                                 const uint16_t* tab, uint4 (&pre)[NLD][R], int next_row0, int* s_next) {
+                                                 const uint16_t* tab, uint4 (&pre)[NLD][R], int next_row0, int* s_next,
+                                                 const UnitCtx& ctx0) {
     const int nvalid = FULL ? R : min(R, ((int)p.rows - 1 - row0) / 32 + 1);
     // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
 #pragma unroll
@@ -258,19 +285,18 @@ struct QuantKernel {
 
     // ---- compute: thread owns permuted channels [16u, 16u+16) of all R rows.  The loop is warp-uniform (full-mask
     // shuffles inside); lanes past the last unit compute on unit 0 and store nothing.
-    const int l = row0 & 31;
-    const int64_t sfrow = (int64_t)(row0 >> 7) * 512;             // x katoms: the row block's first atom
-    const int sfin = l * 16 + ((row0 >> 5) & 3) * 4;               // byte of (row0, group 0) inside an atom
+    const uint32_t sfrow = (uint32_t)(row0 >> 7) * 512u;                                  // x katoms: the row block
+    const uint32_t sfin = (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;  // (row0, group 0) in an atom
 #pragma unroll
     for (int ps = 0; ps < NP; ++ps) {
       if (ps * T >= nunits) break;
-      const bool active = ps * T + t < nunits;
-      const int u = active ? ps * T + t : 0;
-      const int c0 = u << 4;
-      const int sg = (c0 >= p.cend[1]) ? 2 : (c0 >= p.cend[0] ? 1 : 0);
-      const int fmt = p.fmt[sg];
-      const uint32_t p0 = (uint32_t)u * CPT;
-      const uint32_t base = xs_a + ((p0 ^ ((p0 >> 3) & SWM)) << 4);
+      // one pass: the context lives in registers; more: recomputed per item (it would spill otherwise)
+      const UnitCtx cx = (NP == 1) ? ctx0 : make_ctx(p, ps, t, T, nunits);
+      const uint32_t meta = cx.meta;
+      const bool active = (meta & 64u) != 0;
+      const int fmt = (int)(meta & 15u);
+      const int sg = (int)((meta >> 4) & 3u);
+      const uint32_t base = xs_a + cx.xoff;
       uint32_t g[16][RW];
 #pragma unroll
       for (int e = 0; e < CPT; ++e) {
@@ -310,10 +336,8 @@ struct QuantKernel {
       }
 
       // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row)
-      const int cb = (sg == 0) ? 0 : p.cend[sg - 1];
-      if (active && (u & 1) == 0) {
-        const int G = (c0 - cb) >> 5;  // 32-channel group inside the segment
-        uint8_t* d = p.sf[sg] + sfrow * p.katoms[sg] + ((G >> 2) * 512 + (G & 3) + sfin);
+      if (meta & 128u) {
+        uint8_t* d = p.sf[sg] + (sfrow * (uint32_t)p.katoms[sg] + sfin + cx.sfo);
 #pragma unroll
         for (int k = 0; k < RW; ++k) {
           d[8 * k] = (uint8_t)sfb[k];
@@ -323,7 +347,7 @@ struct QuantKernel {
 
       // ---- convert + store: 16 codes per row, contiguous bytes
       const int64_t rbytes = p.rowbytes[sg];
-      uint8_t* dst = p.q[sg] + (int64_t)row0 * rbytes + (((c0 - cb) * fmt) >> 3);
+      uint8_t* dst = p.q[sg] + ((int64_t)row0 * rbytes + cx.qoff);
       const int64_t rstride = 32 * rbytes;
       const int nstore = active ? nvalid : 0;
       if (FULL && !active) {
@@ -363,13 +387,21 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
     else QK::template prefetch<false>(p, row0, t, T, K8, pre);
   }
 
-  // ---- one-time per CTA: inverse permutation as swizzled slot offsets
-  for (int j = t; j < K; j += T) {
-    const uint32_t c = (uint16_t)p.idx[j];
-    const uint32_t pc = ((uint32_t)j * QK::SLOT) >> 4;  // 16-byte chunk of slot j
-    const uint32_t off = ((pc ^ ((pc >> 3) & QK::SWM)) << 4) | (((uint32_t)j * QK::SLOT) & 15u);
-    tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
+  // ---- one-time per CTA: inverse permutation as swizzled slot offsets, eight entries per step
+  for (int j8 = t; j8 < K8; j8 += T) {
+    const uint4 iv = __ldg(reinterpret_cast<const uint4*>(p.idx) + j8);
+    const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t j = (uint32_t)j8 * 8u + e;
+      const uint32_t c = (e & 1) ? (ivw[e >> 1] >> 16) : (ivw[e >> 1] & 0xffffu);
+      const uint32_t pc = (j * QK::SLOT) >> 4;  // 16-byte chunk of slot j
+      const uint32_t off = ((pc ^ ((pc >> 3) & QK::SWM)) << 4) | ((j * QK::SLOT) & 15u);
+      tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
+    }
   }
+  // ---- one-time per thread: what it needs to know about its compute units
+  const UnitCtx ctx0 = QK::make_ctx(p, 0, t, T, nunits);
   __syncthreads();
 
   // items are ordered by row: the first item past the last row ends this CTA's work (block-uniform)
@@ -377,8 +409,8 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   while (row0 < rows) {
     int nrow0 = nitem < num_items ? QK::item_row0(nitem) : rows;
     if (nrow0 >= rows) nrow0 = -1;
-    if (row0 + 32 * (R - 1) < rows) QK::template process<true>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next);
-    else QK::template process<false>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next);
+    if (row0 + 32 * (R - 1) < rows) QK::template process<true>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next, ctx0);
+    else QK::template process<false>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next, ctx0);
     if (nrow0 < 0) break;
     row0 = nrow0;
     nitem = s_next;
@@ -399,9 +431,9 @@ static size_t quant_smem_bytes(int K) {
 
 template <int R, int TMAX, int NLD, int NP, int MINB, bool WIDE>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
-  const size_t smem = quant_smem_bytes<R>(p.K);
   // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
+  const size_t smem = quant_smem_bytes<R>(p.K);
   if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (!WIDE && (int64_t)p.K * 2 * R > 65536)) {
     set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, TMAX,
               NLD, NP, smem);
