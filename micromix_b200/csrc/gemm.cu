@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 #include "common.h"
@@ -38,9 +39,16 @@ constexpr int BM = 128;   // A rows per CTA
 constexpr int BN = 256;   // N per tile
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColSF = 256;   // scale factors: one 24-column slot per smem stage (SFA 8 = 2 atoms x 4, SFB 16)
-constexpr uint32_t kSFSlot = 24;   // per-stage slots, so a stage's tcgen05.cp never overwrites scales that MMAs
-                                   // still in flight are reading (a single slot costs a ~300-cycle bubble per stage)
+// TMEM map (512 columns): two fp32 accumulators of 256 columns that OVERLAP in kAccOverlap columns, then the scale
+// factors.  Tile i accumulates in acc[i & 1]; its epilogue drains the overlap columns first and hands them back, so
+// the MMAs of tile i+1 start after ~kAccOverlap/256 of a drain instead of a whole one (TMEM cannot hold two full
+// 128x256 accumulators plus scales).
+constexpr uint32_t kSFSlot = 24;     // scale columns of one stage: SFA 8 = 2 atoms x 4, SFB 16 = 2 n-blocks x 2 atoms x 4
+constexpr uint32_t kNumSFSlots = 4;  // rotating slots: a stage's tcgen05.cp never lands on scales that MMAs in flight read
+constexpr uint32_t kAccOverlap = 96;  // >= kSFSlot * kNumSFSlots, multiple of 32 (epilogue chunk)
+constexpr uint32_t kColAcc1 = 256 - kAccOverlap;
+constexpr uint32_t kColSF = 512 - kAccOverlap;
+static_assert(kSFSlot * kNumSFSlots <= kAccOverlap && kAccOverlap % 32 == 0, "TMEM map");
 constexpr int kEpiBuf = 2048;      // 32 rows x 32 bf16 (64-byte rows, 64B swizzle): source of one TMA store
 constexpr int kEpiStage = 2 * kEpiBuf;  // two buffers per epilogue warp: stage chunk i+1 while chunk i is read
 
@@ -77,7 +85,7 @@ struct GemmParams {
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
   uint32_t* dbg;
-  uint32_t flags;  // watchdog build only: 1 = skip SF copies, 2 = skip MMAs, 4 = skip C stores, 8 = one SF copy set per tile
+  uint32_t flags;  // watchdog build only: 1 = skip SF copies, 2 = skip MMAs, 4 = skip C stores
 };
 
 struct alignas(64) TmapSet {
@@ -299,6 +307,16 @@ __device__ __forceinline__ uint64_t make_desc_sf(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 
+// The same descriptors from a precomputed low word ((smem address >> 4) & 0x3fff, advanced by immediates) and the
+// constant high word, so the per-stage code is one 32-bit add per descriptor.
+constexpr uint32_t kDescHiOp = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+constexpr uint32_t kDescHiSF = (128u >> 4) | (1u << 14);                // SBO 128, version 1, no swizzle
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -458,14 +476,91 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   } else if (warp == 1) {
     // ======================================================================== MMA issuer (leader CTA)
     // The whole warp walks the loop (converged control flow, warp-uniform operands); one elected lane issues.
+    // This warp is the critical path of the kernel: one stage is only ~512 tensor-pipe cycles (four MMAs), and
+    // every instruction this single warp executes per stage is serial latency in front of the next MMA.  Hence:
+    // all per-stage values are warp-uniform running registers (uniform datapath, no R2UR), descriptors are a
+    // constant high word + a low word advanced by immediates, and the stage body is specialised at compile time
+    // for (kind, scale atoms) so that it is straight-line code.
     if (rank == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t tphase = 0;
       bool ok = true;
       long long t_full = 0, t_tmem = 0, t_begin = WD ? clk() : 0;
       uint32_t n_stage = 0;
+      const bool do_cp = !WD || !(p.flags & 1u);
+      const bool do_mma = !WD || !(p.flags & 2u);
+      // low descriptor words of stage 0; a stage adds kStageBytes >> 4
+      const uint32_t a_lo0 = (smem_base >> 4) & 0x3fffu;
+      const uint32_t b_lo0 = ((smem_base + G::kStageA) >> 4) & 0x3fffu;
+      const uint32_t sf_lo0 = ((smem_base + G::kStageA + G::kStageB) >> 4) & 0x3fffu;
+      constexpr uint32_t kStageInc = G::kStageBytes >> 4;
+      const uint32_t t_sf0 = tmem_base + kColSF;
+      uint32_t stage = 0, soff = 0, phase = 0, slot_off = 0;  // slot_off = kSFSlot * (rotating scale slot)
+      uint32_t tphase = 0, tcount = 0;
+
+      // one pipeline stage: KIND 0 = kind::mxf4 (256 K, NATOMS in {1, 2}), KIND 1 = kind::mxf8f6f4 (128 K, one atom)
+      auto issue_stage = [&](auto kind_c, auto natoms_c, uint32_t idesc, uint32_t d_acc, bool first_of_tile,
+                             bool last_of_tile) {
+        constexpr int KIND = decltype(kind_c)::value, NATOMS = decltype(natoms_c)::value;
+        constexpr int APT = (KIND == 0) ? 2 : 1;
+        const long long tf0 = WD ? clk() : 0;
+        if (!mbar_wait<WD>(bar_base + 8u * stage, phase)) {
+          if (WD && lane == 0) atomicOr(&p.dbg[1], 0x4u | (stage << 8));
+          ok = false;
+          return;
+        }
+        if (WD) {
+          t_full += clk() - tf0;
+          ++n_stage;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t t_sfa = t_sf0 + slot_off;
+          const uint32_t t_sfb = t_sfa + 8;
+          const uint32_t sf_lo = sf_lo0 + soff;
+          if (do_cp) {
+#pragma unroll
+            for (int a = 0; a < NATOMS; ++a) {
+              tc_cp_sf<CG>(t_sfa + 4 * a, desc_from_lo(sf_lo + 32u * a, kDescHiSF));
+              tc_cp_sf<CG>(t_sfb + 8 * a, desc_from_lo(sf_lo + (G::kStageSFA >> 4) + 32u * a, kDescHiSF));  // n-block 0
+              tc_cp_sf<CG>(t_sfb + 8 * a + 4,
+                           desc_from_lo(sf_lo + (G::kStageSFA >> 4) + 32u * (APT + a), kDescHiSF));          // n-block 1
+            }
+          }
+          const uint32_t a_lo = a_lo0 + soff, b_lo = b_lo0 + soff;
+          if (do_mma) {
+            if constexpr (KIND == 0) {
+#pragma unroll
+              for (int j = 0; j < 2 * NATOMS; ++j) {  // K=64 each; two scales per row per MMA: sf id 0 or 2
+                constexpr uint32_t kSid[2] = {0u, (2u << 29) | (2u << 4)};
+                mma_mxf4<CG>(d_acc, desc_from_lo(a_lo + 2u * j, kDescHiOp), desc_from_lo(b_lo + 2u * j, kDescHiOp),
+                             idesc | kSid[j & 1], t_sfa + 4 * (j >> 1), t_sfb + 8 * (j >> 1),
+                             (j == 0 && first_of_tile) ? 0u : 1u);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // K=32 each; sf id = k-block within the 128-K atom
+                mma_mxf8f6f4<CG>(d_acc, desc_from_lo(a_lo + 2u * j, kDescHiOp), desc_from_lo(b_lo + 2u * j, kDescHiOp),
+                                 idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4), t_sfa, t_sfb,
+                                 (j == 0 && first_of_tile) ? 0u : 1u);
+              }
+            }
+          }
+          tc_commit<CG>(bar_base + 8u * (kStages + stage));  // frees the smem slot (both CTAs) once it has been read
+          if (last_of_tile) tc_commit<CG>(tmem_full_bar);
+        }
+        __syncwarp();
+        ++stage;
+        soff += kStageInc;
+        if (stage == (uint32_t)kStages) {
+          stage = 0;
+          soff = 0;
+          phase ^= 1;
+        }
+        slot_off += kSFSlot;
+        if (slot_off == kSFSlot * kNumSFSlots) slot_off = 0;
+      };
+      using std::integral_constant;
       for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
+        // the epilogue must have drained the columns this tile's accumulator shares with the previous one
         const long long tt0 = WD ? clk() : 0;
         if (!mbar_wait<WD>(tmem_empty_bar, tphase ^ 1)) {
           if (WD && lane == 0) atomicOr(&p.dbg[1], 0x2u);
@@ -474,85 +569,51 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         }
         if (WD) t_tmem += clk() - tt0;
         tc_fence_after();
-        uint32_t acc = 0;
-        for (int s = 0; s < p.nseg && ok; ++s) {
-          const GemmSeg& sg = p.seg[s];
-          const int apt = sg.atoms_per_tile;
-          for (int kt = 0; kt < sg.ktiles; ++kt) {
-            const long long tf0 = WD ? clk() : 0;
-            if (!mbar_wait<WD>(full_bar(stage), phase)) {
-              if (WD && lane == 0)
-                atomicOr(&p.dbg[1], 0x4u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (uint32_t)(kt << 20));
-              ok = false;
-              break;
-            }
-            if (WD) {
-              t_full += clk() - tf0;
-              ++n_stage;
-            }
-            tc_fence_after();
-            const int natoms = (kt == sg.ktiles - 1) ? sg.last_atoms : apt;
-            const uint32_t sbase = smem_base + stage * G::kStageBytes;
-            const uint32_t sfa_s = sbase + G::kStageA + G::kStageB;
-            const uint32_t sfb_s = sfa_s + G::kStageSFA;
-            const uint32_t t_sfa = tmem_base + kColSF + kSFSlot * (uint32_t)stage;  // this stage's scale slot
-            const uint32_t t_sfb = t_sfa + 8;
-            const bool do_cp = !WD || !((p.flags & 1u) || ((p.flags & 8u) && (kt > 0)));
-            const bool do_mma = !WD || !(p.flags & 2u);
-            if (elect_one()) {
-              for (int a = 0; a < (do_cp ? natoms : 0); ++a) {
-                tc_cp_sf<CG>(t_sfa + 4 * a, make_desc_sf(sfa_s + 512 * a));
-                tc_cp_sf<CG>(t_sfb + 8 * a, make_desc_sf(sfb_s + 512 * a));              // n-block 0
-                tc_cp_sf<CG>(t_sfb + 8 * a + 4, make_desc_sf(sfb_s + 512 * (apt + a)));  // n-block 1
-              }
-              const uint64_t da = make_desc_sw128(sbase);
-              const uint64_t db = make_desc_sw128(sbase + G::kStageA);
-              if (!do_mma) {
-              } else if (sg.kind == 0) {
-                const int nmma = 2 * natoms;  // K=64 each; two scales per row per MMA: sf id 0 or 2
-#pragma unroll 4
-                for (int j = 0; j < nmma; ++j) {
-                  const uint32_t a = (uint32_t)j >> 1, sid = ((uint32_t)j & 1u) * 2u;
-                  const uint32_t idesc = sg.idesc | (sid << 29) | (sid << 4);
-                  mma_mxf4<CG>(tmem_base, da + 2u * j, db + 2u * j, idesc, t_sfa + 4 * a, t_sfb + 8 * a, acc);
-                  acc = 1;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {  // K=32 each; sf id = k-block within the 128-K atom
-                  const uint32_t idesc = sg.idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4);
-                  mma_mxf8f6f4<CG>(tmem_base, da + 2u * j, db + 2u * j, idesc, t_sfa, t_sfb, acc);
-                  acc = 1;
-                }
-              }
-              tc_commit<CG>(empty_bar(stage));  // frees the smem slot (both CTAs) once MMAs and SF copies have read it
-            }
-            __syncwarp();
-            acc = 1;
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
+        const uint32_t d_acc = tmem_base + ((tcount & 1u) ? kColAcc1 : 0u);
+        for (int sidx = 0; sidx < p.nseg && ok; ++sidx) {
+          const GemmSeg& sg = p.seg[sidx];
+          const int ktiles = sg.ktiles;
+          const uint32_t idesc = sg.idesc;
+          const bool first_seg = sidx == 0, last_seg = sidx == p.nseg - 1;
+          if (sg.kind == 0) {
+            for (int kt = 0; kt < ktiles - 1 && ok; ++kt)
+              issue_stage(integral_constant<int, 0>{}, integral_constant<int, 2>{}, idesc, d_acc, first_seg && kt == 0,
+                          false);
+            if (!ok) break;
+            if (sg.last_atoms == 2)
+              issue_stage(integral_constant<int, 0>{}, integral_constant<int, 2>{}, idesc, d_acc,
+                          first_seg && ktiles == 1, last_seg);
+            else
+              issue_stage(integral_constant<int, 0>{}, integral_constant<int, 1>{}, idesc, d_acc,
+                          first_seg && ktiles == 1, last_seg);
+          } else {
+            for (int kt = 0; kt < ktiles - 1 && ok; ++kt)
+              issue_stage(integral_constant<int, 1>{}, integral_constant<int, 1>{}, idesc, d_acc, first_seg && kt == 0,
+                          false);
+            if (!ok) break;
+            issue_stage(integral_constant<int, 1>{}, integral_constant<int, 1>{}, idesc, d_acc, first_seg && ktiles == 1,
+                        last_seg);
           }
         }
-        if (elect_one()) tc_commit<CG>(tmem_full_bar);
-        __syncwarp();
         tphase ^= 1;
+        ++tcount;
       }
       if (WD && blockIdx.x == 0 && lane == 0) {
         p.dbg[18] = (uint32_t)((clk() - t_begin) >> 4);  // MMA warp: total cycles / 16
-        p.dbg[19] = (uint32_t)(t_full >> 4);             // ... waiting for TMA data / 16
-        p.dbg[20] = (uint32_t)(t_tmem >> 4);             // ... waiting for the epilogue to drain TMEM / 16
+        p.dbg[19] = (uint32_t)(t_full >> 4);             // ... blocked on TMA data / 16
+        p.dbg[20] = (uint32_t)(t_tmem >> 4);             // ... waiting for the epilogue to hand TMEM back / 16
         p.dbg[21] = n_stage;
       }
     }
   } else {
     // ======================================================================== epilogue warps 2..5 (every CTA)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint32_t tphase = 0;
+    uint32_t tphase = 0, tcount = 0;
     long long t_ewait = 0, t_ework = 0;
     uint32_t n_tiles_done = 0;
-    for (int tile = group; tile < num_tiles; tile += ngroups) {
+    const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
+    uint32_t nstore = 0;  // TMA stores issued by this warp: picks the staging buffer
+    for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
       const int m_blk = tile % p.m_tiles;
       const int n_blk = tile / p.m_tiles;
       const long long te0 = WD ? clk() : 0;
@@ -563,41 +624,48 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       const long long te1 = WD ? clk() : 0;
       tc_fence_after();
       const int row0 = (m_blk * CG + (int)rank) * BM + q * 32;  // first C row of this warp's 32-row band
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
-      const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
+      const bool odd = (tcount & 1u) != 0;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? kColAcc1 : 0u);
       const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
-      // ---- phase 1: drain the whole 32 x 256 accumulator band into registers (packed bf16), then hand TMEM back
-      // to the MMA warp at once -- the next tile's MMAs overlap phase 2 although there is a single accumulator.
-      uint32_t packed[BN / 2];
-#pragma unroll
-      for (int ch = 0; ch < BN / 64; ++ch) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tbase + (uint32_t)(ch * 64), r0);
-        tmem_ld32(tbase + (uint32_t)(ch * 64 + 32), r1);
-        tmem_ld_wait();
-        const int col0 = min(n_blk * BN + ch * 64, (int)p.N - 64);  // clamp keeps bias reads in bounds on an N tail
-        pack_chunk(r0, &packed[32 * ch], p.bias ? p.bias + col0 : nullptr);
-        pack_chunk(r1, &packed[32 * ch + 16], p.bias ? p.bias + col0 + 32 : nullptr);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
-      }
-      // ---- phase 2: registers -> swizzled smem (two alternating 2 KB buffers) -> TMA stores
-#pragma unroll
-      for (int sc = 0; sc < BN / 32; ++sc) {
+      // 32-column chunks, the columns shared with the other accumulator first: the top ones of acc0, the bottom
+      // ones of acc1.  Once those are in registers the MMA warp may start the next tile.
+      constexpr int kChunks = BN / 32, kShared = (int)kAccOverlap / 32;
+      auto chunk_col = [&](int i) { return odd ? i : (kChunks - 1 - i); };
+      auto emit = [&](const uint32_t (&r)[32], int sc) {  // 32 rows x 32 columns: bf16, staged, TMA-stored
         const int col0 = n_blk * BN + sc * 32;
         if (col0 < p.N) {  // warp-uniform
-          const uint32_t buf = sbuf + (uint32_t)(sc & 1) * kEpiBuf;
-          // the store issued from this buffer two sub-chunks ago must have finished READING it
+          uint32_t o[16];
+          pack_chunk(r, o, p.bias ? p.bias + col0 : nullptr);
+          const uint32_t buf = sbuf + (nstore & 1u) * kEpiBuf;
+          // the store issued from this buffer two chunks ago must have finished READING it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
-          stage_chunk(&packed[16 * sc], buf, lane);
+          stage_chunk(o, buf, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
           __syncwarp();
           if (lane == 0 && do_store) tma_store_2d(&tmaps.c, buf, col0, row0);  // clipped at M and N by the map
+          ++nstore;
         }
+      };
+      {
+        uint32_t rs[kShared][32];
+#pragma unroll
+        for (int i = 0; i < kShared; ++i) tmem_ld32(tbase + (uint32_t)(chunk_col(i) * 32), rs[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+        }
+#pragma unroll
+        for (int i = 0; i < kShared; ++i) emit(rs[i], chunk_col(i));
+      }
+#pragma unroll
+      for (int i = kShared; i < kChunks; ++i) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)(chunk_col(i) * 32), r);
+        tmem_ld_wait();
+        emit(r, chunk_col(i));
       }
       tphase ^= 1;
       if (WD) {
