@@ -6,21 +6,27 @@
 //   C[M,N] = sum_seg (A_seg o SFA_seg) (B_seg o SFB_seg)^T ,  seg in {FP4xFP4, FP6xFP4|FP6, FP8xFP4|FP8}
 //
 // Kernel shape
-//   * persistent, one CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-//     warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
-//   * CTA tile 128 x 256; one fp32 accumulator of 256 TMEM columns shared by all three K segments, so the
-//     output is rounded to bf16 exactly once and C is written exactly once (no memset, no beta=1 re-reads).
-//   * smem pipeline of 4 stages; every stage is [A 128 rows x 128 B][B 256 rows x 128 B][SFA][SFB], 128B-swizzled:
+//   * persistent, one CTA per SM (CTA pairs, cta_group::2, when M > 128), 192 threads: warp 0 = TMA producer,
+//     warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+//   * tile 128 x 256 per CTA (256 x 256 per pair); all three K segments accumulate into ONE fp32 TMEM accumulator,
+//     so the output is rounded to bf16 exactly once and C is written exactly once (no memset, no beta=1 re-reads).
+//   * TMEM: two 256-column accumulators that overlap in 96 columns + 4 rotating scale-factor slots (see kAccOverlap):
+//     tile i+1 starts as soon as the epilogue of tile i has drained the shared columns, the rest of the drain
+//     (TMEM reads run at ~64 B/clk) hides behind the next tile's MMAs.
+//   * smem pipeline of 6 stages (4 for the single-CTA kernel); a stage is [A 128 x 128 B][B 128|256 x 128 B][SFA][SFB],
+//     128B-swizzled:
 //       FP4xFP4 segment : kind::mxf4.block_scale.block32, packed nibbles, 256 K per stage, 4 MMAs of K=64
 //       other segments  : kind::mxf8f6f4.block_scale, TMA expands FP6/FP4 to the 16-byte-aligned "unpacked"
 //                         smem form (CU_TENSOR_MAP_DATA_TYPE_16U6_ALIGN16B / 16U4_ALIGN16B), 128 K per stage,
 //                         4 MMAs of K=32
 //     so both kinds advance the smem descriptors by 32 bytes per MMA and use identical stage geometry.
 //   * scale factors: the gmem layout (512-byte SfKMajorAtom per 128 rows x 128 K) is already the layout
-//     tcgen05.cp.32x128b.warpx4 wants, so SF tiles go gmem -> smem with cp.async.bulk (no descriptor) and
+//     tcgen05.cp.32x128b.warpx4 wants, so SF tiles go gmem -> smem by TMA (plain u32 boxes) and
 //     smem -> TMEM with tcgen05.cp issued by the MMA thread right before the stage's MMAs.
+//   * the MMA-issuing warp is the kernel's critical path (a stage is only ~512 tensor-pipe cycles): its stage body is
+//     straight-line code specialised on (kind, scale atoms) with running descriptor words -- see the warp == 1 branch.
 //   * epilogue: tcgen05.ld 32x32b.x32 -> fp32 -> bf16 (+ optional bias, rounded like the reference's separate add)
-//     -> 64-byte-per-thread global stores.
+//     -> 64B-swizzled smem staging -> TMA stores (clipped at M and N by the tensor map).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
