@@ -87,6 +87,7 @@ struct GemmParams {
   GemmSeg seg[3];
   int nseg;
   int m_tiles, n_tiles;  // in units of (CG*128) x 256
+  int n_fastest;         // tile order: 1 = consecutive tiles walk N (all of B stays L2-resident per wave), 0 = walk M
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
@@ -443,8 +444,8 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       bool ok = true;
       long long t_wait = 0, t_begin = WD ? clk() : 0;
       for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
-        const int m_blk = tile % p.m_tiles;
-        const int n_blk = tile / p.m_tiles;
+        const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
+        const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
         const int a_row = (m_blk * CG + (int)rank) * BM;          // this CTA's A rows
         const int b_row = n_blk * BN + (int)rank * G::kBRows;      // this CTA's share of the B rows
         for (int s = 0; s < p.nseg && ok; ++s) {
@@ -620,8 +621,8 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
     const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
     uint32_t nstore = 0;  // TMA stores issued by this warp: picks the staging buffer
     for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
-      const int m_blk = tile % p.m_tiles;
-      const int n_blk = tile / p.m_tiles;
+      const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
+      const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
       const long long te0 = WD ? clk() : 0;
       if (!mbar_wait<WD>(tmem_full_bar, tphase)) {
         if (WD && lane == 0) atomicOr(&p.dbg[2], 0x8u | (uint32_t)(q << 8) | (rank << 24));
@@ -840,6 +841,8 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  // one wave of CTAs should re-use the SMALLER operand panel from L2 and stream the other exactly once
+  p.n_fastest = options().gemm_raster == 1 ? 0 : (options().gemm_raster == 2 ? 1 : (p.n_tiles <= p.m_tiles ? 1 : 0));
   int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / CG : sm_count() / CG;
   if (groups < 1) groups = 1;
   if (groups > tiles) groups = tiles;
