@@ -1,0 +1,249 @@
+"""Shared pieces of the quantized decoder-layer wrappers (qLlamaLayer / qQwenLayer / qMixtralLayer).
+
+The reference wraps every `nn.Linear` of a HF decoder layer in a `QLinearLayer` and keeps attention / RoPE / norms in
+stock PyTorch (/root/reference/model/qLlamaLayer.py:69-387, qQwenLayer.py, qMixtralLayer.py).  The B200 version keeps the
+constructors and forward signatures and changes what the hot path costs:
+
+  * q/k/v (and gate/up) read the same activation with the same reorder_index and split, so they are ONE QLinearLayer
+    over the row-concatenated weight: one reorder+quantize and one mixed GEMM instead of three (two);
+  * with a `tp_group`, qkv / gate_up are column-parallel (no collective) and o / down row-parallel with an NCCL all-reduce
+    (micromix_b200.parallel_utils); heads are sharded so every rank runs attention on its own heads only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .parallel_utils import RowParallelQLinear
+from .qLinearLayer import QLinearLayer
+
+NAME = 'layers.{}.{}.{}.{}'  # the key template of the reference's calibration dicts (qLlamaLayer.py:211)
+
+
+def _meta_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> nn.Linear:
+    lin = nn.Linear(weight.shape[1], weight.shape[0], bias=bias is not None, device="meta", dtype=torch.bfloat16)
+    lin.weight = nn.Parameter(weight, requires_grad=False)
+    if bias is not None:
+        lin.bias = nn.Parameter(bias, requires_grad=False)
+    return lin
+
+
+def _same(a, b) -> bool:
+    if isinstance(a, torch.Tensor):
+        return isinstance(b, torch.Tensor) and a.shape == b.shape and bool(torch.equal(a.cpu(), b.cpu()))
+    return int(a) == int(b)
+
+
+class FusedQLinear(nn.Module):
+    """Several linears that read the same activation: one quantize + one GEMM, outputs split on the last dim.
+
+    `row_slices[i]` selects the output rows of linear i this rank owns (column parallelism); None = all rows.
+    """
+
+    def __init__(self, linears: Sequence[nn.Linear], p8_num, p6_num, reorder_index, row_slices=None):
+        super().__init__()
+        ws, bs, self.splits = [], [], []
+        any_bias = any(l.bias is not None for l in linears)
+        for i, l in enumerate(linears):
+            sl = row_slices[i] if row_slices is not None else slice(None)
+            w = l.weight.data[sl]
+            ws.append(w)
+            self.splits.append(w.shape[0])
+            if any_bias:
+                b = l.bias.data[sl] if l.bias is not None else torch.zeros(w.shape[0], dtype=w.dtype, device=w.device)
+                bs.append(b)
+        weight = torch.cat(ws, dim=0).contiguous()
+        bias = torch.cat(bs, dim=0).contiguous() if any_bias else None
+        self.inner = QLinearLayer(_meta_linear(weight, bias), p8_num, p6_num, reorder_index)
+        self.in_features, self.out_features = weight.shape[1], weight.shape[0]
+
+    @torch.no_grad()
+    def forward(self, x):
+        y = self.inner(x)
+        return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
+
+
+def build_input_group(linears, keys, p8_nums, p6_nums, reorder_index, row_slices=None):
+    """One FusedQLinear if all linears share (index, p6, p8) -- calibration gives linears with the same input the same
+    statistics (reorder_indices.py:72-78) -- else one FusedQLinear per linear (the reference's behaviour)."""
+    k0 = keys[0]
+    shared = all(_same(reorder_index[k], reorder_index[k0]) and _same(p8_nums[k], p8_nums[k0]) and
+                 _same(p6_nums[k], p6_nums[k0]) for k in keys[1:])
+    if shared:
+        return nn.ModuleList([FusedQLinear(linears, p8_nums[k0], p6_nums[k0], reorder_index[k0], row_slices)])
+    return nn.ModuleList([FusedQLinear([l], p8_nums[k], p6_nums[k], reorder_index[k],
+                                       None if row_slices is None else [row_slices[i]])
+                          for i, (l, k) in enumerate(zip(linears, keys))])
+
+
+def run_input_group(group, x):
+    outs = []
+    for m in group:
+        outs.extend(m(x))
+    return outs
+
+
+def tp_info(group):
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+@torch.no_grad()
+def quantize_int_group(w, nbits, group_size):
+    """Asymmetric int fake-quant of the KV cache (qLlamaLayer.py:13-23), used when kv_cache=True."""
+    shape = w.shape
+    w = w.reshape(-1, group_size)
+    w_max, w_min = w.amax(dim=-1, keepdim=True), w.amin(dim=-1, keepdim=True)
+    q_max = 2 ** nbits - 1
+    scales = (w_max - w_min).clamp(min=1e-5) / q_max
+    base = torch.round(-w_min / scales).clamp_(min=0, max=q_max)
+    w = (torch.clamp(torch.round(w / scales) + base, 0, q_max) - base) * scales
+    return w.reshape(shape)
+
+
+def apply_rope(q, k, cos, sin):
+    """q, k: [b, heads, s, d]; cos, sin: [b, s, d] (HF convention: halves rotated, qLlamaLayer.py:25-54)."""
+    cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
+
+    def rot(x):
+        h = x.shape[-1] // 2
+        return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+    return q * cos + rot(q) * sin, k * cos + rot(k) * sin
+
+
+class QAttention(nn.Module):
+    """Llama / Qwen2 / Mixtral attention with quantized projections (qLlamaLayer.py:196-321, qQwenLayer.py:205-327)."""
+
+    def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None):
+        super().__init__()
+        cfg = originalAttn.config
+        self.config = cfg
+        self.q_kv_cache = kv_cache
+        self.layer_idx = i
+        self.tp, self.rank = tp_info(tp_group)
+        self.head_dim = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+        if cfg.num_attention_heads % self.tp or cfg.num_key_value_heads % self.tp:
+            raise ValueError(f"heads {cfg.num_attention_heads}/{cfg.num_key_value_heads} do not shard {self.tp} ways")
+        self.num_heads = cfg.num_attention_heads // self.tp          # local
+        self.num_key_value_heads = cfg.num_key_value_heads // self.tp  # local
+        self.num_key_value_groups = self.num_heads // self.num_key_value_heads
+        self.attention_dropout = getattr(originalAttn, "attention_dropout", 0.0)
+        keys = [NAME.format(i, 'self_attn', n, 'input') for n in ('q_proj', 'k_proj', 'v_proj')]
+        d = self.head_dim
+        slices = None
+        if self.tp > 1:
+            slices = [slice(self.rank * self.num_heads * d, (self.rank + 1) * self.num_heads * d),
+                      slice(self.rank * self.num_key_value_heads * d, (self.rank + 1) * self.num_key_value_heads * d),
+                      slice(self.rank * self.num_key_value_heads * d, (self.rank + 1) * self.num_key_value_heads * d)]
+        self.qkv_proj = build_input_group([originalAttn.q_proj, originalAttn.k_proj, originalAttn.v_proj], keys, p8_nums,
+                                          p6_nums, reorder_index, slices)
+        ko = NAME.format(i, 'self_attn', 'o_proj', 'input')
+        if self.tp > 1:
+            self.o_proj = RowParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group)
+        else:
+            self.o_proj = QLinearLayer(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko])
+
+    @torch.no_grad()
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
+        past_key_value = kwargs.get("past_key_values", past_key_value)
+        bsz, q_len, _ = hidden_states.size()
+        q, k, v = run_input_group(self.qkv_proj, hidden_states)
+        q = q.view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
+        k = k.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        v = v.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
+        if position_embeddings is not None:
+            cos, sin = position_embeddings
+            q, k = apply_rope(q, k, cos, sin)
+        else:
+            cos = sin = None
+        if past_key_value is not None:
+            k, v = past_key_value.update(k, v, self.layer_idx, {"sin": sin, "cos": cos, "cache_position": cache_position})
+        if self.q_kv_cache:
+            v = quantize_int_group(v, nbits=4, group_size=128)
+            k = quantize_int_group(k, nbits=4, group_size=128)
+        mask = attention_mask
+        if mask is not None:
+            mask = mask[:, :, :, : k.shape[-2]]
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask,
+                                             dropout_p=self.attention_dropout if self.training else 0.0,
+                                             is_causal=mask is None and q_len > 1,
+                                             enable_gqa=self.num_key_value_groups > 1)
+        out = out.transpose(1, 2).reshape(bsz, q_len, -1)
+        return self.o_proj(out), None, past_key_value
+
+
+class QGatedMLP(nn.Module):
+    """down(act(gate(x)) * up(x)) with quantized projections (qLlamaLayer.py:324-387, qQwenLayer.py:330-393)."""
+
+    def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
+                                                                                               'down_proj'),
+                 key_fmt=None):
+        super().__init__()
+        self.tp, self.rank = tp_info(tp_group)
+        gate, up, down = (getattr(originalMLP, n) for n in names)
+        key = key_fmt or (lambda n: NAME.format(i, 'mlp', n, 'input'))
+        inter = gate.out_features
+        slices = None
+        if self.tp > 1:
+            per = inter // self.tp
+            slices = [slice(self.rank * per, (self.rank + 1) * per)] * 2
+        self.gate_up_proj = build_input_group([gate, up], [key(names[0]), key(names[1])], p8_nums, p6_nums,
+                                              reorder_index, slices)
+        kd = key(names[2])
+        if self.tp > 1:
+            self.down_proj = RowParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group)
+        else:
+            self.down_proj = QLinearLayer(down, p8_nums[kd], p6_nums[kd], reorder_index[kd])
+        self.act_fn = getattr(originalMLP, "act_fn", F.silu)
+
+    @torch.no_grad()
+    def forward(self, x):
+        g, u = run_input_group(self.gate_up_proj, x)
+        return self.down_proj(self.act_fn(g) * u)
+
+
+class QDecoderLayer(nn.Module):
+    """norm -> attention -> residual -> norm -> MLP -> residual, the reference's forward contract
+    (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
+
+    def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None):
+        super().__init__()
+        self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
+        self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
+                                    tp_group)
+        self.mlp = self._build_mlp(originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
+        self.input_layernorm = originalLayer.input_layernorm
+        self.post_attention_layernorm = originalLayer.post_attention_layernorm
+
+    def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
+        return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
+
+    @torch.no_grad()
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, attn_weights, present = self.self_attn(
+            hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+            past_key_value=past_key_value, output_attentions=output_attentions, use_cache=use_cache,
+            cache_position=cache_position, position_embeddings=position_embeddings, **kwargs)
+        hidden_states = residual + hidden_states
+        residual = hidden_states
+        hidden_states = self.post_attention_layernorm(hidden_states)
+        hidden_states = self.mlp(hidden_states)
+        if isinstance(hidden_states, tuple):  # MoE blocks return (hidden_states, router_logits)
+            hidden_states = hidden_states[0]
+        hidden_states = residual + hidden_states
+        outputs = (hidden_states,)
+        if output_attentions:
+            outputs += (attn_weights,)
+        if use_cache:
+            outputs += (present,)
+        return outputs

@@ -1,0 +1,112 @@
+"""GPU tests of the decoder-layer wrappers (qLlamaLayer / qQwenLayer / qMixtralLayer).
+
+The check is against the REFERENCE'S structure rebuilt from per-projection QLinearLayers (one quantize + one GEMM per
+linear, python loop over experts: qLlamaLayer.py:252-321,368-387, qMixtralLayer.py:420-450): fusing q/k/v, gate/up and
+w1/w3 must not change a single bit, because every output column accumulates independently of the N tiling.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TINY = dict(hidden_size=512, intermediate_size=1024, num_attention_heads=4, num_key_value_heads=2, head_dim=128,
+            num_hidden_layers=2, rms_norm_eps=1e-5, qkv_bias=False, rope_theta=10000.0)
+TINY_MOE = dict(TINY, num_local_experts=4, num_experts_per_tok=2)
+
+
+def _unfused_layer(layer, cfg, idx, p6, p8, i, x, cos, sin, moe=False):
+    from micromix_b200._qdecoder import apply_rope
+    from micromix_b200.qLinearLayer import QLinearLayer
+
+    def q(lin, key):
+        return QLinearLayer(lin, p8[key], p6[key], idx[key])
+
+    t = 'layers.{}.{}.{}.input'
+    b, s, _ = x.shape
+    a = layer.self_attn
+    h = layer.input_layernorm(x)
+    qs = q(a.q_proj, t.format(i, 'self_attn', 'q_proj'))(h).view(b, s, cfg['num_attention_heads'], -1).transpose(1, 2)
+    ks = q(a.k_proj, t.format(i, 'self_attn', 'k_proj'))(h).view(b, s, cfg['num_key_value_heads'], -1).transpose(1, 2)
+    vs = q(a.v_proj, t.format(i, 'self_attn', 'v_proj'))(h).view(b, s, cfg['num_key_value_heads'], -1).transpose(1, 2)
+    qs, ks = apply_rope(qs, ks, cos, sin)
+    o = F.scaled_dot_product_attention(qs, ks, vs, is_causal=True, enable_gqa=True)
+    o = q(a.o_proj, t.format(i, 'self_attn', 'o_proj'))(o.transpose(1, 2).reshape(b, s, -1))
+    x = x + o
+    h = layer.post_attention_layernorm(x)
+    if not moe:
+        m = layer.mlp
+        g = q(m.gate_proj, t.format(i, 'mlp', 'gate_proj'))(h)
+        u = q(m.up_proj, t.format(i, 'mlp', 'up_proj'))(h)
+        y = q(m.down_proj, t.format(i, 'mlp', 'down_proj'))(F.silu(g) * u)
+    else:
+        blk = layer.block_sparse_moe
+        te = 'layers.{}.block_sparse_moe.experts.{}.{}.input'
+        hx = h.view(-1, h.shape[-1])
+        w = F.softmax(blk.gate(hx), dim=1, dtype=torch.float)
+        w, sel = torch.topk(w, blk.top_k, dim=-1)
+        w = (w / w.sum(dim=-1, keepdim=True)).to(hx.dtype)
+        y = torch.zeros_like(hx)
+        for j, e in enumerate(blk.experts):
+            tok, slot = torch.where(sel == j)
+            if tok.numel() == 0:
+                continue
+            cur = hx.index_select(0, tok).unsqueeze(0)
+            g = q(e.w1, te.format(i, j, 'w1'))(cur)
+            u = q(e.w3, te.format(i, j, 'w3'))(cur)
+            yy = q(e.w2, te.format(i, j, 'w2'))(F.silu(g) * u).squeeze(0) * w[tok, slot, None]
+            y.index_add_(0, tok, yy.to(hx.dtype))
+        y = y.view_as(h)
+    return x + y
+
+
+def _run(cuda, cfg, cls_path, moe=False, bias=False, bsz=2, seq=96):
+    import importlib
+    from micromix_b200 import model_shapes as S
+    cfg = dict(cfg, qkv_bias=bias)
+    layer = S.make_layer(cfg, cuda, seed=3, moe=moe)
+    idx, p6, p8 = S.make_calibration(cfg, 1, seed=5, moe=moe)
+    mod, name = cls_path.rsplit('.', 1)
+    cls = getattr(importlib.import_module(mod), name)
+    qlayer = cls(layer, False, p8, p6, idx, 1)
+    g = torch.Generator(device=cuda).manual_seed(11)
+    x = torch.randn(bsz, seq, cfg['hidden_size'], generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
+    cos, sin = S.rope_tables(cfg, bsz, seq, cuda)
+    out = qlayer(x, position_embeddings=(cos, sin))
+    assert isinstance(out, tuple) and len(out) == 1
+    ref = _unfused_layer(layer, cfg, idx, p6, p8, 1, x, cos, sin, moe=moe)
+    torch.cuda.synchronize()
+    assert out[0].shape == x.shape and out[0].dtype == torch.bfloat16
+    assert torch.isfinite(out[0].float()).all()
+    assert torch.equal(out[0], ref), float((out[0].float() - ref.float()).abs().max())
+    return qlayer, x, cos, sin
+
+
+def test_llama_layer_matches_unfused_reference_structure(cuda):
+    q, x, cos, sin = _run(cuda, TINY, 'micromix_b200.qLlamaLayer.QLlamaDecoderLayer')
+    assert len(q.self_attn.qkv_proj) == 1 and len(q.mlp.gate_up_proj) == 1  # fused: one quantize + one GEMM each
+    out = q(x, position_embeddings=(cos, sin), output_attentions=True, use_cache=True)
+    assert len(out) == 3  # (hidden, attn_weights=None, present=None): the reference's tuple contract
+
+
+def test_qwen_layer_with_qkv_bias(cuda):
+    _run(cuda, TINY, 'micromix_b200.qQwenLayer.QQwen2DecoderLayer', bias=True)
+
+
+def test_mixtral_layer_matches_expert_loop(cuda):
+    _run(cuda, TINY_MOE, 'micromix_b200.qMixtralLayer.QMixtralDecoderLayer', moe=True)
+
+
+def test_unshared_calibration_falls_back_to_separate_linears(cuda):
+    from micromix_b200 import model_shapes as S
+    from micromix_b200.qLlamaLayer import QLlamaDecoderLayer
+    layer = S.make_layer(TINY, cuda, seed=3)
+    idx, p6, p8 = S.make_calibration(TINY, 0, seed=5)
+    k = 'layers.0.self_attn.k_proj.input'
+    idx[k] = torch.randperm(TINY['hidden_size'], generator=torch.Generator().manual_seed(9)).to(torch.int16)
+    q = QLlamaDecoderLayer(layer, False, p8, p6, idx, 0)
+    assert len(q.self_attn.qkv_proj) == 3
+    x = torch.randn(1, 40, TINY['hidden_size'], device=cuda).to(torch.bfloat16)
+    cos, sin = S.rope_tables(TINY, 1, 40, cuda)
+    ref = _unfused_layer(layer, TINY, idx, p6, p8, 0, x, cos, sin)
+    assert torch.equal(q(x, position_embeddings=(cos, sin))[0], ref)

@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Model-level measurements of BASELINE configs 3-5 on the B200 box (one JSON line per config on stdout).
+
+  config 3  python tools/bench_models.py prefill [--layers 32] [--batch 8] [--seq 2048]
+            full Llama-3-8B prefill through QLlamaDecoderLayer, random-init weights, tokens/s
+  config 4  torchrun --nproc-per-node N tools/bench_models.py qwen_tp [--tokens 16384]
+            one Qwen2.5-32B-shaped layer, tensor parallel N ways (column qkv/gate_up, row o/down + all-reduce)
+  config 5  [torchrun --nproc-per-node N] tools/bench_models.py mixtral_ep [--tokens 16384]
+            Mixtral-8x7B MoE block (8 experts, top-2), experts sharded over N ranks
+
+Timing: CUDA events around `iters` forwards after warm-up, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from micromix_b200 import mixedgemm  # noqa: E402
+from micromix_b200 import model_shapes as S  # noqa: E402
+
+
+def setup():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        from micromix_b200.parallel_utils import init_tensor_parallel
+        rank, world, dev = init_tensor_parallel("nccl")
+    else:
+        rank, dev = 0, torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+    return rank, world, dev
+
+
+def timed(fn, iters, warmup, world, dev):
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = mixedgemm.launch_count()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, (mixedgemm.launch_count() - l0) // iters
+
+
+def layer_flops(cfg, tokens, moe=False):
+    h, i, d = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
+    nq, nkv = cfg["num_attention_heads"], cfg["num_key_value_heads"]
+    lin = h * (nq + 2 * nkv) * d + nq * d * h
+    lin += (cfg["num_experts_per_tok"] if moe else 1) * 3 * h * i
+    return 2.0 * tokens * lin
+
+
+def prefill(args, rank, world, dev):
+    from micromix_b200.qLlamaLayer import QLlamaDecoderLayer
+    cfg = S.LLAMA3_8B
+    group = dist.group.WORLD if world > 1 else None
+    layers = []
+    for i in range(args.layers):
+        layer = S.make_layer(cfg, dev, seed=i)
+        idx, p6, p8 = S.make_calibration(cfg, i)
+        layers.append(QLlamaDecoderLayer(layer, False, p8, p6, idx, i, tp_group=group))
+        del layer
+    torch.cuda.empty_cache()
+    b, s = args.batch, args.seq
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(b, s, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    pos = S.rope_tables(cfg, b, s, dev)
+
+    @torch.no_grad()
+    def fwd():
+        x = x0
+        for l in layers:
+            x = l(x, position_embeddings=pos)[0]
+        return x
+
+    ms, launches = timed(fwd, args.iters, 2, world, dev)
+    y = fwd()
+    assert torch.isfinite(y.float()).all()
+    tokens = b * s
+    scale = cfg["num_hidden_layers"] / args.layers
+    return {"config": "Llama-3-8B full prefill, random-init weights, synthetic reorder_index, "
+                      f"batch {b} x seq {s}", "layers_run": args.layers, "ms_per_prefill": ms * scale,
+            "tokens_per_s": tokens / (ms * scale) * 1e3, "linear_tflops": layer_flops(cfg, tokens) * args.layers / ms / 1e9,
+            "n_gpus": world, "parallelism": f"tp{world}" if world > 1 else "single", "mmx_launches_per_forward": launches,
+            "note": "decoder layers only (no embedding / lm_head, as in the reference's layer-wise eval); attention = SDPA"}
+
+
+def qwen_tp(args, rank, world, dev):
+    from micromix_b200.qQwenLayer import QQwen2DecoderLayer
+    cfg = S.QWEN25_32B
+    group = dist.group.WORLD if world > 1 else None
+    layer = S.make_layer(cfg, dev, seed=0)
+    idx, p6, p8 = S.make_calibration(cfg, 0)
+    q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group)
+    del layer
+    torch.cuda.empty_cache()
+    b, s = max(1, args.tokens // 2048), 2048
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(b, s, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    pos = S.rope_tables(cfg, b, s, dev)
+    ms, launches = timed(lambda: q(x0, position_embeddings=pos), args.iters, 3, world, dev)
+    tokens = b * s
+    return {"config": f"Qwen2.5-32B-shaped decoder layer, {tokens} tokens, tensor parallel {world} (column qkv/gate_up, "
+                      "row o/down + NCCL all-reduce)", "ms_per_layer": ms, "tokens_per_s_per_layer": tokens / ms * 1e3,
+            "linear_tflops": layer_flops(cfg, tokens) / ms / 1e9, "n_gpus": world, "mmx_launches_per_forward": launches}
+
+
+def mixtral_ep(args, rank, world, dev):
+    from micromix_b200.qMixtralLayer import QMixtralSparseMoeBlock
+    cfg = S.MIXTRAL_8X7B
+    group = dist.group.WORLD if world > 1 else None
+    layer = S.make_layer(cfg, dev, seed=0, moe=True)
+    idx, p6, p8 = S.make_calibration(cfg, 0, moe=True)
+    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, ep_group=group)
+    del layer
+    torch.cuda.empty_cache()
+    tokens = args.tokens
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(1, tokens, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    ms, launches = timed(lambda: blk(x0), args.iters, 3, world, dev)
+    flops = 2.0 * tokens * cfg["num_experts_per_tok"] * 3 * cfg["hidden_size"] * cfg["intermediate_size"]
+    return {"config": f"Mixtral-8x7B expert FFN (8 experts, top-2), {tokens} tokens, expert parallel {world}",
+            "ms_per_block": ms, "tokens_per_s": tokens / ms * 1e3, "expert_tflops": flops / ms / 1e9, "n_gpus": world,
+            "mmx_launches_per_forward": launches}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["prefill", "qwen_tp", "mixtral_ep"])
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--tokens", type=int, default=16384)
+    ap.add_argument("--iters", type=int, default=3)
+    args = ap.parse_args()
+    rank, world, dev = setup()
+    try:
+        res = {"prefill": prefill, "qwen_tp": qwen_tp, "mixtral_ep": mixtral_ep}[args.what](args, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
