@@ -20,6 +20,7 @@ struct Options {
   int64_t quant_ctas = 0;     // 0: SMs x occupancy, else force the persistent grid size
   int64_t gemm_ctas = 0;      // 0: one CTA per SM, else force the persistent grid size
   int64_t gemm_debug_flags = 0;  // watchdog build: timing experiments (results are wrong), see GemmParams::flags
+  int64_t pdl = 1;            // 1: kernels are launched with programmatic stream serialization (prologue overlap)
   int64_t gemm_raster = 0;    // 0: auto, 1: force M-fastest tile order, 2: force N-fastest
   int64_t gemm_cta_group = 0; // 0: auto (pairs when M > 128), 1: force the single-CTA kernel
 };

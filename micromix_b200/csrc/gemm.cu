@@ -410,6 +410,8 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   const int ngroups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
+  // programmatic dependent launch: the next kernel in the stream may start its prologue as SMs free up
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);   // the leader's producer arrives once (with the expected bytes of the whole pair)
@@ -435,6 +437,8 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
+  // everything above overlapped the previous kernel's tail; its outputs (our operands) are complete after this
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     // ======================================================================== TMA producer (one lane per CTA)
@@ -859,13 +863,15 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = G::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MMX_OK;

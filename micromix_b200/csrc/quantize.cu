@@ -375,6 +375,9 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   const int t = threadIdx.x;
   const int rows = (int)p.rows;
 
+  // programmatic dependent launch: let the next kernel in the stream begin its own prologue as SMs free up ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   uint4 pre[NLD][R];  // prefetched rows of the next item
   __shared__ int s_next;
   const int num_items = p.num_items;
@@ -382,10 +385,6 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   // from a global counter one item ahead of their prefetch, so SMs that run ahead simply take more items
   int item = blockIdx.x;
   int row0 = item < num_items ? QK::item_row0(item) : rows;
-  if (row0 < rows) {  // first loads go out before the table is built
-    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true>(p, row0, t, T, K8, pre);
-    else QK::template prefetch<false>(p, row0, t, T, K8, pre);
-  }
 
   // ---- one-time per CTA: inverse permutation as swizzled slot offsets, eight entries per step
   for (int j8 = t; j8 < K8; j8 += T) {
@@ -402,6 +401,13 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   }
   // ---- one-time per thread: what it needs to know about its compute units
   const UnitCtx ctx0 = QK::make_ctx(p, 0, t, T, nunits);
+  // ... and wait for the previous kernel (which may still be producing X) only now: the table above depends on
+  // reorder_index alone, which no kernel of this library writes, so it was built under the previous kernel's tail.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (row0 < rows) {
+    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true>(p, row0, t, T, K8, pre);
+    else QK::template prefetch<false>(p, row0, t, T, K8, pre);
+  }
   __syncthreads();
 
   // items are ordered by row: the first item past the last row ends this CTA's work (block-uniform)
@@ -466,9 +472,18 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   if (!sched_base) MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base), g_quant_sched));
   static std::atomic<unsigned int> seq{0};
   p.sched = sched_base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) & 63u);
-  kern<<<(unsigned)grid, T, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  MMX_CUDA_TRY(cudaGetLastError());
   return MMX_OK;
 }
 
