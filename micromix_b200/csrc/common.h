@@ -17,6 +17,7 @@ struct Options {
   int64_t gemm_watchdog = 0;  // 1: bounded mbarrier spins, status words written to the debug buffer
   int64_t gemm_tx_mode = 0;   // 0: TMA tx bytes = packed gmem bytes (FP4 64B/row, FP6 96B/row); 1: smem footprint
   int64_t quant_rows = 0;     // 0: auto (two rows per item), 4: force the four-rows-per-item kernel for K <= 4096
+  int64_t quant_variant = 0; // tuning sweeps only: alternative table encoding / occupancy bound of the quantize kernel
   int64_t quant_ctas = 0;     // 0: SMs x occupancy, else force the persistent grid size
   int64_t gemm_ctas = 0;      // 0: one CTA per SM, else force the persistent grid size
   int64_t gemm_debug_flags = 0;  // watchdog build: timing experiments (results are wrong), see GemmParams::flags

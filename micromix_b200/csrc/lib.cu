@@ -65,6 +65,7 @@ extern "C" __attribute__((visibility("default"))) int mmx_set_option(const char*
   if (!std::strcmp(key, "gemm_watchdog")) o.gemm_watchdog = value;
   else if (!std::strcmp(key, "gemm_tx_mode")) o.gemm_tx_mode = value;
   else if (!std::strcmp(key, "quant_rows")) o.quant_rows = value;
+  else if (!std::strcmp(key, "quant_variant")) o.quant_variant = value;
   else if (!std::strcmp(key, "quant_ctas")) o.quant_ctas = value;
   else if (!std::strcmp(key, "gemm_ctas")) o.gemm_ctas = value;
   else if (!std::strcmp(key, "gemm_cta_group")) o.gemm_cta_group = value;

@@ -176,8 +176,8 @@ __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], co
   }
 }
 
-// What a thread needs to know about one of its compute units (16 permuted channels); item-invariant, so it is
-// computed once per CTA and kept in three registers per pass.
+// What a thread needs to know about one of its compute units (16 permuted channels of all R rows).  Item-invariant:
+// computed once per CTA; kept in registers when a thread has one unit (NP == 1), in shared memory otherwise.
 struct UnitCtx {
   uint32_t meta;  // bits 0..3 fmt (4|6|8), bits 4..5 segment, bit 6 active, bit 7 writes the group's scale bytes
   uint32_t qoff;  // byte offset of the unit's codes inside a packed row of its segment
@@ -185,27 +185,42 @@ struct UnitCtx {
   uint32_t xoff;  // byte offset of the unit's first (swizzled) 16-byte chunk inside xs
 };
 
-// R rows per item, T threads, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), NP = compute passes
-// (NP * T * 16 >= K), WIDE = table offsets in 4-byte units (K * 2R > 65536).
+// Everything else a unit needs, derived from its context and the launch parameters.  For NP == 1 this lives in
+// registers for the whole kernel, so the per-item address work is one multiply-add per pointer.
+struct UnitPtrs {
+  uint8_t* qp;      // p.q[sg] + qoff
+  uint8_t* sfp;     // p.sf[sg] + sfo
+  uint32_t rbytes;  // bytes of one packed row of the segment
+  uint32_t ka512;   // scale bytes of one 128-row block of the segment: katoms * 512
+  uint32_t q2;      // log2floor(QMAX) in both 16-bit lanes: 2 | 4 | 8
+  uint32_t add2;    // 127 - mantissa threshold (0x40 for QMAX = 6 = 1.5 * 4, 0x60 for 28 | 448 = 1.75 * 2^n) in both lanes
+};
+
+// R rows per item, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), NP = compute passes
+// (NP * T * 16 >= K), TABMODE = encoding of the scatter table: 0 = u16 byte offset into xs, 1 = u16 offset / 4
+// (K * 2R > 65536), 2 = u32 absolute shared-memory address (no unpacking in the scatter loop).
 //
-// Shared memory: tab[K] u16 | xs[K] slots of 2R bytes
-//   tab[c]  byte offset (WIDE: /4) inside xs of the slot of ORIGINAL channel c, i.e. of permuted position j with
-//           idx[j] == c, after the chunk swizzle.  Built once per CTA.
+// Shared memory: tab[K] | xs[K] slots of 2R bytes | NP > 1: ctx[K/16]
+//   tab[c]  where the slot of ORIGINAL channel c lives inside xs, i.e. of permuted position j with idx[j] == c,
+//           after the chunk swizzle.  Built once per CTA.
 //   xs      slot j holds the R rows of permuted channel j; 16-byte chunk p = j * 2R / 16 is stored at chunk
 //           p ^ ((p >> 3) & SWM) so that the lane-strided 128-bit reads of the compute phase are conflict-free.
-template <int R, int NLD, int NP, bool WIDE>
+template <int R, int NLD, int NP, int TABMODE>
 struct QuantKernel {
   static constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
   static constexpr int SLOT = 2 * R;        // bytes per slot
   static constexpr int CPT = SLOT;          // 16-byte chunks holding a thread's 16 channels: 8 (R=4) | 4 (R=2)
   static constexpr uint32_t SWM = (R == 4) ? 7u : 3u;
+  static constexpr int TABW = (TABMODE == 2) ? 4 : 2;
 
   // item -> first row: 32 consecutive items share a block of 32R rows, item i takes rows row0 + 32j, j < R
-  static __device__ __forceinline__ int item_row0(int item) { return (item >> 5) * (32 * R) + (item & 31); }
+  static __device__ __forceinline__ int item_row0(int item, int num_items, int rows) {
+    return item < num_items ? (item >> 5) * (32 * R) + (item & 31) : rows;
+  }
 
-  static __device__ __forceinline__ UnitCtx make_ctx(const QuantParams& p, int ps, int t, int T, int nunits) {
-    const bool active = ps * T + t < nunits;
-    const int u = active ? ps * T + t : 0;
+  static __device__ __forceinline__ UnitCtx make_ctx(const QuantParams& p, int u, int nunits) {
+    const bool active = u < nunits;
+    if (!active) u = 0;
     const int c0 = u << 4;
     const int sg = (c0 >= p.cend[1]) ? 2 : (c0 >= p.cend[0] ? 1 : 0);
     const int fmt = p.fmt[sg];
@@ -220,11 +235,26 @@ struct QuantKernel {
     return cx;
   }
 
-  template <bool FULL>
-  static __device__ __forceinline__ void prefetch(const QuantParams& p, int row0, int t, int T, int K8,
+  static __device__ __forceinline__ UnitPtrs make_ptrs(const QuantParams& p, const UnitCtx& cx) {
+    const int sg = (int)((cx.meta >> 4) & 3u);
+    const int fmt = (int)(cx.meta & 15u);
+    UnitPtrs up;
+    up.qp = p.q[sg] + cx.qoff;
+    up.sfp = p.sf[sg] + cx.sfo;
+    up.rbytes = (uint32_t)p.rowbytes[sg];
+    up.ka512 = (uint32_t)p.katoms[sg] * 512u;
+    up.q2 = (fmt == 4) ? 0x00020002u : ((fmt == 6) ? 0x00040004u : 0x00080008u);
+    up.add2 = (fmt == 4) ? 0x003f003fu : 0x001f001fu;
+    return up;
+  }
+
+  // The global loads of one item: thread t takes the 16-byte chunks t, t + T, ... of each of the R rows.
+  // EXACT: NLD * T * 8 == K, no chunk predicate.  FULL: all R rows exist.
+  template <bool FULL, bool EXACT>
+  static __device__ __forceinline__ void prefetch(const QuantParams& p, const uint16_t* xt, int row0, int t, int T, int K8,
                                                   uint4 (&pre)[NLD][R]) {
     const int K = p.K;
-    const uint16_t* b0 = p.x + (int64_t)row0 * K + 8 * t;
+    const uint16_t* b0 = xt + (int64_t)row0 * K;
     const int64_t rs = (int64_t)32 * K;  // elements between two rows of the item
     const int nvalid = FULL ? R : min(R, ((int)p.rows - 1 - row0) / 32 + 1);
 #pragma unroll
@@ -233,22 +263,32 @@ struct QuantKernel {
       const uint16_t* bj = (FULL || j < nvalid) ? b0 + j * rs : b0;
 #pragma unroll
       for (int i = 0; i < NLD; ++i)
-        if (i * T + t < K8) pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
+        if (EXACT || i * T + t < K8) pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
     }
   }
 
-  template <bool FULL>
-  static __device__ __forceinline__ void process(const QuantParams& p, int row0, int t, int T, int K8, int nunits, uint32_t xs_a,
-                                                 const uint16_t* tab, uint4 (&pre)[NLD][R], int next_row0, int* s_next,
-                                                 const UnitCtx& ctx0) {
-    const int nvalid = FULL ? R : min(R, ((int)p.rows - 1 - row0) / 32 + 1);
-    // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
+  // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
+  template <bool FULL, bool EXACT>
+  static __device__ __forceinline__ void scatter(int nvalid, int t, int T, int K8, uint32_t xs_a, uint32_t tab_a,
+                                                 const uint4 (&pre)[NLD][R]) {
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       const int c8 = i * T + t;
-      if (c8 < K8) {
-        const uint4 ov = *reinterpret_cast<const uint4*>(tab + 8 * c8);
-        const uint32_t o[4] = {ov.x, ov.y, ov.z, ov.w};
+      if (EXACT || c8 < K8) {
+        uint32_t adr[8];  // shared-memory address of the slot of original channel 8*c8 + e
+        if constexpr (TABMODE == 2) {
+          const uint4 o0 = lds128(tab_a + 32u * (uint32_t)c8), o1 = lds128(tab_a + 32u * (uint32_t)c8 + 16u);
+          adr[0] = o0.x; adr[1] = o0.y; adr[2] = o0.z; adr[3] = o0.w;
+          adr[4] = o1.x; adr[5] = o1.y; adr[6] = o1.z; adr[7] = o1.w;
+        } else {
+          const uint4 ov = lds128(tab_a + 16u * (uint32_t)c8);
+          const uint32_t o[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            adr[2 * m] = xs_a + ((TABMODE == 1) ? ((o[m] & 0xffffu) << 2) : (o[m] & 0xffffu));
+            adr[2 * m + 1] = xs_a + ((TABMODE == 1) ? ((o[m] >> 16) << 2) : (o[m] >> 16));
+          }
+        }
         uint32_t w[R][4];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -260,118 +300,144 @@ struct QuantKernel {
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {  // channels 8*c8 + 2m (low halves) and + 2m+1 (high halves)
-          const uint32_t a_lo = xs_a + (WIDE ? ((o[m] & 0xffffu) << 2) : (o[m] & 0xffffu));
-          const uint32_t a_hi = xs_a + (WIDE ? ((o[m] >> 16) << 2) : (o[m] >> 16));
           if constexpr (R == 4) {
-            sts64(a_lo, __byte_perm(w[0][m], w[1][m], 0x5410), __byte_perm(w[2][m], w[3][m], 0x5410));
-            sts64(a_hi, __byte_perm(w[0][m], w[1][m], 0x7632), __byte_perm(w[2][m], w[3][m], 0x7632));
+            sts64(adr[2 * m], __byte_perm(w[0][m], w[1][m], 0x5410), __byte_perm(w[2][m], w[3][m], 0x5410));
+            sts64(adr[2 * m + 1], __byte_perm(w[0][m], w[1][m], 0x7632), __byte_perm(w[2][m], w[3][m], 0x7632));
           } else {
-            sts32(a_lo, __byte_perm(w[0][m], w[1][m], 0x5410));
-            sts32(a_hi, __byte_perm(w[0][m], w[1][m], 0x7632));
+            sts32(adr[2 * m], __byte_perm(w[0][m], w[1][m], 0x5410));
+            sts32(adr[2 * m + 1], __byte_perm(w[0][m], w[1][m], 0x7632));
           }
         }
       }
     }
-    __syncthreads();
-    // the next item's rows: in flight during the compute below
-    if (next_row0 >= 0) {
-      if (next_row0 + 32 * (R - 1) < (int)p.rows) prefetch<true>(p, next_row0, t, T, K8, pre);
-      else prefetch<false>(p, next_row0, t, T, K8, pre);
+  }
+
+  // ---- compute: one unit = permuted channels [16u, 16u+16) of all R rows.  Warp-uniform (full-mask shuffle inside);
+  // lanes past the last unit compute on unit 0 and store nothing.
+  template <bool FULL>
+  static __device__ __forceinline__ void compute_unit(const UnitCtx& cx, const UnitPtrs& up, uint32_t xs_a, int row0,
+                                                      int nvalid) {
+    const uint32_t meta = cx.meta;
+    const bool active = (meta & 64u) != 0;
+    const int fmt = (int)(meta & 15u);
+    const uint32_t base = xs_a + cx.xoff;
+    uint32_t g[16][RW];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+      const uint4 v = lds128(base ^ ((uint32_t)e << 4));
+      if constexpr (R == 4) {
+        g[2 * e][0] = v.x;
+        g[2 * e][1] = v.y;
+        g[2 * e + 1][0] = v.z;
+        g[2 * e + 1][1] = v.w;
+      } else {
+        g[4 * e][0] = v.x;
+        g[4 * e + 1][0] = v.y;
+        g[4 * e + 2][0] = v.z;
+        g[4 * e + 3][0] = v.w;
+      }
     }
 
-    // dynamic schedule: claim the item after next now; the answer is only needed one whole item later
-    unsigned int claimed = 0;
-    if (t == 0) claimed = atomicAdd(p.sched, 1u);
-
-    // ---- compute: thread owns permuted channels [16u, 16u+16) of all R rows.  The loop is warp-uniform (full-mask
-    // shuffles inside); lanes past the last unit compute on unit 0 and store nothing.
-    const uint32_t sfrow = (uint32_t)(row0 >> 7) * 512u;                                  // x katoms: the row block
-    const uint32_t sfin = (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;  // (row0, group 0) in an atom
+    // ---- absmax per row over the 32-group (16 local channels + the partner lane), scale byte, multiplier
+    uint32_t mult[RW];
+    uint32_t sfb[RW];
 #pragma unroll
-    for (int ps = 0; ps < NP; ++ps) {
-      if (ps * T >= nunits) break;
-      // one pass: the context lives in registers; more: recomputed per item (it would spill otherwise)
-      const UnitCtx cx = (NP == 1) ? ctx0 : make_ctx(p, ps, t, T, nunits);
-      const uint32_t meta = cx.meta;
-      const bool active = (meta & 64u) != 0;
-      const int fmt = (int)(meta & 15u);
-      const int sg = (int)((meta >> 4) & 3u);
-      const uint32_t base = xs_a + cx.xoff;
-      uint32_t g[16][RW];
+    for (int k = 0; k < RW; ++k) {
+      uint32_t m = absmax2(g[0][k], g[1][k]);
 #pragma unroll
-      for (int e = 0; e < CPT; ++e) {
-        const uint4 v = lds128(base ^ ((uint32_t)e << 4));
-        if constexpr (R == 4) {
-          g[2 * e][0] = v.x;
-          g[2 * e][1] = v.y;
-          g[2 * e + 1][0] = v.z;
-          g[2 * e + 1][1] = v.w;
-        } else {
-          g[4 * e][0] = v.x;
-          g[4 * e + 1][0] = v.y;
-          g[4 * e + 2][0] = v.z;
-          g[4 * e + 3][0] = v.w;
-        }
-      }
+      for (int c = 2; c < 16; ++c) m = absmax2(m, g[c][k]);
+      m = absmax2(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      const uint32_t a = m & 0x7fff7fffu;  // |bf16| bits of the group's absmax, two rows
+      // byte = max(exp - qexp, 0) + (mant > thr), both rows of the pair at once; 0x7E for an all-zero group
+      const uint32_t ex2 = (a >> 7) & 0x00ff00ffu;
+      const uint32_t gt2 = (((a & 0x007f007fu) + up.add2) >> 7) & 0x00010001u;
+      const uint32_t b2 = __vmaxu2(ex2, up.q2) - up.q2 + gt2;
+      mult[k] = (0x00fe00feu - b2) << 7;  // bf16x2 of 2^(127-byte)
+      // an all-zero group has b2 == 0 (exp 0 < qexp, mant 0): add 0x7E exactly there
+      const uint32_t nz = __vminu2(a, 0x00010001u);  // 1 where the row's absmax is non-zero
+      sfb[k] = b2 + 0x007e007eu - nz * 0x7eu;
+    }
 
-      // ---- absmax per row over the 32-group (16 local channels + the partner lane), scale byte, multiplier
-      const uint32_t q2 = (fmt == 4) ? 0x00020002u : ((fmt == 6) ? 0x00040004u : 0x00080008u);  // log2floor(QMAX)
-      const uint32_t add2 = (fmt == 4) ? (63u * 0x00010001u) : (31u * 0x00010001u);             // 127 - thr, thr = 64 | 96
-      uint32_t mult[RW];
-      uint32_t sfb[RW];
+    // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row, 4 bytes apart)
+    if (meta & 128u) {
+      const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
+      uint8_t* d = up.sfp + sfoff;
 #pragma unroll
       for (int k = 0; k < RW; ++k) {
-        uint32_t m = absmax2(g[0][k], g[1][k]);
-#pragma unroll
-        for (int c = 2; c < 16; ++c) m = absmax2(m, g[c][k]);
-        m = absmax2(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        const uint32_t a = m & 0x7fff7fffu;  // |bf16| bits of the group's absmax, two rows
-        // byte = max(exp - qexp, 0) + (mant > thr), both rows of the pair at once; 0x7E for an all-zero group
-        const uint32_t ex2 = (a >> 7) & 0x00ff00ffu;
-        const uint32_t gt2 = (((a & 0x007f007fu) + add2) >> 7) & 0x00010001u;
-        const uint32_t b2 = __vmaxu2(ex2, q2) - q2 + gt2;
-        mult[k] = (0x00fe00feu - b2) << 7;  // bf16x2 of 2^(127-byte)
-        const uint32_t z = __vcmpeq2(a, 0u);
-        sfb[k] = (b2 & ~z) | (0x007e007eu & z);
+        d[8 * k] = (uint8_t)sfb[k];
+        d[8 * k + 4] = (uint8_t)(sfb[k] >> 16);
       }
-
-      // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row)
-      if (meta & 128u) {
-        uint8_t* d = p.sf[sg] + (sfrow * (uint32_t)p.katoms[sg] + sfin + cx.sfo);
-#pragma unroll
-        for (int k = 0; k < RW; ++k) {
-          d[8 * k] = (uint8_t)sfb[k];
-          d[8 * k + 4] = (uint8_t)(sfb[k] >> 16);
-        }
-      }
-
-      // ---- convert + store: 16 codes per row, contiguous bytes
-      const int64_t rbytes = p.rowbytes[sg];
-      uint8_t* dst = p.q[sg] + ((int64_t)row0 * rbytes + cx.qoff);
-      const int64_t rstride = 32 * rbytes;
-      const int nstore = active ? nvalid : 0;
-      if (FULL && !active) {
-      } else if (fmt == 4) convert_store<4, R, FULL>(g, mult, dst, rstride, nstore);
-      else if (fmt == 6) convert_store<6, R, FULL>(g, mult, dst, rstride, nstore);
-      else convert_store<8, R, FULL>(g, mult, dst, rstride, nstore);
     }
-    if (t == 0) *s_next = (int)(claimed + 2u * gridDim.x);
-    __syncthreads();  // every read of xs is done before the next item's scatter overwrites it; publishes *s_next
+
+    // ---- convert + store: 16 codes per row, contiguous bytes
+    uint8_t* dst = up.qp + (uint64_t)(uint32_t)row0 * up.rbytes;
+    const int64_t rstride = (int64_t)(32u * up.rbytes);
+    const int nstore = active ? nvalid : 0;
+    if (FULL && !active) {
+    } else if (fmt == 4) convert_store<4, R, FULL>(g, mult, dst, rstride, nstore);
+    else if (fmt == 6) convert_store<6, R, FULL>(g, mult, dst, rstride, nstore);
+    else convert_store<8, R, FULL>(g, mult, dst, rstride, nstore);
   }
 };
 
-template <int R, int TMAX, int NLD, int NP, int MINB, bool WIDE>
+// One item, start to finish.  `pre` holds the item's rows on entry and the next item's rows on exit; returns the
+// next item's first row.  Schedule protocol: s_next[(n+1)&1] holds the first row of item n+1 (written during item
+// n-1, or before the loop for n == 0); thread 0 claims item n+2 and publishes it in s_next[n&1].
+// NBUF == 2: xs is double-buffered and ONE barrier per item suffices (the buffer written by item n+1 was last read by
+// item n-1, which every thread has left before it passes item n's barrier).
+template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT>
+__device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_t* xt, int row0, int n, int t, int T, int K8,
+                                             int nunits, uint32_t xs_a, uint32_t tab_a, uint32_t ctx_a,
+                                             uint4 (&pre)[NLD][R], int* s_next, const UnitCtx& ctx0, const UnitPtrs& up0) {
+  const int rows = (int)p.rows;
+  const int nvalid = FULL ? R : min(R, (rows - 1 - row0) / 32 + 1);
+  QK::template scatter<FULL, EXACT>(nvalid, t, T, K8, xs_a, tab_a, pre);
+  __syncthreads();
+  // the next item's rows: in flight during the compute below
+  const int next_row0 = s_next[(n + 1) & 1];
+  if (next_row0 < rows) {
+    if (next_row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, next_row0, t, T, K8, pre);
+    else QK::template prefetch<false, EXACT>(p, xt, next_row0, t, T, K8, pre);
+  }
+  // dynamic schedule: thread 0 claims the item after next now; the answer is needed one whole item later
+  unsigned int claimed = 0;
+  if (t == 0) claimed = atomicAdd(p.sched, 1u);
+
+  if constexpr (NP == 1) {
+    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid);
+  } else {
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps) {
+      if (ps * T >= nunits) break;
+      const uint4 cv = lds128(ctx_a + 16u * (uint32_t)(ps * T + t));
+      UnitCtx cx;
+      cx.meta = cv.x;
+      cx.qoff = cv.y;
+      cx.sfo = cv.z;
+      cx.xoff = cv.w;
+      const UnitPtrs up = QK::make_ptrs(p, cx);
+      QK::template compute_unit<FULL>(cx, up, xs_a, row0, nvalid);
+    }
+  }
+  if (t == 0) s_next[n & 1] = QK::item_row0((int)(claimed + 2u * gridDim.x), p.num_items, rows);
+  if constexpr (NBUF == 1) __syncthreads();  // every read of xs is done before the next item's scatter overwrites it
+  return next_row0;
+}
+
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT>
 __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
-  using QK = QuantKernel<R, NLD, NP, WIDE>;
+  static_assert(NBUF == 1 || (NBUF == 2 && TABMODE != 2), "absolute table addresses cannot follow a second xs buffer");
+  using QK = QuantKernel<R, NLD, NP, TABMODE>;
   const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
   extern __shared__ __align__(128) uint8_t smem[];
   const int K = p.K;
   const int K8 = K >> 3;
   const int nunits = K >> 4;
-  uint16_t* tab = reinterpret_cast<uint16_t*>(smem);
-  uint8_t* xs = smem + ((K * 2 + 127) & ~127);
-  const uint32_t xs_a = smem_addr(xs);
+  const uint32_t tab_a = smem_addr(smem);
+  const uint32_t xs_a = tab_a + (uint32_t)((K * QK::TABW + 127) & ~127);
+  const uint32_t xs_bytes = (uint32_t)K * QK::SLOT;
+  const uint32_t ctx_a = xs_a + NBUF * xs_bytes;  // NP > 1 only
   const int t = threadIdx.x;
   const int rows = (int)p.rows;
 
@@ -379,47 +445,59 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   uint4 pre[NLD][R];  // prefetched rows of the next item
-  __shared__ int s_next;
+  __shared__ int s_next[2];
   const int num_items = p.num_items;
   // schedule: the first two rounds are static (item = blockIdx.x, blockIdx.x + gridDim.x), later items are claimed
   // from a global counter one item ahead of their prefetch, so SMs that run ahead simply take more items
-  int item = blockIdx.x;
-  int row0 = item < num_items ? QK::item_row0(item) : rows;
+  int row0 = QK::item_row0((int)blockIdx.x, num_items, rows);
+  if (t == 0) s_next[1] = QK::item_row0((int)(blockIdx.x + gridDim.x), num_items, rows);
 
-  // ---- one-time per CTA: inverse permutation as swizzled slot offsets, eight entries per step
+  // ---- one-time per CTA: inverse permutation as swizzled slot positions.  Eight consecutive permuted positions
+  // j = 8*j8 + e occupy 8*SLOT contiguous bytes of xs whose chunks share one swizzle mask, so position e is at
+  // base ^ (e * SLOT).
   for (int j8 = t; j8 < K8; j8 += T) {
     const uint4 iv = __ldg(reinterpret_cast<const uint4*>(p.idx) + j8);
     const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
+    const uint32_t pc0 = (uint32_t)j8 * (QK::SLOT / 2);  // first 16-byte chunk of the eight slots
+    const uint32_t base = ((pc0 ^ ((pc0 >> 3) & QK::SWM)) << 4) + (TABMODE == 2 ? xs_a : 0u);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const uint32_t j = (uint32_t)j8 * 8u + e;
       const uint32_t c = (e & 1) ? (ivw[e >> 1] >> 16) : (ivw[e >> 1] & 0xffffu);
-      const uint32_t pc = (j * QK::SLOT) >> 4;  // 16-byte chunk of slot j
-      const uint32_t off = ((pc ^ ((pc >> 3) & QK::SWM)) << 4) | ((j * QK::SLOT) & 15u);
-      tab[c] = (uint16_t)(WIDE ? (off >> 2) : off);
+      const uint32_t pos = base ^ (uint32_t)(e * QK::SLOT);
+      if constexpr (TABMODE == 2) sts32(tab_a + 4u * c, pos);
+      else asm volatile("st.shared.u16 [%0], %1;" ::"r"(tab_a + 2u * c), "h"((uint16_t)(TABMODE == 1 ? (pos >> 2) : pos)) : "memory");
     }
   }
-  // ---- one-time per thread: what it needs to know about its compute units
-  const UnitCtx ctx0 = QK::make_ctx(p, 0, t, T, nunits);
+  // ---- one-time per thread (NP == 1) or per CTA (NP > 1, in shared memory): the compute units' contexts
+  UnitCtx ctx0 = QK::make_ctx(p, t, nunits);
+  UnitPtrs up0 = QK::make_ptrs(p, ctx0);
+  if constexpr (NP > 1) {
+    for (int u = t; u < NP * T; u += T) {
+      const UnitCtx cx = QK::make_ctx(p, u, nunits);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ctx_a + 16u * (uint32_t)u), "r"(cx.meta), "r"(cx.qoff),
+                   "r"(cx.sfo), "r"(cx.xoff)
+                   : "memory");
+    }
+  }
+  const uint16_t* xt = p.x + 8 * t;
   // ... and wait for the previous kernel (which may still be producing X) only now: the table above depends on
   // reorder_index alone, which no kernel of this library writes, so it was built under the previous kernel's tail.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (row0 < rows) {
-    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true>(p, row0, t, T, K8, pre);
-    else QK::template prefetch<false>(p, row0, t, T, K8, pre);
+    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, row0, t, T, K8, pre);
+    else QK::template prefetch<false, EXACT>(p, xt, row0, t, T, K8, pre);
   }
   __syncthreads();
 
   // items are ordered by row: the first item past the last row ends this CTA's work (block-uniform)
-  int nitem = item + (int)gridDim.x;
+  int n = 0;
   while (row0 < rows) {
-    int nrow0 = nitem < num_items ? QK::item_row0(nitem) : rows;
-    if (nrow0 >= rows) nrow0 = -1;
-    if (row0 + 32 * (R - 1) < rows) QK::template process<true>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next, ctx0);
-    else QK::template process<false>(p, row0, t, T, K8, nunits, xs_a, tab, pre, nrow0, &s_next, ctx0);
-    if (nrow0 < 0) break;
-    row0 = nrow0;
-    nitem = s_next;
+    const uint32_t xs_cur = xs_a + ((NBUF == 2 && (n & 1)) ? xs_bytes : 0u);
+    if (row0 + 32 * (R - 1) < rows)
+      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0);
+    else
+      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0);
+    ++n;
   }
   // the last CTA to leave resets the schedule for the next launch that uses this slot
   if (t == 0) {
@@ -430,32 +508,34 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
 
 __device__ unsigned int g_quant_sched[64][2];  // rotating schedule slots (zero-initialised, self-resetting)
 
-template <int R>
-static size_t quant_smem_bytes(int K) {
-  return ((size_t)(K * 2 + 127) & ~(size_t)127) + (size_t)K * 2 * R;
-}
-
-template <int R, int TMAX, int NLD, int NP, int MINB, bool WIDE>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
   // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
-  const size_t smem = quant_smem_bytes<R>(p.K);
-  if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (!WIDE && (int64_t)p.K * 2 * R > 65536)) {
-    set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, TMAX,
-              NLD, NP, smem);
+  constexpr int TABW = (TABMODE == 2) ? 4 : 2;
+  const size_t smem = ((size_t)(p.K * TABW + 127) & ~(size_t)127) + (size_t)NBUF * p.K * 2 * R + (NP > 1 ? (size_t)NP * T * 16 : 0);
+  const int64_t xs_bytes = (int64_t)p.K * 2 * R;
+  if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (TABMODE == 0 && xs_bytes > 65536) ||
+      (TABMODE == 1 && xs_bytes > 4 * 65536)) {
+    set_error("reorder_quantize: K=%d does not fit the <%d,%d,%d,%d,%d> kernel (%zu bytes of shared memory)", p.K, R, TMAX,
+              NLD, NP, TABMODE * 10 + NBUF, smem);
     return MMX_ERR_INVALID;
   }
-  auto kern = reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, WIDE>;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
+  const bool exact = (int64_t)NLD * T * 8 == p.K && (int64_t)NP * T * 16 == p.K;
+  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true>
+                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false>;
+  static size_t attr_set[2] = {0, 0};
+  if (smem > attr_set[exact]) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
+    attr_set[exact] = smem;
   }
   static int occ_cached = 0;
   static size_t occ_smem = 0;
   static int occ_T = 0;
-  if (occ_cached == 0 || occ_smem != smem || occ_T != T) {
+  static bool occ_exact = false;
+  if (occ_cached == 0 || occ_smem != smem || occ_T != T || occ_exact != exact) {
     occ_T = T;
+    occ_exact = exact;
     int occ = 0;
     MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
     occ_cached = occ < 1 ? 1 : occ;
@@ -541,13 +621,22 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int force = (int)options().quant_rows;
-  // configuration by K: rows per item R, thread bound, 16-byte chunks per thread and row NLD, compute passes NP
-  if (force == 4 && K <= 4096) return launch_quant<4, 256, 2, 1, 3, false>(p, st);
-  if (K <= 4096) return launch_quant<2, 256, 2, 1, 4, false>(p, st);
-  if (K <= 8192) return launch_quant<2, 512, 2, 1, 2, false>(p, st);
-  if (K <= 14336) return launch_quant<2, 448, 4, 2, 2, false>(p, st);  // 72 registers at two CTAs per SM
-  if (K <= 16384) return launch_quant<2, 512, 4, 2, 2, false>(p, st);
-  return launch_quant<2, 1024, 4, 2, 1, true>(p, st);
+  const int var = (int)options().quant_variant;
+  // configuration by K: rows per item R, thread bound, 16-byte chunks per thread and row NLD, compute passes NP,
+  // minimum CTAs per SM (register bound), table encoding
+  // (measured on B200, profiles/r01_quantize_sweep.log: all K <= 4096 variants are within 3 % of each other; the
+  // double-buffered form wins by 2-3 % where one CTA owns the whole SM)
+  if (K <= 4096) {
+    if (force == 4) return launch_quant<4, 256, 2, 1, 2, 0, 2>(p, st);
+    if (var == 1) return launch_quant<2, 256, 2, 1, 4, 0, 2>(p, st);
+    return launch_quant<2, 256, 2, 1, 4, 0, 1>(p, st);
+  }
+  if (K <= 8192) {
+    if (force == 4) return launch_quant<4, 512, 2, 1, 1, 0, 2>(p, st);
+    return var == 1 ? launch_quant<2, 512, 2, 1, 2, 0, 1>(p, st) : launch_quant<2, 512, 2, 1, 2, 0, 2>(p, st);
+  }
+  if (K <= 16384) return var == 1 ? launch_quant<2, 1024, 2, 1, 1, 0, 1>(p, st) : launch_quant<2, 1024, 2, 1, 1, 0, 2>(p, st);
+  return launch_quant<2, 1024, 4, 2, 1, 1, 1>(p, st);
 }
 
 }  // namespace mmx

@@ -27,5 +27,5 @@ for off, ln, txt in seq:
 tot = sum(per.values()); tst = sum(pst.values())
 src = open(srcf).read().splitlines()
 print('sass', len(seq), 'ncu', len(body), 'total warp insts', tot, ('thread-inst/elem %.2f' % (tot * 32 / elems)) if elems else '')
-for ln, c in per.most_common(36):
+for ln, c in per.most_common(int(sys.argv[6]) if len(sys.argv)>6 else 36):
     print(f'{c:9d} {100*c/tot:5.1f}% stall {100*pst[ln]/max(tst,1):5.1f}%  L{ln}: {src[ln-1].strip()[:95] if ln and ln <= len(src) else ""}')
