@@ -82,6 +82,46 @@ int mmx_reorder_quantize_w4(const void* w, int64_t N, int K, const int16_t* idx,
                             uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
 
 /*
+ * mixedgemm.rmsnorm_quantize_x(X, W, eps, reorder_index, KN, KS, KO)    bindings.cpp:257-303
+ *   -> run_rmsnorm_bf16_mixed<32,K> -> rmsnorm_bf16_mixed_kernel          rmsnorm.cu:96-310
+ * RMSNorm fused into reorder+quantize:  y[r,c] = bf16((float(x[r,c]) * float(w[c])) * rinv[r]),
+ * rinv[r] = 1 / sqrt(sum_c x[r,c]^2 / K + eps), then exactly mmx_reorder_quantize_x on y.  Any K that
+ * mmx_reorder_quantize_x accepts (the reference: K in {3072,3584,4096,5120} and a reduction that is only
+ * right for 128 threads, rmsnorm.cu:166-173); codes are RNE like every other op (the reference rounds
+ * x/scale to an INTEGER first, rmsnorm.cu:264 -- a defect that is not reproduced).
+ * The sum of squares is taken in a fixed order so that the result does not depend on the launch shape:
+ * fp32 fma chain over each aligned 8-channel chunk, then a perfect binary tree over the chunk index.
+ *   x bf16 [M, K]   w bf16 [K]   outputs as mmx_reorder_quantize_x
+ */
+int mmx_rmsnorm_quantize_x(const void* x, const void* w, float eps, int64_t M, int K, const int16_t* idx, int KN, int KS,
+                           int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
+                           void* stream);
+
+/*
+ * mixedgemm.activate_quantize_x(A, B, KN, KS, KO)                       bindings.cpp:307-334
+ *   -> run_activate_bf16_mixed -> activate_quantize_kernel_with_cute_layout   activate.cu:510-552, 40-202
+ * v = silu(float(a)) * float(b) in fp32, NO channel permutation (the producer already emits down_proj's order),
+ * per-32 absmax, scale 2^ceil(log2(amax/QMAX)) (1.0 when amax <= 1e-6), codes RNE straight from fp32.
+ *   a, b bf16 [M, K], K = KN+KS+KO     outputs as mmx_reorder_quantize_x
+ */
+int mmx_activate_quantize_x(const void* a, const void* b, int64_t M, int KN, int KS, int KO, uint8_t* xn, uint8_t* xs,
+                            uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/*
+ * mixedgemm.downproj_quantize_w(W, KN, KS, KO)                          bindings.cpp:336-360
+ *   -> run_downproj_bf16_mixed -> downproj_quantize_kernel_with_cute_layout   activate.cu:554-592, 204-349
+ * mixedgemm.downproj_quantize_w4(W, KN, KS, KO)                         bindings.cpp:362-387
+ *   -> run_downproj_bf16_mxfp4 -> downproj_quantize_kernel_with_cute_layout_w4  activate.cu:594-632, 351-507
+ * Weight rows that are already in down_proj's channel order: the activate op's quantizer on float(w), to
+ * FP4 | FP6 | FP8 (_w) or FP4 in all three segments (_w4).  SF buffers are sized like activations,
+ * mmx_sf_bytes_act(N, Kseg) (bindings.cpp:346-348).
+ */
+int mmx_downproj_quantize_w(const void* w, int64_t N, int KN, int KS, int KO, uint8_t* wn, uint8_t* ws, uint8_t* wo,
+                            uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+int mmx_downproj_quantize_w4(const void* w, int64_t N, int KN, int KS, int KO, uint8_t* wn, uint8_t* ws, uint8_t* wo,
+                             uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/*
  * mixedgemm.matmul(AN,BN,AS,BS,AO,BO,SFAN,SFBN,SFAS,SFBS,SFAO,SFBO)      bindings.cpp:50-102
  *   -> matmul_w4_host (w4 != 0: W4A4 + W4A6 + W4A8)                        gemm.cu:53-78
  *   -> matmul_host    (w4 == 0: W4A4 + W6A6 + W8A8)                        gemm.cu:26-51

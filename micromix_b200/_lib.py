@@ -22,6 +22,10 @@ SYMBOLS = {
     "mmx_reorder_quantize_x": (_i32, _QUANT_ARGS),
     "mmx_reorder_quantize_w": (_i32, _QUANT_ARGS),
     "mmx_reorder_quantize_w4": (_i32, _QUANT_ARGS),
+    "mmx_rmsnorm_quantize_x": (_i32, [_vp, _vp, ctypes.c_float, _i64, _i32, _vp, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_activate_quantize_x": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_downproj_quantize_w": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_downproj_quantize_w4": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_matmul": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "mmx_launch_count": (_i64, []),
     "mmx_set_option": (_i32, [ctypes.c_char_p, _i64]),

@@ -43,6 +43,8 @@ struct QuantParams {
   int64_t rowbytes[3];
   uint8_t* q[3];
   uint8_t* sf[3];
+  const uint16_t* nw;  // RMSNorm weight (bf16 [K], ORIGINAL channel order); NORM kernels only
+  float eps;
 };
 
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
@@ -205,7 +207,13 @@ struct UnitPtrs {
 //           after the chunk swizzle.  Built once per CTA.
 //   xs      slot j holds the R rows of permuted channel j; 16-byte chunk p = j * 2R / 16 is stored at chunk
 //           p ^ ((p >> 3) & SWM) so that the lane-strided 128-bit reads of the compute phase are conflict-free.
-template <int R, int NLD, int NP, int TABMODE>
+//
+// NORM (mmx_rmsnorm_quantize_x): the rows are RMS-normalised on the way through.  The sum of squares of a row is taken
+// in a FIXED order that does not depend on the launch shape (oracle/mmx_oracle.c restates it): an fp32 fma chain over
+// each aligned 8-channel chunk (exactly the 16 bytes one thread loads), then a perfect binary tree over the chunk
+// index -- five shuffle levels inside a warp, the warp sums through shared memory, seven more levels redone by every
+// warp.  y = bf16((x * w) * rinv) is applied in the compute phase with the weight staged in PERMUTED order.
+template <int R, int NLD, int NP, int TABMODE, bool NORM = false>
 struct QuantKernel {
   static constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
   static constexpr int SLOT = 2 * R;        // bytes per slot
@@ -270,7 +278,39 @@ struct QuantKernel {
   // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
   template <bool FULL, bool EXACT>
   static __device__ __forceinline__ void scatter(int nvalid, int t, int T, int K8, uint32_t xs_a, uint32_t tab_a,
-                                                 const uint4 (&pre)[NLD][R]) {
+                                                 const uint4 (&pre)[NLD][R], uint32_t ss_a = 0) {
+    if constexpr (NORM) {
+      // sum of squares: chunk c8 = i*T + t is this thread's, the warp owns 32 consecutive chunks (T % 32 == 0)
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        const int c8 = i * T + t;
+        float ssq[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          float acc = 0.0f;
+          if ((EXACT || c8 < K8) && (FULL || j < nvalid)) {
+            const uint32_t wv[4] = {pre[i][j].x, pre[i][j].y, pre[i][j].z, pre[i][j].w};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const float lo = __uint_as_float(wv[m] << 16), hi = __uint_as_float(wv[m] & 0xffff0000u);
+              acc = __fmaf_rn(lo, lo, acc);
+              acc = __fmaf_rn(hi, hi, acc);
+            }
+          }
+          ssq[j] = acc;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) ssq[j] = __fadd_rn(ssq[j], __shfl_xor_sync(0xffffffffu, ssq[j], d));
+        }
+        if ((t & 31) == 0) {
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(ss_a + 4u * (uint32_t)(j * 128 + ((i * T + t) >> 5))), "f"(ssq[j]) : "memory");
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < NLD; ++i) {
       const int c8 = i * T + t;
@@ -316,7 +356,7 @@ struct QuantKernel {
   // lanes past the last unit compute on unit 0 and store nothing.
   template <bool FULL>
   static __device__ __forceinline__ void compute_unit(const UnitCtx& cx, const UnitPtrs& up, uint32_t xs_a, int row0,
-                                                      int nvalid) {
+                                                      int nvalid, uint32_t wp_a = 0, const float* rinv = nullptr) {
     const uint32_t meta = cx.meta;
     const bool active = (meta & 64u) != 0;
     const int fmt = (int)(meta & 15u);
@@ -335,6 +375,23 @@ struct QuantKernel {
         g[4 * e + 1][0] = v.y;
         g[4 * e + 2][0] = v.z;
         g[4 * e + 3][0] = v.w;
+      }
+    }
+
+    if constexpr (NORM) {
+      // y = bf16((x * w) * rinv): wp_a points at the 16 permuted weights of this unit (bf16, 32 bytes)
+      const uint4 wa = lds128(wp_a), wb = lds128(wp_a + 16u);
+      const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float wv = __uint_as_float((c & 1) ? (ww[c >> 1] & 0xffff0000u) : (ww[c >> 1] << 16));
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+          const float y0 = __fmul_rn(__fmul_rn(__uint_as_float(g[c][k] << 16), wv), rinv[2 * k]);
+          const float y1 = __fmul_rn(__fmul_rn(__uint_as_float(g[c][k] & 0xffff0000u), wv), rinv[2 * k + 1]);
+          const __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
+          g[c][k] = *reinterpret_cast<const uint32_t*>(&y);
+        }
       }
     }
 
@@ -385,14 +442,31 @@ struct QuantKernel {
 // n-1, or before the loop for n == 0); thread 0 claims item n+2 and publishes it in s_next[n&1].
 // NBUF == 2: xs is double-buffered and ONE barrier per item suffices (the buffer written by item n+1 was last read by
 // item n-1, which every thread has left before it passes item n's barrier).
-template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT>
+// NORM: ss_a = this item's warp sums of squares [R][128] fp32 (double-buffered with xs), wp_unit = this thread's 16
+// permuted RMSNorm weights.
+template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT, bool NORM>
 __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_t* xt, int row0, int n, int t, int T, int K8,
                                              int nunits, uint32_t xs_a, uint32_t tab_a, uint32_t ctx_a,
-                                             uint4 (&pre)[NLD][R], int* s_next, const UnitCtx& ctx0, const UnitPtrs& up0) {
+                                             uint4 (&pre)[NLD][R], int* s_next, const UnitCtx& ctx0, const UnitPtrs& up0,
+                                             uint32_t ss_a, uint32_t wp_unit) {
   const int rows = (int)p.rows;
   const int nvalid = FULL ? R : min(R, (rows - 1 - row0) / 32 + 1);
-  QK::template scatter<FULL, EXACT>(nvalid, t, T, K8, xs_a, tab_a, pre);
+  QK::template scatter<FULL, EXACT>(nvalid, t, T, K8, xs_a, tab_a, pre, ss_a);
   __syncthreads();
+  float rinv[R];
+  if constexpr (NORM) {
+    // the top seven levels of the tree over the chunk index: 128 warp sums per row (unused ones are zero), four
+    // consecutive ones per lane, then five shuffle levels.  Every warp redoes it: cheaper than a second barrier.
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint4 v = lds128(ss_a + (uint32_t)(j * 512 + (t & 31) * 16));
+      float sum = __fadd_rn(__fadd_rn(__uint_as_float(v.x), __uint_as_float(v.y)),
+                            __fadd_rn(__uint_as_float(v.z), __uint_as_float(v.w)));
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, d));
+      rinv[j] = __frcp_rn(__fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)p.K), p.eps)));
+    }
+  }
   // the next item's rows: in flight during the compute below
   const int next_row0 = s_next[(n + 1) & 1];
   if (next_row0 < rows) {
@@ -404,7 +478,7 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
   if (t == 0) claimed = atomicAdd(p.sched, 1u);
 
   if constexpr (NP == 1) {
-    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid);
+    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid, wp_unit, rinv);
   } else {
 #pragma unroll
     for (int ps = 0; ps < NP; ++ps) {
@@ -424,11 +498,12 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
   return next_row0;
 }
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT, bool NORM>
 __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
   static_assert(NBUF == 1 || (NBUF == 2 && TABMODE != 2), "absolute table addresses cannot follow a second xs buffer");
-  using QK = QuantKernel<R, NLD, NP, TABMODE>;
+  static_assert(!NORM || NP == 1, "the fused RMSNorm keeps a thread's weights addressable by thread index");
+  using QK = QuantKernel<R, NLD, NP, TABMODE, NORM>;
   const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
   extern __shared__ __align__(128) uint8_t smem[];
   const int K = p.K;
@@ -438,6 +513,8 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   const uint32_t xs_a = tab_a + (uint32_t)((K * QK::TABW + 127) & ~127);
   const uint32_t xs_bytes = (uint32_t)K * QK::SLOT;
   const uint32_t ctx_a = xs_a + NBUF * xs_bytes;  // NP > 1 only
+  const uint32_t wp_a = ctx_a;                    // NORM only (NP == 1): bf16 weights in permuted order [K]
+  const uint32_t ss_a = wp_a + (uint32_t)K * 2u;  // NORM only: warp sums of squares [NBUF][R][128] fp32
   const int t = threadIdx.x;
   const int rows = (int)p.rows;
 
@@ -467,6 +544,20 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
       if constexpr (TABMODE == 2) sts32(tab_a + 4u * c, pos);
       else asm volatile("st.shared.u16 [%0], %1;" ::"r"(tab_a + 2u * c), "h"((uint16_t)(TABMODE == 1 ? (pos >> 2) : pos)) : "memory");
     }
+    if constexpr (NORM) {  // the weights of permuted channels 8*j8 .. 8*j8+7
+      uint32_t wq[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t lo = __ldg(p.nw + (ivw[e] & 0xffffu)), hi = __ldg(p.nw + (ivw[e] >> 16));
+        wq[e] = lo | (hi << 16);
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wp_a + 16u * (uint32_t)j8), "r"(wq[0]), "r"(wq[1]),
+                   "r"(wq[2]), "r"(wq[3])
+                   : "memory");
+    }
+  }
+  if constexpr (NORM) {
+    for (int i = t; i < NBUF * R * 128; i += T) sts32(ss_a + 4u * (uint32_t)i, 0u);
   }
   // ---- one-time per thread (NP == 1) or per CTA (NP > 1, in shared memory): the compute units' contexts
   UnitCtx ctx0 = QK::make_ctx(p, t, nunits);
@@ -479,6 +570,7 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
                    : "memory");
     }
   }
+  const uint32_t wp_unit = wp_a + ((ctx0.meta & 64u) ? 32u * (uint32_t)t : 0u);
   const uint16_t* xt = p.x + 8 * t;
   // ... and wait for the previous kernel (which may still be producing X) only now: the table above depends on
   // reorder_index alone, which no kernel of this library writes, so it was built under the previous kernel's tail.
@@ -493,10 +585,11 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   int n = 0;
   while (row0 < rows) {
     const uint32_t xs_cur = xs_a + ((NBUF == 2 && (n & 1)) ? xs_bytes : 0u);
+    const uint32_t ss_cur = ss_a + ((NBUF == 2 && (n & 1)) ? (uint32_t)(R * 512) : 0u);
     if (row0 + 32 * (R - 1) < rows)
-      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT, NORM>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit);
     else
-      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit);
     ++n;
   }
   // the last CTA to leave resets the schedule for the next launch that uses this slot
@@ -508,12 +601,13 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
 
 __device__ unsigned int g_quant_sched[64][2];  // rotating schedule slots (zero-initialised, self-resetting)
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool NORM = false>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
   // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
   constexpr int TABW = (TABMODE == 2) ? 4 : 2;
-  const size_t smem = ((size_t)(p.K * TABW + 127) & ~(size_t)127) + (size_t)NBUF * p.K * 2 * R + (NP > 1 ? (size_t)NP * T * 16 : 0);
+  const size_t smem = ((size_t)(p.K * TABW + 127) & ~(size_t)127) + (size_t)NBUF * p.K * 2 * R + (NP > 1 ? (size_t)NP * T * 16 : 0) +
+                      (NORM ? (size_t)p.K * 2 + (size_t)NBUF * R * 512 : 0);
   const int64_t xs_bytes = (int64_t)p.K * 2 * R;
   if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (TABMODE == 0 && xs_bytes > 65536) ||
       (TABMODE == 1 && xs_bytes > 4 * 65536)) {
@@ -522,8 +616,8 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
     return MMX_ERR_INVALID;
   }
   const bool exact = (int64_t)NLD * T * 8 == p.K && (int64_t)NP * T * 16 == p.K;
-  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true>
-                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false>;
+  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM>
+                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM>;
   static size_t attr_set[2] = {0, 0};
   if (smem > attr_set[exact]) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -569,7 +663,8 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
 
 static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO,
                             const int fmt[3], uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1,
-                            uint8_t* s2, void* stream) {
+                            uint8_t* s2, void* stream, const void* norm_w = nullptr, float eps = 0.0f,
+                            bool norm = false) {
   if (rows < 0 || K <= 0 || KN < 0 || KS < 0 || KO < 0 || KN + KS + KO != K) {
     set_error("reorder_quantize: bad shape rows=%lld K=%d (KN,KS,KO)=(%d,%d,%d)", (long long)rows, K, KN, KS, KO);
     return MMX_ERR_INVALID;
@@ -603,8 +698,18 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
     set_error("reorder_quantize: pointers must be 16-byte aligned");
     return MMX_ERR_INVALID;
   }
+  if (norm && (!norm_w || ((uintptr_t)norm_w & 15))) {
+    set_error("rmsnorm_quantize_x: the norm weight must be a non-null 16-byte aligned pointer");
+    return MMX_ERR_INVALID;
+  }
+  if (norm && K > 16384) {
+    set_error("rmsnorm_quantize_x: K=%d exceeds the supported 16384", K);
+    return MMX_ERR_INVALID;
+  }
   if (rows == 0) return MMX_OK;
   QuantParams p;
+  p.nw = static_cast<const uint16_t*>(norm_w);
+  p.eps = eps;
   p.x = static_cast<const uint16_t*>(x);
   p.idx = idx;
   p.rows = rows;
@@ -626,6 +731,11 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   // minimum CTAs per SM (register bound), table encoding
   // (measured on B200, profiles/r01_quantize_sweep.log: all K <= 4096 variants are within 3 % of each other; the
   // double-buffered form wins by 2-3 % where one CTA owns the whole SM)
+  if (norm) {
+    if (K <= 4096) return launch_quant<2, 256, 2, 1, 3, 0, 1, true>(p, st);
+    if (K <= 8192) return launch_quant<2, 512, 2, 1, 1, 0, 2, true>(p, st);
+    return launch_quant<2, 1024, 2, 1, 1, 0, 2, true>(p, st);
+  }
   if (K <= 4096) {
     if (force == 4) return launch_quant<4, 256, 2, 1, 2, 0, 2>(p, st);
     if (var == 1) return launch_quant<2, 256, 2, 1, 4, 0, 2>(p, st);
@@ -660,4 +770,11 @@ extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_w4(co
                                        void* stream) {
   const int fmt[3] = {4, 4, 4};
   return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int mmx_rmsnorm_quantize_x(const void* x, const void* w, float eps, int64_t M, int K, const int16_t* idx,
+                                      int KN, int KS, int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn,
+                                      uint8_t* sfs, uint8_t* sfo, void* stream) {
+  const int fmt[3] = {4, 6, 8};
+  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, w, eps, true);
 }

@@ -12,7 +12,9 @@ Differences from the reference, all deliberate:
   * inputs are validated (device, dtype, contiguity, shapes) -> ValueError/RuntimeError instead of UB;
   * kernels run on torch's current stream (the reference: legacy default stream) and are graph-capturable;
   * matmul: one launch, fp32 accumulation across all three segments, one bf16 rounding; C is not pre-zeroed;
-  * ops that are not on the hot path yet raise NotImplementedError (see DESIGN.md "next rows").
+  * rmsnorm_quantize_x implements the INTENDED semantics of the reference kernel (norm -> bf16 -> the reorder
+    quantizer) for any K <= 16384; the reference's own kernel rounds to integers and mis-reduces for K != 4096;
+  * the six flashinfer decode ops (bindings.cpp:418-674) are outside the hot path and absent.
 """
 from __future__ import annotations
 
@@ -151,19 +153,78 @@ def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None
     return out
 
 
-def _not_yet(name, where):
-    def f(*args, **kwargs):
-        raise NotImplementedError(
-            f"mixedgemm.{name} ({where}) is not called by any Python code of the reference and is a 'next' row of "
-            "the hot-path scope (SURVEY.md section 8f); it is not implemented yet.")
-    f.__name__ = name
-    return f
+def rmsnorm_quantize_x(X, W, eps, reorder_index, KN, KS, KO):
+    """RMSNorm fused into reorder+quantize (bindings.cpp:257-303): X bf16 [M, K], W bf16 [K] -> the six tensors of
+    reorder_quantize_x computed on bf16((x * w) * rsqrt(mean(x^2) + eps)).  Any K <= 16384 (the reference: four K)."""
+    lib = _lib.load()
+    _check_cuda("X", X, torch.bfloat16, 2)
+    _check_cuda("W", W, torch.bfloat16, 1)
+    _check_cuda("reorder_index", reorder_index, torch.int16, 1)
+    M, K = X.shape
+    KN, KS, KO = _check_split(K, KN, KS, KO)
+    if W.numel() != K or reorder_index.numel() != K:
+        raise ValueError(f"W and reorder_index must have K={K} entries, got {W.numel()} and {reorder_index.numel()}")
+    if W.device != X.device or reorder_index.device != X.device:
+        raise ValueError("W and reorder_index must live on the same device as X")
+    if K > 16384:
+        raise ValueError(f"rmsnorm_quantize_x supports K <= 16384, got {K}")
+    opts = dict(dtype=torch.uint8, device=X.device)
+    with torch.cuda.device(X.device):
+        q = [torch.empty((M, w), **opts) for w in (KN // 2, KS // 4 * 3, KO)]
+        sf = [torch.empty((int(lib.mmx_sf_bytes_act(M, k)),), **opts) for k in (KN, KS, KO)]
+        rc = 0
+        if M > 0:
+            rc = lib.mmx_rmsnorm_quantize_x(_ptr(X), _ptr(W), float(eps), M, K, _ptr(reorder_index), KN, KS, KO,
+                                            _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]),
+                                            _stream())
+    _lib.check(rc, "mmx_rmsnorm_quantize_x")
+    return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
 
 
-rmsnorm_quantize_x = _not_yet("rmsnorm_quantize_x", "bindings.cpp:257-303")
-activate_quantize_x = _not_yet("activate_quantize_x", "bindings.cpp:307-334")
-downproj_quantize_w = _not_yet("downproj_quantize_w", "bindings.cpp:336-360")
-downproj_quantize_w4 = _not_yet("downproj_quantize_w4", "bindings.cpp:362-387")
+def _rowwise(fn_name, tensors, names, KN, KS, KO, widths):
+    lib = _lib.load()
+    for n, t in zip(names, tensors):
+        _check_cuda(n, t, torch.bfloat16, 2)
+    rows, K = tensors[0].shape
+    for n, t in zip(names[1:], tensors[1:]):
+        if t.shape != tensors[0].shape or t.device != tensors[0].device:
+            raise ValueError(f"{n} must match {names[0]} in shape and device")
+    KN, KS, KO = int(KN), int(KS), int(KO)
+    if min(KN, KS, KO) < 0 or KN + KS + KO != K:
+        raise ValueError(f"KN+KS+KO must equal K={K}, got ({KN},{KS},{KO})")
+    if KN % 128 or KS % 128 or KO % 128:
+        raise ValueError(f"KN, KS, KO must be multiples of 128, got ({KN},{KS},{KO})")
+    dev = tensors[0].device
+    opts = dict(dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        q = [torch.empty((rows, w), **opts) for w in widths(KN, KS, KO)]
+        # all three ops size their scale buffers like activations (bindings.cpp:320-322, 346-348, 373-375)
+        sf = [torch.empty((int(lib.mmx_sf_bytes_act(rows, k)),), **opts) for k in (KN, KS, KO)]
+        rc = 0
+        if rows > 0:
+            rc = getattr(lib, fn_name)(*[_ptr(t) for t in tensors], rows, KN, KS, KO, _ptr(q[0]), _ptr(q[1]),
+                                       _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
+    _lib.check(rc, fn_name)
+    return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
+
+
+def activate_quantize_x(A, B, KN, KS, KO):
+    """SiLU(A) * B -> MX quantize without a permutation (bindings.cpp:307-334): A = gate, B = up, both bf16 [M, K]
+    already in down_proj's channel order -> (XN, XS, XO, SFXN, SFXS, SFXO)."""
+    return _rowwise("mmx_activate_quantize_x", (A, B), ("A", "B"), KN, KS, KO,
+                    lambda kn, ks, ko: (kn // 2, ks // 4 * 3, ko))
+
+
+def downproj_quantize_w(W, KN, KS, KO):
+    """Quantize already-ordered weight rows to FP4|FP6|FP8 (bindings.cpp:336-360)."""
+    return _rowwise("mmx_downproj_quantize_w", (W,), ("W",), KN, KS, KO,
+                    lambda kn, ks, ko: (kn // 2, ks // 4 * 3, ko))
+
+
+def downproj_quantize_w4(W, KN, KS, KO):
+    """Quantize already-ordered weight rows to MXFP4 in all three segments (bindings.cpp:362-387)."""
+    return _rowwise("mmx_downproj_quantize_w4", (W,), ("W",), KN, KS, KO,
+                    lambda kn, ks, ko: (kn // 2, ks // 2, ko // 2))
 
 
 def test_function():

@@ -61,6 +61,20 @@ def lib():
         L.mmxo_scale_byte_float.argtypes = [ctypes.c_uint16, ctypes.c_int]
         L.mmxo_scale_byte_float.restype = ctypes.c_int
         L.mmxo_num_threads.restype = ctypes.c_int
+        L.mmxo_cuda_log2f.argtypes = [ctypes.c_float]
+        L.mmxo_cuda_log2f.restype = ctypes.c_float
+        L.mmxo_act_scale_exp.argtypes = [ctypes.c_float, ctypes.c_int]
+        L.mmxo_act_scale_exp.restype = ctypes.c_int
+        L.mmxo_act_scale_exp_fast.argtypes = [ctypes.c_float, ctypes.c_int]
+        L.mmxo_act_scale_exp_fast.restype = ctypes.c_int
+        L.mmxo_check_scale_shortcut.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.mmxo_check_scale_shortcut.restype = ctypes.c_int64
+        L.mmxo_silu_mul.argtypes = [u16p, u16p, ctypes.c_int64, f32p]
+        L.mmxo_silu_mul.restype = None
+        L.mmxo_quantize_f32.argtypes = [f32p, ctypes.c_int64, ctypes.c_int] + [ctypes.c_int] * 6 + [u8p] * 6
+        L.mmxo_quantize_f32.restype = ctypes.c_int
+        L.mmxo_rmsnorm.argtypes = [u16p, u16p, ctypes.c_float, ctypes.c_int64, ctypes.c_int, u16p]
+        L.mmxo_rmsnorm.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -125,6 +139,56 @@ def reorder_quantize(x_bits: np.ndarray, idx: np.ndarray, KN: int, KS: int, KO: 
     if rc != 0:
         raise ValueError(f"mmxo_reorder_quantize rc={rc}")
     return (*q, *sf)
+
+
+# ------------------------------------------------------------------ ops without a permutation (activate.cu)
+def silu_mul(a_bits: np.ndarray, b_bits: np.ndarray) -> np.ndarray:
+    """fp32 silu(a) * b of activate.cu:29,107 with libm's expf (CUDA's ends in ex2.approx: not restatable)."""
+    a_bits = np.ascontiguousarray(a_bits, dtype=np.uint16)
+    b_bits = np.ascontiguousarray(b_bits, dtype=np.uint16)
+    out = np.empty(a_bits.shape, dtype=np.float32)
+    lib().mmxo_silu_mul(_p(a_bits, ctypes.c_uint16), _p(b_bits, ctypes.c_uint16), a_bits.size, _p(out, ctypes.c_float))
+    return out
+
+
+def quantize_f32(v: np.ndarray, KN: int, KS: int, KO: int, w4: bool = False, sf_fill: int = 0):
+    """The activate / downproj quantizer (activate.cu:109-176) on fp32 values [rows, K] already in segment order:
+    scale 2^ceil(log2f(amax/QMAX)) (1.0 when amax <= 1e-6), codes RNE straight from fp32.  SF buffers are sized like
+    activations for all three ops (bindings.cpp:320-322,346-348,373-375)."""
+    v = np.ascontiguousarray(v, dtype=np.float32)
+    rows, K = v.shape
+    assert KN + KS + KO == K
+    fm = FMT_W4 if w4 else FMT_X
+    q = [np.zeros((rows, packed_width(k, f)), dtype=np.uint8) for k, f in zip((KN, KS, KO), fm)]
+    sf = [np.full((sf_bytes(rows, k, True),), sf_fill, dtype=np.uint8) for k in (KN, KS, KO)]
+    rc = lib().mmxo_quantize_f32(_p(v, ctypes.c_float), rows, K, KN, KS, KO, *fm, *[_p(a, ctypes.c_uint8) for a in q],
+                                 *[_p(a, ctypes.c_uint8) for a in sf])
+    if rc != 0:
+        raise ValueError(f"mmxo_quantize_f32 rc={rc}")
+    return (*q, *sf)
+
+
+def downproj_quantize(w_bits: np.ndarray, KN: int, KS: int, KO: int, w4: bool):
+    """downproj_quantize_w / _w4 (activate.cu:204-507): bit-exact restatement (no transcendental but log2f)."""
+    return quantize_f32(bf16_bits_to_f32(w_bits), KN, KS, KO, w4)
+
+
+def rmsnorm(x_bits: np.ndarray, w_bits: np.ndarray, eps: float) -> np.ndarray:
+    """bf16((x * w) * rinv) with the fixed-order sum of squares (see mmx_oracle.c); returns bf16 bits [rows, K]."""
+    x_bits = np.ascontiguousarray(x_bits, dtype=np.uint16)
+    w_bits = np.ascontiguousarray(w_bits, dtype=np.uint16)
+    rows, K = x_bits.shape
+    y = np.empty_like(x_bits)
+    rc = lib().mmxo_rmsnorm(_p(x_bits, ctypes.c_uint16), _p(w_bits, ctypes.c_uint16), float(np.float32(eps)), rows, K,
+                            _p(y, ctypes.c_uint16))
+    if rc != 0:
+        raise ValueError(f"mmxo_rmsnorm rc={rc}")
+    return y
+
+
+def rmsnorm_quantize(x_bits, w_bits, eps, idx, KN, KS, KO):
+    """rmsnorm_quantize_x (bindings.cpp:257-303), intended semantics: norm -> bf16 -> reorder_quantize_x."""
+    return reorder_quantize(rmsnorm(x_bits, w_bits, eps), idx, KN, KS, KO, "x")
 
 
 def dequant(q: np.ndarray, sf: np.ndarray, rows: int, kseg: int, fmt: int) -> np.ndarray:

@@ -95,3 +95,30 @@ def golden_inputs(tag):
 
 def load_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "ref_reorder_golden.npz"))
+
+
+# ---- ops without a permutation (activate.cu): inputs and the cases whose reference-kernel outputs are committed in
+# tests/golden/ref_rowquant_golden.npz (generated on a B200 by tools/make_golden_rowquant.py)
+def make_gate_up(M: int, K: int, seed: int):
+    """gate ~ N(0, 1.5), up ~ N(0, 1) with a channel gain so that the FP8 segment carries outliers (bf16)."""
+    g = torch.Generator().manual_seed(seed)
+    gate = (torch.randn(M, K, generator=g) * 1.5).to(torch.bfloat16)
+    gain = 1.0 + 15.0 * (torch.arange(K, dtype=torch.float32) / K) ** 8
+    up = (torch.randn(M, K, generator=g) * gain).to(torch.bfloat16)
+    return gate, up
+
+
+# tag -> (mode, rows, split); mode 0 activate_quantize_x, 1 downproj_quantize_w, 2 downproj_quantize_w4.
+# KN and KN+KS are multiples of 512: the reference kernel's __syncthreads (activate.cu:187) is divergent otherwise.
+ROWQ_GOLDEN = {
+    "act_4096": (0, 300, (2560, 1024, 512)), "act_14336": (0, 130, (8704, 3584, 2048)),
+    "w_4096": (1, 257, (2560, 1024, 512)), "w4_4096": (2, 257, (2560, 1024, 512)),
+}
+
+
+def rowq_golden_inputs(tag):
+    mode, M, split = ROWQ_GOLDEN[tag]
+    K = sum(split)
+    if mode == 0:
+        return make_gate_up(M, K, seed=1000 + K)
+    return (make_weights(M, K, seed=2000 + K),)

@@ -49,6 +49,12 @@ def test_argument_validation_without_gpu(mmx_lib):
     rc = mmx_lib.mmx_matmul(*([None] * 12), 16, 100, 128, 0, 0, 1, None, None, None)
     assert rc == -1 and "multiple of 128" in _lib.last_error()
     assert mmx_lib.mmx_set_option(b"no_such_option", 1) == -1
+    rc = mmx_lib.mmx_activate_quantize_x(None, None, 4, 100, 100, 56, None, None, None, None, None, None, None)
+    assert rc == -1 and "multiples of 128" in _lib.last_error()
+    rc = mmx_lib.mmx_downproj_quantize_w4(None, 4, 128, 0, 0, None, None, None, None, None, None, None)
+    assert rc == -1 and "null" in _lib.last_error()
+    rc = mmx_lib.mmx_rmsnorm_quantize_x(None, None, 1e-5, 4, 256, None, 128, 128, 0, *([None] * 7))
+    assert rc == -1 and "null" in _lib.last_error()
 
 
 def test_shim_mirrors_reference_surface():
@@ -59,13 +65,14 @@ def test_shim_mirrors_reference_surface():
         "reorder_quantize_x": ["X", "reorder_index", "KN", "KS", "KO"],
         "reorder_quantize_w": ["W", "reorder_index", "KN", "KS", "KO"],
         "reorder_quantize_w4": ["W", "reorder_index", "KN", "KS", "KO"],
+        "rmsnorm_quantize_x": ["X", "W", "eps", "reorder_index", "KN", "KS", "KO"],
+        "activate_quantize_x": ["A", "B", "KN", "KS", "KO"],
+        "downproj_quantize_w": ["W", "KN", "KS", "KO"],
+        "downproj_quantize_w4": ["W", "KN", "KS", "KO"],
     }
     for name, args in ref_ops.items():
         params = list(inspect.signature(getattr(mixedgemm, name)).parameters)
         assert params[:len(args)] == args, name
-    for name in ("rmsnorm_quantize_x", "activate_quantize_x", "downproj_quantize_w", "downproj_quantize_w4"):
-        with pytest.raises(NotImplementedError):
-            getattr(mixedgemm, name)()
     assert mixedgemm.test_function() == "Hello from test_function!"
 
 
@@ -77,6 +84,12 @@ def test_no_cpu_fallback():
         mixedgemm.reorder_quantize_x(x, idx, 128, 0, 0)
     with pytest.raises(RuntimeError, match="CUDA"):
         mixedgemm.matmul(*[torch.zeros(4, 64, dtype=torch.uint8)] * 12)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mixedgemm.activate_quantize_x(x, x, 128, 0, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mixedgemm.downproj_quantize_w(x, 128, 0, 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mixedgemm.rmsnorm_quantize_x(x, x[0], 1e-5, idx, 128, 0, 0)
 
 
 def test_product_does_not_import_oracle():

@@ -151,3 +151,62 @@ def test_matmul_oracle_chain_vs_fused_and_identity_scale():
     assert mx <= 2e-2 and mean <= 1e-3  # inter-segment bf16 roundings of the reference: a couple of bf16 ulps
     f64 = O.matmul(*args, chain=False, f64=True)
     assert H.rel_err(fused, f64)[0] <= 8e-3  # at most one bf16 ulp from fp32 vs fp64 accumulation
+
+
+# ---------------------------------------------------------------- activate.cu / rmsnorm.cu restatements
+def test_cuda_log2f_restatement():
+    """mmxo_cuda_log2f restates the PTX nvcc 12.9 emits for log2f: exact on powers of two, within 2 ulp elsewhere."""
+    import math
+    L = O.lib()
+    for e in range(-126, 128):
+        assert L.mmxo_cuda_log2f(float(2.0 ** e)) == float(e)
+    rng = np.random.default_rng(0)
+    xs = np.exp(rng.uniform(-60, 60, 4000)).astype(np.float32)
+    for x in xs:
+        got, want = L.mmxo_cuda_log2f(float(x)), math.log2(float(x))
+        assert abs(got - want) <= 2.5 * np.spacing(np.float32(abs(want) + 1e-30)), (x, got, want)
+    # KATs read off a B200 run of the reference's kernel are in tests/golden/ref_rowquant_golden.npz (scale bytes)
+
+
+def test_scale_exponent_shortcut_is_exact():
+    """The CUDA kernel reads ceil(log2(amax/QMAX)) off the exponent unless the ratio is within 2^-13 above a power of
+    two; the polynomial must agree there for every exponent (65536 mantissas next to each end of the range)."""
+    assert O.lib().mmxo_check_scale_shortcut(-100, 128) == 0
+    L = O.lib()
+    rng = np.random.default_rng(1)
+    for fmt in (4, 6, 8):
+        for a in np.exp(rng.uniform(-13, 80, 3000)).astype(np.float32):
+            assert L.mmxo_act_scale_exp(float(a), fmt) == L.mmxo_act_scale_exp_fast(float(a), fmt)
+
+
+def test_quantize_f32_agrees_with_reorder_oracle_on_bf16_inputs():
+    """On bf16 inputs with an identity permutation the activate.cu recipe and the reorder.cu recipe coincide wherever
+    the group maximum is > 1e-6 (they differ only in the all-zero / tiny rule: scale 1.0 vs 0.5)."""
+    M, K, split = 64, 1024, (512, 256, 256)
+    idx = H.make_index(K, identity=True)
+    x = H.make_activations(M, K, idx)
+    a = O.reorder_quantize(H.bits(x), idx.numpy(), *split, "x")
+    b = O.quantize_f32(O.bf16_bits_to_f32(H.bits(x)), *split)
+    for i in range(3):
+        assert np.array_equal(a[i], b[i])
+    for i, k in enumerate(split):
+        m = O.sf_valid_mask(M, k, a[3 + i].shape[0])
+        assert np.array_equal(a[3 + i][m], b[3 + i][m])
+    z = O.quantize_f32(np.zeros((1, 128), dtype=np.float32), 128, 0, 0)
+    assert z[3][0] == 0x7F and not z[0].any()
+
+
+def test_rmsnorm_oracle_is_an_rmsnorm():
+    import torch
+    M, K = 16, 4096
+    x = H.make_activations(M, K, H.make_index(K))
+    g = torch.Generator().manual_seed(1)
+    w = (1.0 + 0.1 * torch.randn(K, generator=g)).to(torch.bfloat16)
+    y = O.bf16_bits_to_f32(O.rmsnorm(H.bits(x), H.bits(w), 1e-5))
+    xf = x.float()
+    t = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()).numpy()
+    assert np.all(np.abs(y - t) <= 2.0 ** -7 * np.abs(t) + 1e-30)
+    # the tree sum is exact on data whose squares add without rounding
+    ones = np.full((1, 256), 0x3F80, dtype=np.uint16)
+    y1 = O.rmsnorm(ones, ones[0], 0.0)
+    assert np.all(y1 == 0x3F80)
