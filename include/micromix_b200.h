@@ -137,11 +137,44 @@ int mmx_matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const ui
                const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
                const void* bias, void* c, void* stream);
 
+/*
+ * Row-parallel linear fused with its all-reduce over NVLink peer memory (tensor parallelism inside one NVSwitch box).
+ * The reference has no counterpart: model/parallel_utils.py:89-163 only places whole layers on different GPUs.
+ * BASELINE.json's north_star asks for row-parallel o_proj / down_proj whose bf16 partials are summed across ranks;
+ * mmx_matmul + ncclAllReduce is the plain way, this is the fused one (micromix_b200/csrc/tp_reduce.cu):
+ * the GEMM epilogue pushes each partial tile to the rank that owns it while the tensor cores run the next tile, and
+ * a co-resident reducer kernel sums a tile as soon as all tp partials have landed and writes it to every rank's C.
+ *
+ *   mmx_peer_alloc / _open / _close / _free   one zero-filled device workspace per rank + its 64-byte cudaIpc handle;
+ *       the host code exchanges the handles (torch.distributed all_gather_object) and opens the peers' workspaces.
+ *   mmx_tp_workspace_bytes(M_cap, N_cap, tp)   size of that workspace for outputs up to M_cap x N_cap.
+ *   mmx_tp_ctx_create(ws, tp, rank, ...)       ws[d] = rank d's workspace as mapped in THIS process (ws[rank] = own).
+ *   mmx_matmul_allreduce(ctx, <mmx_matmul operands of this rank's K shard>, M, N, KN, KS, KO, w4, bias, &c, stream)
+ *       C = sum over ranks of this rank's partial product; *c receives a pointer INTO the own workspace holding the
+ *       full bf16 [M, N] result (valid until the second next call on this context); bias is added by the rank
+ *       that passes it (pass it on rank 0 only).  All ranks must issue the same call sequence on one stream.
+ *   mmx_tp_status(ctx, &w)                     0 = clean; bit 0 / bit 1 = a cross-rank wait timed out
+ *       (option "tp_timeout_ms", default 10 s) -- a lost peer produces an error word, never a hung GPU.
+ */
+#define MMX_PEER_HANDLE_BYTES 64
+int mmx_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle);
+int mmx_peer_open(const uint8_t* handle, void** ptr);
+int mmx_peer_close(void* ptr);
+int mmx_peer_free(void* ptr);
+int64_t mmx_tp_workspace_bytes(int64_t M_cap, int64_t N_cap, int tp);
+int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, void** ctx);
+int mmx_tp_ctx_destroy(void* ctx);
+int mmx_tp_status(void* ctx, uint32_t* out);
+int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                         const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                         const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
+                         int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
 int64_t mmx_launch_count(void);
 
 /* Debug/bring-up knobs (tests only): key in {"gemm_watchdog","gemm_tx_mode","quant_rows",
- * "gemm_ctas","gemm_cta_group"}. */
+ * "gemm_ctas","gemm_cta_group","pdl","tp_reduce_ctas","tp_timeout_ms", ...}. */
 int mmx_set_option(const char* key, int64_t value);
 
 /* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n). */

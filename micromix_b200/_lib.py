@@ -27,6 +27,16 @@ SYMBOLS = {
     "mmx_downproj_quantize_w": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_downproj_quantize_w4": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_matmul": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_peer_alloc": (_i32, [_i64, ctypes.POINTER(_vp), ctypes.c_char_p]),
+    "mmx_peer_open": (_i32, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "mmx_peer_close": (_i32, [_vp]),
+    "mmx_peer_free": (_i32, [_vp]),
+    "mmx_tp_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "mmx_tp_ctx_create": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, ctypes.POINTER(_vp)]),
+    "mmx_tp_ctx_destroy": (_i32, [_vp]),
+    "mmx_tp_status": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
+    "mmx_matmul_allreduce": (_i32, [_vp] + [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp,
+                                                       ctypes.POINTER(_vp), _vp]),
     "mmx_launch_count": (_i64, []),
     "mmx_set_option": (_i32, [ctypes.c_char_p, _i64]),
     "mmx_gemm_debug_status": (_i32, [ctypes.POINTER(ctypes.c_uint32), _i32]),

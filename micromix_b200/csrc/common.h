@@ -24,6 +24,8 @@ struct Options {
   int64_t pdl = 1;            // 1: kernels are launched with programmatic stream serialization (prologue overlap)
   int64_t gemm_raster = 0;    // 0: auto, 1: force M-fastest tile order, 2: force N-fastest
   int64_t gemm_cta_group = 0; // 0: auto (pairs when M > 128), 1: force the single-CTA kernel
+  int64_t tp_reduce_ctas = 0; // 0: one reducer CTA per SM, else cap the tile_allreduce_kernel grid (single-GPU tests)
+  int64_t tp_timeout_ms = 10000;  // bound on every cross-rank spin of tile_allreduce_kernel (a lost peer cannot hang the GPU)
 };
 Options& options();
 
@@ -37,6 +39,23 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     cudaError_t _e = (expr);                                  \
     if (_e != cudaSuccess) return ::mmx::cuda_fail(_e, #expr); \
   } while (0)
+
+constexpr int kMaxTp = 8;  // ranks of one NVSwitch box
+
+// Fused row-parallel GEMM -> all-reduce: what tp_reduce.cu hands to gemm.cu's matmul_impl (see RsParams in gemm.cu).
+struct RsLaunch {
+  const void* dst_maps;      // CUtensorMap[tp]: MY slot in rank d's staging buffer as bf16 [own_tiles_cap * 256, 256]
+  uint32_t* tile_flags[kMaxTp];  // rank d's arrival counters for the tiles it owns (this call's parity)
+  int tp, rank;
+  int64_t own_tiles_cap;     // staging tiles (256 rows each) per (rank, slot)
+  // filled in by matmul_impl: the tile geometry the reducer must mirror
+  int cg, m_tiles, n_tiles, n_fastest;
+};
+int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                const void* bias, void* c, void* stream, RsLaunch* rsl);
+int encode_store_tmap(void* ptr, int64_t rows, int64_t cols, void* out /* CUtensorMap* */);
 
 int sm_count();       // cached multiprocessor count of the current device
 bool device_is_sm100();

@@ -103,6 +103,20 @@ struct alignas(64) TmapSet {
   CUtensorMap c;       // bf16 [M, N], box 32 x 32, 64B swizzle: epilogue TMA stores
 };
 
+// Fused row-parallel mode (RS = true, driven by tp_reduce.cu): instead of writing C, the epilogue PUSHES every partial
+// tile into the staging buffer of the rank that owns it (owner = tile % tp, slot = this rank) -- a peer-mapped address,
+// so the TMA store travels over NVLink -- and then bumps the owner's per-tile counter with a system-scope release.
+// The owner's tile_allreduce_kernel (co-resident with this kernel through programmatic dependent launch) sums the tp
+// slots as soon as a tile's counter is full and writes the bf16 result to every rank's C.
+struct alignas(64) RsParams {
+  CUtensorMap dst[kMaxTp];      // bf16 [own_tiles_cap * tile_rows, 256] views of MY slot in rank d's staging buffer
+  uint32_t* tile_flags[kMaxTp];  // rank d's per-owned-tile arrival counters (peer-mapped)
+  int tp, rank;
+};
+struct NoRsParams {
+  int unused;
+};
+
 __device__ uint32_t g_gemm_dbg[64];
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -388,9 +402,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int CG, bool WD>
+template <int CG, bool WD, bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
-mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p) {
+mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p,
+                  const __grid_constant__ std::conditional_t<RS, RsParams, NoRsParams> rs) {
   using G = Geo<CG>;
   constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
@@ -429,7 +444,11 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       prefetch_tmap(&tmaps.sfa[s]);
       prefetch_tmap(&tmaps.sfb[s]);
     }
-    prefetch_tmap(&tmaps.c);
+    if constexpr (RS) {
+      for (int d = 0; d < rs.tp; ++d) prefetch_tmap(&rs.dst[d]);
+    } else {
+      prefetch_tmap(&tmaps.c);
+    }
   }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -638,6 +657,17 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       const bool odd = (tcount & 1u) != 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? kColAcc1 : 0u);
       const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
+      // where this warp's 32-row band goes: C itself, or (RS) the owner rank's staging tile, tile-local coordinates
+      const CUtensorMap* cmap = &tmaps.c;
+      int st_row0 = row0, st_col_base = n_blk * BN;
+      int owner = 0, own_idx = 0;
+      if constexpr (RS) {
+        owner = tile % rs.tp;
+        own_idx = tile / rs.tp;
+        cmap = &rs.dst[owner];
+        st_row0 = own_idx * (CG * BM) + (int)rank * BM + q * 32;
+        st_col_base = 0;
+      }
       // 32-column chunks, the columns shared with the other accumulator first: the top ones of acc0, the bottom
       // ones of acc1.  Once those are in registers the MMA warp may start the next tile.
       constexpr int kChunks = BN / 32, kShared = (int)kAccOverlap / 32;
@@ -654,7 +684,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           stage_chunk(o, buf, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
           __syncwarp();
-          if (lane == 0 && do_store) tma_store_2d(&tmaps.c, buf, col0, row0);  // clipped at M and N by the map
+          if (lane == 0 && do_store) tma_store_2d(cmap, buf, st_col_base + sc * 32, st_row0);  // clipped by the map
           ++nstore;
         }
       };
@@ -677,6 +707,17 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         tmem_ld32(tbase + (uint32_t)(chunk_col(i) * 32), r);
         tmem_ld_wait();
         emit(r, chunk_col(i));
+      }
+      if constexpr (RS) {
+        // this warp's share of the partial tile has LANDED in the owner's memory (wait_group without .read), then a
+        // system-scope release on the owner's counter: 4 * CG arrivals per source rank complete a tile
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          __threadfence_system();
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(rs.tile_flags[owner] + own_idx) : "memory");
+        }
+        __syncwarp();
       }
       tphase ^= 1;
       if (WD) {
@@ -840,7 +881,7 @@ static uint32_t make_idesc(int kind, int a_bits, int b_bits, int mma_m) {
 }
 
 template <int CG>
-static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs) {
   using G = Geo<CG>;
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
@@ -850,13 +891,7 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
   int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / CG : sm_count() / CG;
   if (groups < 1) groups = 1;
   if (groups > tiles) groups = tiles;
-  const bool wd = options().gemm_watchdog != 0;
-  auto kern = wd ? mixed_gemm_kernel<CG, true> : mixed_gemm_kernel<CG, false>;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[wd]) {
-    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
-    attr_done[wd] = true;
-  }
+  const bool wd = options().gemm_watchdog != 0 && rs == nullptr;
   if (wd) MMX_CUDA_TRY(cudaMemsetAsync(p.dbg, 0, 64 * sizeof(uint32_t), st));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
@@ -872,15 +907,30 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p));
+  static bool attr_done[3] = {false, false, false};
+  auto prepare = [&](auto kern, int slot) -> cudaError_t {
+    if (attr_done[slot]) return cudaSuccess;
+    attr_done[slot] = true;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+  };
+  if (rs != nullptr) {
+    auto kern = mixed_gemm_kernel<CG, false, true>;
+    MMX_CUDA_TRY(prepare(kern, 2));
+    MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, *rs));
+  } else {
+    const NoRsParams none = {0};
+    auto kern = wd ? mixed_gemm_kernel<CG, true, false> : mixed_gemm_kernel<CG, false, false>;
+    MMX_CUDA_TRY(prepare(kern, wd ? 1 : 0));
+    MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, none));
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MMX_OK;
 }
 
-static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
-                  const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
-                  const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
-                  const void* bias, void* c, void* stream) {
+int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                const void* bias, void* c, void* stream, RsLaunch* rsl) {
   if (M < 0 || N <= 0 || KN < 0 || KS < 0 || KO < 0 || (KN % 128) || (KS % 128) || (KO % 128) || KN + KS + KO == 0) {
     set_error("matmul: bad shape M=%lld N=%lld (KN,KS,KO)=(%d,%d,%d)", (long long)M, (long long)N, KN, KS, KO);
     return MMX_ERR_INVALID;
@@ -889,7 +939,7 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
     set_error("matmul: N=%lld must be a multiple of 128", (long long)N);
     return MMX_ERR_INVALID;
   }
-  if (!c || ((uintptr_t)c & 15)) {
+  if (rsl == nullptr && (!c || ((uintptr_t)c & 15))) {
     set_error("matmul: output must be a non-null 16-byte aligned pointer");
     return MMX_ERR_INVALID;
   }
@@ -949,7 +999,26 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
     if (rc) return rc;
     ++ns;
   }
-  if (int rc = get_c_tmap(c, M, N, &tm.c)) return rc;
+  RsParams rs;
+  if (rsl != nullptr) {
+    // fused row-parallel mode: the epilogue stores into the owners' staging tiles (maps prepared by tp_reduce.cu)
+    const int64_t tiles = ((M + BM * cg - 1) / (BM * cg)) * ((N + BN - 1) / BN);
+    if (rsl->tp < 1 || rsl->tp > kMaxTp || (tiles + rsl->tp - 1) / rsl->tp * (BM * cg) > rsl->own_tiles_cap * 256) {
+      set_error("matmul_allreduce: %lld tiles over tp=%d exceed the workspace (%lld tiles per rank)", (long long)tiles,
+                rsl->tp, (long long)rsl->own_tiles_cap);
+      return MMX_ERR_INVALID;
+    }
+    memset(&rs, 0, sizeof(rs));
+    const CUtensorMap* maps = static_cast<const CUtensorMap*>(rsl->dst_maps);
+    for (int d = 0; d < rsl->tp; ++d) {
+      rs.dst[d] = maps[d];
+      rs.tile_flags[d] = rsl->tile_flags[d];
+    }
+    rs.tp = rsl->tp;
+    rs.rank = rsl->rank;
+  } else if (int rc = get_c_tmap(c, M, N, &tm.c)) {
+    return rc;
+  }
   p.nseg = ns;
   p.M = M;
   p.N = N;
@@ -960,7 +1029,20 @@ static int matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const
   p.dbg = dbg;
   p.flags = (uint32_t)options().gemm_debug_flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return cg == 2 ? launch_gemm<2>(tm, p, st) : launch_gemm<1>(tm, p, st);
+  const RsParams* rsp = rsl != nullptr ? &rs : nullptr;
+  const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp) : launch_gemm<1>(tm, p, st, rsp);
+  if (rc == MMX_OK && rsl != nullptr) {
+    rsl->cg = cg;
+    rsl->m_tiles = p.m_tiles;
+    rsl->n_tiles = p.n_tiles;
+    rsl->n_fastest = p.n_fastest;
+  }
+  return rc;
+}
+
+// bf16 [rows, cols] row-major view for the epilogue's 32x32 TMA stores (C itself, or a staging slot of tile rows)
+int encode_store_tmap(void* ptr, int64_t rows, int64_t cols, void* out) {
+  return get_c_tmap(ptr, rows, cols, static_cast<CUtensorMap*>(out));
 }
 
 }  // namespace mmx
@@ -969,7 +1051,8 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul(const uint8_t* 
                           const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
                           const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
                           int64_t N, int KN, int KS, int KO, int w4, const void* bias, void* c, void* stream) {
-  return mmx::matmul(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c, stream);
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c,
+                          stream, nullptr);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_gemm_debug_status(uint32_t* out, int n) {

@@ -72,6 +72,8 @@ extern "C" __attribute__((visibility("default"))) int mmx_set_option(const char*
   else if (!std::strcmp(key, "gemm_debug_flags")) o.gemm_debug_flags = value;
   else if (!std::strcmp(key, "gemm_raster")) o.gemm_raster = value;
   else if (!std::strcmp(key, "pdl")) o.pdl = value;
+  else if (!std::strcmp(key, "tp_reduce_ctas")) o.tp_reduce_ctas = value;
+  else if (!std::strcmp(key, "tp_timeout_ms")) o.tp_timeout_ms = value;
   else {
     mmx::set_error("mmx_set_option: unknown key '%s'", key);
     return MMX_ERR_INVALID;

@@ -1,0 +1,409 @@
+// tp_reduce.cu -- row-parallel mixed GEMM fused with its all-reduce over NVLink peer memory (sm_100a).
+//
+// The reference has no tensor parallelism (model/parallel_utils.py:89-163 only places whole layers on GPUs);
+// BASELINE.json's north_star asks for row-parallel o_proj / down_proj whose bf16 partials are summed across the
+// ranks of one NVSwitch box.  The plain way is mmx_matmul followed by ncclAllReduce.  This file is the fused way:
+//
+//   rank r:  mixed_gemm_kernel<.., RS=true>   the epilogue TMA-stores every partial tile straight into the staging
+//                                             buffer of the rank that OWNS the tile (owner = tile % tp; a peer-mapped
+//                                             address, the bytes cross NVLink while the tensor cores run the next
+//                                             tile) and bumps the owner's per-tile counter (red.release.sys);
+//            tile_allreduce_kernel            launched behind the GEMM with programmatic dependent launch, so its
+//                                             CTAs are co-resident with the GEMM's from the start: for each owned
+//                                             tile, wait until tp * (4 * CG) arrivals, sum the tp slots in fp32 in
+//                                             rank order (every rank gets the SAME bits), round to bf16 once and
+//                                             write the result into C on every rank (peer stores).  A final counter
+//                                             tells each rank that all owners have filled its C.
+//
+// Per rank the NVLink traffic is (tp-1)/tp of C out (partials) + (tp-1)/tp of C out (results) -- the same bytes as a
+// reduce-scatter + all-gather, but the first half hides behind the MMAs and no rank ever waits for a ring step.
+//
+// Memory: one peer-mapped workspace per rank (mmx_peer_alloc + cudaIpc handles exchanged by the host code):
+//   [flags 256 KB][staging: 2 parities x tp slots x own_tiles_cap tiles of 256x256 bf16][C: 2 parities x M_cap x N_cap]
+// Calls alternate the parity, which is all the protection the protocol needs: a rank can run at most one call ahead
+// of its peers (its reducer of call c cannot finish before every peer has pushed call c), so while a slow rank still
+// reads staging[c & 1] a fast rank writes staging[(c+1) & 1].  Counters are reset by their only reader.
+// Every rank must issue the same sequence of calls (same shapes) on one stream -- the usual SPMD contract.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <new>
+
+#include "common.h"
+
+namespace mmx {
+
+constexpr int kFlagCap = 8192;                 // owned tiles per rank and call
+constexpr int64_t kFlagBytes = 256 * 1024;     // flags region at the start of every workspace
+constexpr int64_t kTileBytes = 256 * 256 * 2;  // one staging tile of the CTA-pair kernel
+// byte offsets inside the flags region
+constexpr int64_t kOffTileFlags = 0;                 // u32 [2][kFlagCap]
+constexpr int64_t kOffConsumed = 2 * kFlagCap * 4;   // u32 [2][kFlagCap]
+constexpr int64_t kOffDone = 4 * kFlagCap * 4;       // u32 [2], 128 bytes apart
+constexpr int64_t kOffTicket = kOffDone + 256;       // u32 [2], 128 bytes apart
+constexpr int64_t kOffErr = kOffTicket + 256;        // u32: 1 = tile wait timed out, 2 = final wait timed out
+
+struct TpLayout {
+  int64_t own_tiles_cap, slot_bytes, stage_off, out_off, out_bytes, total;
+};
+
+static TpLayout make_layout(int64_t M_cap, int64_t N_cap, int tp) {
+  TpLayout L;
+  const int64_t tiles = ((M_cap + 255) / 256) * ((N_cap + 255) / 256);
+  L.own_tiles_cap = (tiles + tp - 1) / tp;
+  L.slot_bytes = L.own_tiles_cap * kTileBytes;
+  L.stage_off = kFlagBytes;
+  L.out_off = L.stage_off + 2 * (int64_t)tp * L.slot_bytes;
+  L.out_bytes = ((M_cap * N_cap * 2 + 1023) / 1024) * 1024;
+  L.total = L.out_off + 2 * L.out_bytes;
+  return L;
+}
+
+struct TpCtx {
+  int tp, rank;
+  int64_t M_cap, N_cap;
+  uint8_t* ws[kMaxTp];
+  TpLayout L;
+  CUtensorMap maps[2][kMaxTp];  // [parity][destination rank]
+  uint64_t calls;
+};
+
+struct ReduceParams {
+  const uint4* stage;       // local staging of this parity, slot 0
+  int64_t slot_u4;          // uint4 per slot
+  uint32_t* tile_flags;     // local, this parity
+  uint32_t* consumed;       // local, this parity
+  uint32_t* done[kMaxTp];   // this parity's "C is complete" counter on every rank (peer-mapped)
+  uint32_t* ticket;         // local
+  uint32_t* err;            // local
+  __nv_bfloat16* c[kMaxTp];  // this parity's C on every rank (peer-mapped)
+  int64_t M, N;
+  int rank, tile_rows, own_tiles, m_tiles, n_tiles, n_fastest;
+  uint32_t tile_expect;     // tp * 4 * CG arrivals complete a tile
+  uint32_t done_expect;     // reducer CTAs of all ranks
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded spin: a peer that never arrives (crashed rank, mismatched call sequence) costs a timeout, not the GPU
+__device__ bool spin_until(const uint32_t* flag, uint32_t target, unsigned long long timeout_ns) {
+  unsigned long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (ld_acquire_sys(flag) >= target) return true;
+    __nanosleep(64);
+    if ((it & 1023u) == 0) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) return false;
+    }
+  }
+}
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {  // L2 only: the lines were written by peers / the async proxy
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void acc_bf16x8(float (&a)[8], const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a[2 * i] += __uint_as_float(w[i] << 16);
+    a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// Work unit = 64 rows of one owned tile (256 threads: 32 x 16-byte columns, 8 rows per pass).
+template <int TP>
+__global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_constant__ ReduceParams p) {
+  // the next kernel in the stream may start its prologue; this kernel itself does NOT wait for the GEMM grid in front of
+  // it -- the per-tile counters are the dependency -- until the very end (griddepcontrol.wait below)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int tid = threadIdx.x;
+  const int c16 = tid & 31, r0 = tid >> 5;
+  const int upt = p.tile_rows >> 6;
+  const int units = p.own_tiles * upt;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int own_idx = u / upt, sub = u - own_idx * upt;
+    if (tid == 0 && !spin_until(p.tile_flags + own_idx, p.tile_expect, p.timeout_ns)) atomicOr(p.err, 1u);
+    __syncthreads();
+    const int tile = own_idx * TP + p.rank;
+    const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
+    const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+    const int64_t grow0 = (int64_t)m_blk * p.tile_rows + sub * 64 + r0;
+    const int64_t gcol = (int64_t)n_blk * 256 + c16 * 8;
+    const uint4* src = p.stage + ((int64_t)own_idx * p.tile_rows + sub * 64 + r0) * 32 + c16;
+    if (gcol < p.N) {
+#pragma unroll 1
+      for (int i = 0; i < 8; i += 2) {
+        uint4 v[2][TP];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool live = grow0 + 8 * (i + j) < p.M;
+#pragma unroll
+          for (int s = 0; s < TP; ++s)
+            v[j][s] = live ? ld_cg_u4(src + (int64_t)s * p.slot_u4 + (i + j) * 8 * 32) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int64_t grow = grow0 + 8 * (i + j);
+          if (grow < p.M) {
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int s = 0; s < TP; ++s) acc_bf16x8(a, v[j][s]);  // rank order: identical bits on every rank
+            uint4 o;
+            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * e], a[2 * e + 1]);
+              ow[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            const int64_t off = grow * p.N + gcol;
+#pragma unroll
+            for (int d = 0; d < TP; ++d) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // the last unit of a tile hands its counters back (their next use is two calls away, see the header)
+    if (tid == 0) {
+      const uint32_t old = atomicAdd(p.consumed + own_idx, 1u);
+      if (old == (uint32_t)upt - 1u) {
+        p.consumed[own_idx] = 0;
+        p.tile_flags[own_idx] = 0;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // everything this CTA wrote into the ranks' C buffers is visible before the arrival
+    __threadfence_system();
+#pragma unroll
+    for (int d = 0; d < TP; ++d) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done[d]) : "memory");
+    // ... and this rank's C is complete once the reducer CTAs of ALL ranks have arrived here
+    if (!spin_until(p.done[p.rank], p.done_expect, p.timeout_ns)) atomicOr(p.err, 2u);
+    const uint32_t t = atomicAdd(p.ticket, 1u);
+    if (t == gridDim.x - 1) {  // every local CTA is past its spin: reset for the call after next
+      *p.done[p.rank] = 0;
+      *p.ticket = 0;
+      __threadfence();
+    }
+  }
+  // completion of this grid implies completion of the GEMM grid in front of it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+static int reducer_grid(int own_tiles, int tile_rows) {
+  int64_t units = (int64_t)own_tiles * (tile_rows / 64);
+  int64_t cap = options().tp_reduce_ctas > 0 ? options().tp_reduce_ctas : sm_count();
+  if (units < 1) units = 1;  // a rank that owns nothing still takes part in the final arrival
+  return (int)(units < cap ? units : cap);
+}
+
+template <int TP>
+static int launch_reducer(const ReduceParams& p, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, tile_allreduce_kernel<TP>, p));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MMX_OK;
+}
+
+}  // namespace mmx
+
+using namespace mmx;
+#define MMX_API extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------------ peer memory
+MMX_API int mmx_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle) {
+  if (bytes <= 0 || !ptr || !handle) {
+    set_error("mmx_peer_alloc: bad arguments");
+    return MMX_ERR_INVALID;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == MMX_PEER_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  MMX_CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e, "mmx_peer_alloc");
+  }
+  memcpy(handle, &h, sizeof(h));
+  *ptr = p;
+  return MMX_OK;
+}
+
+MMX_API int mmx_peer_open(const uint8_t* handle, void** ptr) {
+  if (!handle || !ptr) {
+    set_error("mmx_peer_open: bad arguments");
+    return MMX_ERR_INVALID;
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  MMX_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MMX_OK;
+}
+
+MMX_API int mmx_peer_close(void* ptr) {
+  if (ptr) MMX_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return MMX_OK;
+}
+
+MMX_API int mmx_peer_free(void* ptr) {
+  if (ptr) MMX_CUDA_TRY(cudaFree(ptr));
+  return MMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ context
+MMX_API int64_t mmx_tp_workspace_bytes(int64_t M_cap, int64_t N_cap, int tp) {
+  if (M_cap <= 0 || N_cap <= 0 || tp < 1 || tp > kMaxTp) return -1;
+  return make_layout(M_cap, N_cap, tp).total;
+}
+
+MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, void** ctx) {
+  if (!ws || !ctx || !(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank < 0 || rank >= tp || M_cap <= 0 || N_cap <= 0 ||
+      (N_cap % 128)) {
+    set_error("mmx_tp_ctx_create: bad arguments (tp must be 1, 2, 4 or 8; N_cap a multiple of 128)");
+    return MMX_ERR_INVALID;
+  }
+  TpCtx* c = new (std::nothrow) TpCtx;
+  if (!c) {
+    set_error("mmx_tp_ctx_create: out of host memory");
+    return MMX_ERR_INVALID;
+  }
+  memset(c, 0, sizeof(*c));
+  c->tp = tp;
+  c->rank = rank;
+  c->M_cap = M_cap;
+  c->N_cap = N_cap;
+  c->L = make_layout(M_cap, N_cap, tp);
+  if (c->L.own_tiles_cap > kFlagCap) {
+    set_error("mmx_tp_ctx_create: %lld tiles per rank exceed the flag capacity %d", (long long)c->L.own_tiles_cap, kFlagCap);
+    delete c;
+    return MMX_ERR_INVALID;
+  }
+  for (int d = 0; d < tp; ++d) {
+    if (!ws[d] || ((uintptr_t)ws[d] & 1023)) {
+      set_error("mmx_tp_ctx_create: workspace %d must be a non-null 1024-byte aligned device pointer", d);
+      delete c;
+      return MMX_ERR_INVALID;
+    }
+    c->ws[d] = static_cast<uint8_t*>(ws[d]);
+  }
+  // my slot (index = my rank) in every destination's staging buffer, as a [rows, 256] bf16 tensor of tile rows
+  for (int par = 0; par < 2; ++par)
+    for (int d = 0; d < tp; ++d) {
+      uint8_t* base = c->ws[d] + c->L.stage_off + ((int64_t)par * tp + rank) * c->L.slot_bytes;
+      if (int rc = encode_store_tmap(base, c->L.own_tiles_cap * 256, 256, &c->maps[par][d])) {
+        delete c;
+        return rc;
+      }
+    }
+  *ctx = c;
+  return MMX_OK;
+}
+
+MMX_API int mmx_tp_ctx_destroy(void* ctx) {
+  delete static_cast<TpCtx*>(ctx);
+  return MMX_OK;
+}
+
+MMX_API int mmx_tp_status(void* ctx, uint32_t* out) {
+  TpCtx* c = static_cast<TpCtx*>(ctx);
+  if (!c || !out) return MMX_ERR_INVALID;
+  MMX_CUDA_TRY(cudaMemcpy(out, c->ws[c->rank] + kOffErr, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return MMX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ the fused op
+MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                                 const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                                 const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo,
+                                 int64_t M, int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out,
+                                 void* stream) {
+  TpCtx* c = static_cast<TpCtx*>(ctx);
+  if (!c || !c_out) {
+    set_error("mmx_matmul_allreduce: null context or output slot");
+    return MMX_ERR_INVALID;
+  }
+  if (M <= 0 || M * N > c->M_cap * c->N_cap || N > c->N_cap) {
+    set_error("mmx_matmul_allreduce: M=%lld N=%lld exceed the workspace (M_cap=%lld, N_cap=%lld)", (long long)M,
+              (long long)N, (long long)c->M_cap, (long long)c->N_cap);
+    return MMX_ERR_INVALID;
+  }
+  const int par = (int)(c->calls & 1);
+  const int tp = c->tp;
+  RsLaunch rsl;
+  memset(&rsl, 0, sizeof(rsl));
+  rsl.dst_maps = c->maps[par];
+  for (int d = 0; d < tp; ++d)
+    rsl.tile_flags[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffTileFlags) + (int64_t)par * kFlagCap;
+  rsl.tp = tp;
+  rsl.rank = c->rank;
+  rsl.own_tiles_cap = c->L.own_tiles_cap;
+  int rc = matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, nullptr,
+                       stream, &rsl);
+  if (rc) return rc;
+  const int tile_rows = 128 * rsl.cg;
+  const int num_tiles = rsl.m_tiles * rsl.n_tiles;
+  auto own_tiles = [&](int r) { return (num_tiles - r + tp - 1) / tp; };
+  uint8_t* me = c->ws[c->rank];
+  ReduceParams p;
+  memset(&p, 0, sizeof(p));
+  p.stage = reinterpret_cast<const uint4*>(me + c->L.stage_off + (int64_t)par * tp * c->L.slot_bytes);
+  p.slot_u4 = c->L.slot_bytes / 16;
+  p.tile_flags = rsl.tile_flags[c->rank];
+  p.consumed = reinterpret_cast<uint32_t*>(me + kOffConsumed) + (int64_t)par * kFlagCap;
+  p.ticket = reinterpret_cast<uint32_t*>(me + kOffTicket + 128 * par);
+  p.err = reinterpret_cast<uint32_t*>(me + kOffErr);
+  uint32_t done_expect = 0;
+  for (int d = 0; d < tp; ++d) {
+    p.done[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffDone + 128 * par);
+    p.c[d] = reinterpret_cast<__nv_bfloat16*>(c->ws[d] + c->L.out_off + (int64_t)par * c->L.out_bytes);
+    done_expect += (uint32_t)reducer_grid(own_tiles(d), tile_rows);
+  }
+  p.M = M;
+  p.N = N;
+  p.rank = c->rank;
+  p.tile_rows = tile_rows;
+  p.own_tiles = own_tiles(c->rank);
+  p.m_tiles = rsl.m_tiles;
+  p.n_tiles = rsl.n_tiles;
+  p.n_fastest = rsl.n_fastest;
+  p.tile_expect = (uint32_t)(tp * 4 * rsl.cg);
+  p.done_expect = done_expect;
+  p.timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
+  const int grid = reducer_grid(p.own_tiles, tile_rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (tp) {
+    case 1: rc = launch_reducer<1>(p, grid, st); break;
+    case 2: rc = launch_reducer<2>(p, grid, st); break;
+    case 4: rc = launch_reducer<4>(p, grid, st); break;
+    default: rc = launch_reducer<8>(p, grid, st); break;
+  }
+  if (rc) return rc;
+  c->calls++;
+  *c_out = p.c[c->rank];
+  return MMX_OK;
+}

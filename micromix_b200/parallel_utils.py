@@ -10,8 +10,12 @@ NCCL all-reduce over NVLink 5 / NVSwitch.
   * RowParallelQLinear:    W[N,K] sharded on K.  Rank r owns the contiguous input-channel slice
     [r*K/tp, (r+1)*K/tp), a RANK-LOCAL permutation of that slice (the global importance order filtered to the slice)
     and its own (p4,p6,p8), all multiples of 128.  Local quantize + local three-segment GEMM give a partial [M,N];
-    partials are summed with all_reduce (bf16).  `overlap_chunks > 1` splits M so the all-reduce of chunk i overlaps
-    the quantize+GEMM of chunk i+1 (NCCL runs on its own stream).
+    partials are summed
+      - fused (`workspace=` a PeerWorkspace): by libmicromix_b200's own GEMM -> all-reduce over NVLink peer memory
+        (csrc/tp_reduce.cu): the GEMM epilogue pushes each partial tile to its owner rank while the next tile's MMAs
+        run, a co-resident reducer kernel sums and broadcasts tiles as they complete;
+      - plain: with an NCCL all_reduce (bf16).  `overlap_chunks > 1` splits M so the all-reduce of chunk i overlaps
+        the quantize+GEMM of chunk i+1 (NCCL runs on its own stream).
 
 The shard planning functions are pure tensor code (CPU-testable; tests/test_parallel_gloo.py runs them under a
 world_size-2 gloo group).  The layers themselves run only on CUDA.
@@ -71,6 +75,130 @@ def all_reduce_sum(t: torch.Tensor, group=None, async_op: bool = False):
     return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+# --------------------------------------------------------------------------------------------------- peer workspace
+class _DeviceBytes:
+    """Zero-copy torch view of raw device memory owned by libmicromix_b200 (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 2,), "typestr": "<i2", "data": (ptr, False), "version": 2}
+
+
+class PeerWorkspace:
+    """Peer-mapped workspace + context of the fused row-parallel GEMM -> all-reduce (include/micromix_b200.h,
+    mmx_tp_*).  One per process; shared by every RowParallelQLinear of the model (o_proj and down_proj alternate on it).
+
+    torch.distributed is only the plumbing here: the 64-byte cudaIpc handles travel through all_gather_object, a
+    barrier orders "workspaces are zeroed and mapped" before the first kernel.  The data path is our kernels' own
+    loads / stores / reductions over NVLink.
+    """
+
+    def __init__(self, M_cap: int, N_cap: int, group=None, device=None, _sim=None):
+        import ctypes
+        from . import _lib
+        self.lib = lib = _lib.load()
+        self._ctypes = ctypes
+        self.group = group
+        self.M_cap, self.N_cap = int(M_cap), int(N_cap)
+        self.peers, self.own = [], None
+        if _sim is not None:  # (tp, rank, [workspace pointers]) -- several "ranks" inside one process (tests)
+            self.tp, self.rank, ptrs = _sim
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
+        else:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("PeerWorkspace needs an initialised torch.distributed process group")
+            self.tp, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
+            if self.nbytes <= 0:
+                raise ValueError(f"tensor-parallel degree {self.tp} is not supported by the fused path (1, 2, 4, 8)")
+            with torch.cuda.device(self.device):
+                own = ctypes.c_void_p()
+                handle = ctypes.create_string_buffer(64)
+                _lib.check(lib.mmx_peer_alloc(self.nbytes, ctypes.byref(own), handle), "mmx_peer_alloc")
+                self.own = own.value
+                handles = [None] * self.tp
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                ptrs = []
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        ptrs.append(self.own)
+                        continue
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.mmx_peer_open(h, ctypes.byref(p)), f"mmx_peer_open(rank {r})")
+                    self.peers.append(p.value)
+                    ptrs.append(p.value)
+        arr = (ctypes.c_void_p * self.tp)(*ptrs)
+        ctx = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.mmx_tp_ctx_create(arr, self.tp, self.rank, self.M_cap, self.N_cap, ctypes.byref(ctx)),
+                       "mmx_tp_ctx_create")
+        self.ctx = ctx
+        self._base = ptrs[self.rank]
+        self._views = {}
+        if _sim is None:
+            dist.barrier(group)  # every rank's workspace is zeroed and mapped before anyone's first kernel
+
+    @classmethod
+    def simulate(cls, tp: int, M_cap: int, N_cap: int):
+        """`tp` contexts inside ONE process on the current device (each "rank" on its own stream): the same kernels
+        and protocol with local pointers instead of cudaIpc mappings.  For the single-GPU parity tests."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        nbytes = int(lib.mmx_tp_workspace_bytes(M_cap, N_cap, tp))
+        ptrs = []
+        for _ in range(tp):
+            p = ctypes.c_void_p()
+            h = ctypes.create_string_buffer(64)
+            _lib.check(lib.mmx_peer_alloc(nbytes, ctypes.byref(p), h), "mmx_peer_alloc")
+            ptrs.append(p.value)
+        out = [cls(M_cap, N_cap, _sim=(tp, r, ptrs)) for r in range(tp)]
+        for r, w in enumerate(out):
+            w.own = ptrs[r]
+        return out
+
+    def matmul_allreduce(self, A, W, bias=None):
+        """A = this rank's quantized activation shard (XN, XS, XO, SFXN, SFXS, SFXO), W = the weight shard's six
+        tensors (MXFP4 in all segments) -> bf16 [M, N] = sum over ranks, a view into the workspace that stays valid
+        until the second next call."""
+        ctypes = self._ctypes
+        M, N = A[0].size(0), W[0].size(0)
+        KN, KS, KO = A[0].size(1) * 2, A[1].size(1) * 4 // 3, A[2].size(1)
+        p = lambda t: t.data_ptr() if t is not None and t.numel() > 0 else None
+        c = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_matmul_allreduce(self.ctx, p(A[0]), p(W[0]), p(A[1]), p(W[1]), p(A[2]), p(W[2]), p(A[3]),
+                                               p(W[3]), p(A[4]), p(W[4]), p(A[5]), p(W[5]), M, N, KN, KS, KO, 1, p(bias),
+                                               ctypes.byref(c), torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_matmul_allreduce")
+        view = self._views.get(c.value)
+        if view is None:
+            nbytes = self.nbytes - (c.value - self._base)
+            nbytes = min(nbytes, self.M_cap * self.N_cap * 2)
+            view = torch.as_tensor(_DeviceBytes(c.value, nbytes), device=self.device).view(torch.bfloat16)
+            self._views[c.value] = view
+        return view[: M * N].view(M, N)
+
+    def status(self) -> int:
+        w = self._ctypes.c_uint32(0)
+        from . import _lib
+        _lib.check(self.lib.mmx_tp_status(self.ctx, self._ctypes.byref(w)), "mmx_tp_status")
+        return int(w.value)
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            torch.cuda.synchronize()
+            self.lib.mmx_tp_ctx_destroy(self.ctx)
+            self.ctx = None
+            for p in self.peers:
+                self.lib.mmx_peer_close(p)
+            if self.own is not None:
+                self.lib.mmx_peer_free(self.own)
+            self.peers, self.own = [], None
+
+
 # --------------------------------------------------------------------------------------------------- layers
 class ColumnParallelQLinear(nn.Module):
     """qkv / gate_up: output features sharded, no collective.  forward(x[b,s,K]) -> [b,s,N/tp]."""
@@ -109,10 +237,11 @@ class RowParallelQLinear(nn.Module):
     """
 
     def __init__(self, originalLayer: nn.Linear, p8_num, p6_num, reorder_index, tp_group=None,
-                 overlap_chunks: int = 1):
+                 overlap_chunks: int = 1, workspace: Optional[PeerWorkspace] = None):
         super().__init__()
         from .qLinearLayer import QLinearLayer
         self.group = tp_group
+        self.workspace = workspace
         self.tp = dist.get_world_size(tp_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(tp_group) if dist.is_initialized() else 0
         self.overlap_chunks = max(1, int(overlap_chunks))
@@ -131,6 +260,14 @@ class RowParallelQLinear(nn.Module):
         bsz, q_len, _ = x.shape
         if self.tp == 1:
             return self.linear(x)
+        if self.workspace is not None:
+            # fused: quantize -> GEMM whose epilogue pushes partial tiles to their owner ranks -> co-resident reducer
+            from . import mixedgemm
+            lin = self.linear
+            a = mixedgemm.reorder_quantize_x(x.reshape(bsz * q_len, -1).contiguous(), lin.reorder_index, lin.p4_num, lin.p6_num,
+                                             lin.p8_num)
+            y = self.workspace.matmul_allreduce(a, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), lin.bias)
+            return y.view(bsz, q_len, -1)
         if self.overlap_chunks == 1:
             y = self.linear(x)
             all_reduce_sum(y, self.group)

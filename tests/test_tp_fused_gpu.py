@@ -1,0 +1,111 @@
+"""Fused row-parallel GEMM -> all-reduce over peer memory (csrc/tp_reduce.cu, mmx_matmul_allreduce).
+
+Single-GPU parity: `tp` ranks are simulated inside ONE process (PeerWorkspace.simulate: the same kernels, counters and
+parity protocol with local pointers instead of cudaIpc mappings, one stream per "rank").  The expectation is exact:
+every rank's partial is what mmx_matmul writes for its K shard (bf16), the fused path must return
+bf16(sum in fp32, in rank order) of those partials -- bit for bit, on every rank.
+The real multi-process run (cudaIpc over NVLink, vs NCCL) is tools/tp_fused_check.py under torchrun.
+"""
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _shards(tp, M, N, K, seed):
+    from micromix_b200 import mixedgemm
+    from micromix_b200.parallel_utils import row_shard_plan
+    dev = torch.device("cuda:0")
+    idx = H.make_index(K, seed=seed)
+    x = H.make_activations(M, K, idx, seed=721 + seed).to(dev)
+    w = H.make_weights(N, K, seed=1234 + seed).to(dev)
+    p8 = (K // 8) // 128 * 128
+    p6 = (K // 4) // 128 * 128
+    out = []
+    for r in range(tp):
+        k0, k1, lidx, p4, l6, l8 = row_shard_plan(idx, p6, p8, tp, r)
+        lidx = lidx.to(dev)
+        a = mixedgemm.reorder_quantize_x(x[:, k0:k1].contiguous(), lidx, p4, l6, l8)
+        b = mixedgemm.reorder_quantize_w4(w[:, k0:k1].contiguous(), lidx, p4, l6, l8)
+        out.append((a, b))
+    return out
+
+
+def _expected(shards, bias=None):
+    from micromix_b200 import mixedgemm
+    acc = None
+    for r, (a, b) in enumerate(shards):
+        part = mixedgemm.matmul(a[0], b[0], a[1], b[1], a[2], b[2], a[3], b[3], a[4], b[4], a[5], b[5],
+                                bias=bias if r == 0 else None).float()
+        acc = part if acc is None else acc + part
+    return acc.to(torch.bfloat16)
+
+
+CASES = [
+    (1, 200, 256, 256),     # degenerate: GEMM -> staging -> reducer -> C
+    (2, 128, 256, 512),     # single-CTA kernel (M <= 128), 128-row tiles
+    (2, 300, 512, 1024),    # CTA pairs, ragged M
+    (4, 1000, 1152, 2048),  # N tail of 128 columns, uneven tile ownership
+    (8, 520, 768, 4096),    # every rank of an 8-GPU box
+    (2, 2048, 4096, 1024),  # more tiles than reducer CTAs
+]
+
+
+@pytest.mark.parametrize("tp,M,N,K", CASES)
+def test_fused_allreduce_matches_sum_of_partials(cuda, mmx_lib, tp, M, N, K):
+    from micromix_b200.parallel_utils import PeerWorkspace
+    mmx_lib.mmx_set_option(b"tp_reduce_ctas", 8)    # tp reducer grids must be co-resident on the one GPU
+    mmx_lib.mmx_set_option(b"tp_timeout_ms", 4000)  # a protocol bug costs a timeout, not the GPU
+    try:
+        shards = _shards(tp, M, N, K, seed=tp)
+        bias = (torch.randn(N, device=cuda) * 0.1).to(torch.bfloat16)
+        want = _expected(shards, bias)
+        works = PeerWorkspace.simulate(tp, M, N)
+        streams = [torch.cuda.Stream() for _ in range(tp)]
+        torch.cuda.synchronize()
+        for call in range(3):  # both parities, and the counters handed back by call 0 are reused by call 2
+            ys = []
+            for r in range(tp):
+                with torch.cuda.stream(streams[r]):
+                    ys.append(works[r].matmul_allreduce(*shards[r], bias=bias if r == 0 else None))
+            torch.cuda.synchronize()
+            for r in range(tp):
+                assert works[r].status() == 0, f"rank {r}: cross-rank wait timed out (call {call})"
+                assert torch.equal(ys[r], want), f"rank {r} call {call}: fused result differs from the sum of partials"
+        for w in works:
+            w.close()
+    finally:
+        mmx_lib.mmx_set_option(b"tp_reduce_ctas", 0)
+        mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)
+
+
+def test_fused_allreduce_alternating_shapes(cuda, mmx_lib):
+    """o_proj and down_proj share one workspace: different shapes on alternating parities."""
+    from micromix_b200.parallel_utils import PeerWorkspace
+    mmx_lib.mmx_set_option(b"tp_reduce_ctas", 8)
+    mmx_lib.mmx_set_option(b"tp_timeout_ms", 4000)
+    try:
+        tp = 2
+        sa = _shards(tp, 600, 512, 1024, seed=11)
+        sb = _shards(tp, 300, 1024, 2048, seed=12)
+        wa, wb = _expected(sa), _expected(sb)
+        works = PeerWorkspace.simulate(tp, 600, 1024)
+        streams = [torch.cuda.Stream() for _ in range(tp)]
+        torch.cuda.synchronize()
+        for call in range(5):
+            sh, want = (sa, wa) if call % 2 == 0 else (sb, wb)
+            ys = []
+            for r in range(tp):
+                with torch.cuda.stream(streams[r]):
+                    ys.append(works[r].matmul_allreduce(*sh[r]))
+            torch.cuda.synchronize()
+            for r in range(tp):
+                assert works[r].status() == 0
+                assert torch.equal(ys[r], want), f"rank {r} call {call}"
+        for w in works:
+            w.close()
+    finally:
+        mmx_lib.mmx_set_option(b"tp_reduce_ctas", 0)
+        mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)
