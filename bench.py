@@ -161,6 +161,7 @@ def workload_config(args, world):
                         f"quantize + mixed GEMM per linear",
             "tokens": args.tokens, "split_4096": list(split_for(4096)), "split_14336": list(split_for(14336)),
             "parallelism": f"tp{world}" if world > 1 else "single",
+            "tp_reduce": (args.tp_reduce if world > 1 and args.impl == "ours" else None),
             "l2": "inputs+weights+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -168,13 +169,15 @@ def workload_config(args, world):
 class HotLinear:
     """One (possibly TP-sharded) linear with every buffer preallocated; calls the C ABI directly."""
 
-    def __init__(self, name, N, K, mode, M, rank, world, dev, lib, seed):
+    def __init__(self, name, N, K, mode, M, rank, world, dev, lib, seed, workspace=None):
         import torch
         from micromix_b200 import mixedgemm
         from micromix_b200.parallel_utils import column_shard_range, row_shard_plan
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import helpers as H
         self.name, self.mode, self.lib, self.M, self.world = name, mode, lib, M, world
+        self.ws = workspace if (world > 1 and mode == "row") else None
+        self._c_out = ctypes.c_void_p()
         idx = H.make_index(K, seed=seed)
         g = torch.Generator(device=dev).manual_seed(1234 + seed)
         w = (torch.randn(N, K, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
@@ -218,12 +221,16 @@ class HotLinear:
         rc = self.lib.mmx_reorder_quantize_x(*self._qargs, stream)
         if events is not None:
             events[1].record()
-        rc |= self.lib.mmx_matmul(*self._margs, stream)
+        if self.ws is not None:
+            # fused: GEMM epilogue pushes partial tiles to their owner rank over NVLink, co-resident reducer kernel
+            rc |= self.lib.mmx_matmul_allreduce(self.ws.ctx, *self._margs[:-1], ctypes.byref(self._c_out), stream)
+        else:
+            rc |= self.lib.mmx_matmul(*self._margs, stream)
         if events is not None:
             events[2].record()
         if rc:
             raise RuntimeError(self.lib.mmx_last_error().decode())
-        if self.world > 1 and self.mode == "row":
+        if self.ws is None and self.world > 1 and self.mode == "row":
             dist.all_reduce(self.out)
 
 
@@ -239,7 +246,12 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     M = args.tokens
     peaks = load_peaks()
-    lins = [HotLinear(n, N, K, mode, M, rank, world, dev, lib, seed=i) for i, (n, N, K, mode) in enumerate(LINEARS)]
+    ws = None
+    if world > 1 and args.tp_reduce == "fused":
+        from micromix_b200.parallel_utils import PeerWorkspace
+        ws = PeerWorkspace(M, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
+    lins = [HotLinear(n, N, K, mode, M, rank, world, dev, lib, seed=i, workspace=ws)
+            for i, (n, N, K, mode) in enumerate(LINEARS)]
     stream = torch.cuda.current_stream().cuda_stream
     total_flops = M * flops_per_token()  # whole job, all ranks together
 
@@ -302,6 +314,10 @@ def run_ours(args, rank, world, local_rank):
 
     clocks = sampler.summary()
     sampler.stop_flag.set()
+    tp_status = None
+    if ws is not None:
+        tp_status = ws.status()  # 0 = no reducer wait ever timed out
+        ws.close()
     line = {"metric": METRIC, "value": total_flops / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/mxfp6/mxfp8 x mxfp4 -> fp32 acc -> bf16",
@@ -316,6 +332,8 @@ def run_ours(args, rank, world, local_rank):
                                   "traffic": None, "peak_note": f"{peaks['source']} copy bandwidth"},
             "share": {"gemm": g_ms / ms_total if world == 1 else None, "quantize": q_ms / ms_total if world == 1 else None},
             "per_linear": per_lin}
+    if tp_status is not None:
+        line["tp_fused_status"] = tp_status
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
@@ -326,6 +344,7 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
     import torch
     import torch.distributed as dist
     import torch.nn as nn
+    from micromix_b200 import mixedgemm
     from micromix_b200.qLinearLayer import QLinearLayer
     M = args.tokens
     layers, xin, yout = [], [], []
@@ -354,9 +373,13 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
                 e_in.record(s_in)
             s_run.wait_event(e_in)
             with torch.cuda.stream(s_run):
-                yd = q(xd.view(1, M, -1))
-                if world > 1 and l.mode == "row":
-                    dist.all_reduce(yd)
+                if l.ws is not None:
+                    a = mixedgemm.reorder_quantize_x(xd, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
+                    yd = l.ws.matmul_allreduce(a, l.W)
+                else:
+                    yd = q(xd.view(1, M, -1))
+                    if world > 1 and l.mode == "row":
+                        dist.all_reduce(yd)
                 e_run = torch.cuda.Event()
                 e_run.record(s_run)
             s_out.wait_event(e_run)
@@ -404,6 +427,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-tokens", type=int, default=2048, help="token sample for the host-core baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp-reduce", default="nccl", choices=["nccl", "fused"],
+                    help="row-parallel reduction at N>1: NCCL all-reduce, or our GEMM->all-reduce over NVLink peer memory")
     args = ap.parse_args()
     args.steps_ref = max(1, min(args.steps, 3))
     args.warmup_ref = max(1, min(args.warmup, 1))

@@ -240,6 +240,9 @@ MMX_API int mmx_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle) {
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == MMX_PEER_HANDLE_BYTES, "handle size");
   void* p = nullptr;
+  // whole 2 MiB pages: small cudaMalloc requests are sub-allocated at 256/512-byte granularity, and an IPC handle
+  // exports the allocation it came from; a page-sized request gets (and exports) a block of its own
+  bytes = (bytes + (2ll << 20) - 1) / (2ll << 20) * (2ll << 20);
   MMX_CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
   cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -304,8 +307,8 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
     return MMX_ERR_INVALID;
   }
   for (int d = 0; d < tp; ++d) {
-    if (!ws[d] || ((uintptr_t)ws[d] & 1023)) {
-      set_error("mmx_tp_ctx_create: workspace %d must be a non-null 1024-byte aligned device pointer", d);
+    if (!ws[d] || ((uintptr_t)ws[d] & 255)) {  // TMA stores and 16-byte vector accesses need far less
+      set_error("mmx_tp_ctx_create: workspace %d must be a non-null 256-byte aligned device pointer", d);
       delete c;
       return MMX_ERR_INVALID;
     }
