@@ -169,7 +169,7 @@ def workload_config(args, world):
 class HotLinear:
     """One (possibly TP-sharded) linear with every buffer preallocated; calls the C ABI directly."""
 
-    def __init__(self, name, N, K, mode, M, rank, world, dev, lib, seed, workspace=None):
+    def __init__(self, name, N, K, mode, M, rank, world, dev, lib, seed, workspace=None, share=None, chunk=0):
         import torch
         from micromix_b200 import mixedgemm
         from micromix_b200.parallel_utils import column_shard_range, row_shard_plan
@@ -178,22 +178,27 @@ class HotLinear:
         self.name, self.mode, self.lib, self.M, self.world = name, mode, lib, M, world
         self.ws = workspace if (world > 1 and mode == "row") else None
         self._c_out = ctypes.c_void_p()
-        idx = H.make_index(K, seed=seed)
-        g = torch.Generator(device=dev).manual_seed(1234 + seed)
-        w = (torch.randn(N, K, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
-        p4, p6, p8 = split_for(K)
-        if world > 1 and mode == "col":
-            n0, n1 = column_shard_range(N, world, rank)
-            w = w[n0:n1].contiguous()
-        elif world > 1 and mode == "row":
-            k0, k1, idx, p4, p6, p8 = row_shard_plan(idx, p6, p8, world, rank)
-            w = w[:, k0:k1].contiguous()
-        self.N, self.K = w.shape
-        self.split = (p4, p6, p8)
-        self.idx = idx.to(dev)
-        self.W = mixedgemm.reorder_quantize_w4(w, self.idx, p4, p6, p8)
-        del w
-        gx = torch.Generator(device=dev).manual_seed(721 + seed + 97 * rank * (mode == "row"))
+        if share is not None:
+            # another token chunk of the same (sharded) linear: same quantized weights, permutation and split
+            self.N, self.K, self.split, self.idx, self.W = share.N, share.K, share.split, share.idx, share.W
+            p4, p6, p8 = self.split
+        else:
+            idx = H.make_index(K, seed=seed)
+            g = torch.Generator(device=dev).manual_seed(1234 + seed)
+            w = (torch.randn(N, K, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+            p4, p6, p8 = split_for(K)
+            if world > 1 and mode == "col":
+                n0, n1 = column_shard_range(N, world, rank)
+                w = w[n0:n1].contiguous()
+            elif world > 1 and mode == "row":
+                k0, k1, idx, p4, p6, p8 = row_shard_plan(idx, p6, p8, world, rank)
+                w = w[:, k0:k1].contiguous()
+            self.N, self.K = w.shape
+            self.split = (p4, p6, p8)
+            self.idx = idx.to(dev)
+            self.W = mixedgemm.reorder_quantize_w4(w, self.idx, p4, p6, p8)
+            del w
+        gx = torch.Generator(device=dev).manual_seed(721 + seed + 97 * rank * (mode == "row") + 7919 * chunk)
         gain = 1.0 + 31.0 * (torch.arange(self.K, device=dev, dtype=torch.float32) / self.K) ** 8
         x = torch.randn(M, self.K, generator=gx, device=dev, dtype=torch.float32)
         xg = torch.empty_like(x)
@@ -214,8 +219,7 @@ class HotLinear:
                        p(self.SFA[1]), p(W[4]), p(self.SFA[2]), p(W[5]), M, self.N, p4, p6, p8, 1, None, p(self.out))
 
     def run(self, stream, events=None):
-        import torch
-        import torch.distributed as dist
+        """quantize + GEMM of this rank's shard (fused mode: + the reduction, inside the GEMM launch pair)."""
         if events is not None:
             events[0].record()
         rc = self.lib.mmx_reorder_quantize_x(*self._qargs, stream)
@@ -230,8 +234,14 @@ class HotLinear:
             events[2].record()
         if rc:
             raise RuntimeError(self.lib.mmx_last_error().decode())
+
+    def reduce_async(self):
+        """Row-parallel partial sum over the ranks: NCCL all-reduce on NCCL's own stream (returns the Work to wait on
+        before the result is consumed).  Nothing to do for column-parallel linears and in fused mode."""
+        import torch.distributed as dist
         if self.ws is None and self.world > 1 and self.mode == "row":
-            dist.all_reduce(self.out)
+            return dist.all_reduce(self.out, async_op=True)
+        return None
 
 
 def run_ours(args, rank, world, local_rank):
@@ -246,13 +256,25 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     M = args.tokens
     peaks = load_peaks()
+    # token chunks: at N > 1 the step runs as C micro-batches so that the all-reduce of one chunk's row-parallel
+    # linear (NCCL stream) overlaps the other chunks' quantize + GEMM; every chunk keeps a real layer's dependency
+    # chain qkv -> o -> all-reduce -> gate_up -> down -> all-reduce (gate_up of chunk c waits for ITS o all-reduce)
+    C = max(1, args.tp_chunks) if world > 1 else 1
+    if M % (C * 128):
+        C = 1
+    Mc = M // C
     ws = None
     if world > 1 and args.tp_reduce == "fused":
         from micromix_b200.parallel_utils import PeerWorkspace
-        ws = PeerWorkspace(M, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
-    lins = [HotLinear(n, N, K, mode, M, rank, world, dev, lib, seed=i, workspace=ws)
-            for i, (n, N, K, mode) in enumerate(LINEARS)]
-    stream = torch.cuda.current_stream().cuda_stream
+        ws = PeerWorkspace(Mc, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
+    if world > 1 and args.gemm_ctas > 0:
+        lib.mmx_set_option(b"gemm_ctas", args.gemm_ctas)  # leave SMs to the concurrent NCCL kernel
+    chunks = []
+    for c in range(C):
+        chunks.append([HotLinear(n, N, K, mode, Mc, rank, world, dev, lib, seed=i, workspace=ws,
+                                 share=(chunks[0][i] if c else None), chunk=c)
+                       for i, (n, N, K, mode) in enumerate(LINEARS)])
+    lins = chunks[0]
     total_flops = M * flops_per_token()  # whole job, all ranks together
 
     def barrier():
@@ -260,47 +282,102 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def issue_step(ev=None):
+        """One pass of the hot path over the batch.  ev[c][li] = three events around quantize / GEMM."""
+        stream = torch.cuda.current_stream().cuda_stream
+        if world == 1:
+            for li, l in enumerate(lins):
+                l.run(stream, ev[0][li] if ev is not None else None)
+            return
+        pend = [None] * C
+        for half in ((0, 1), (2, 3)):  # attention linears, MLP linears
+            for c in range(C):
+                if pend[c] is not None:
+                    pend[c].wait()  # this chunk's previous all-reduce: overlapped the other chunks' kernels
+                    pend[c] = None
+                for li in half:
+                    chunks[c][li].run(stream, ev[c][li] if ev is not None else None)
+                pend[c] = chunks[c][half[1]].reduce_async()
+        for c in range(C):
+            if pend[c] is not None:
+                pend[c].wait()
+
+    def new_events():
+        return [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in LINEARS] for _ in range(C)]
+
     for _ in range(max(args.warmup, 3)):
-        for l in lins:
-            l.run(stream)
+        issue_step()
     barrier()
+    # N > 1: the step is replayed from a CUDA graph (8C kernels + 2C NCCL all-reduces per replay) -- at tp=8 the
+    # kernels are 10-70 us each and eager launches from 8 Python processes would bound the step
+    graph, graph_note = None, None
+    if world > 1 and not args.no_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                issue_step()
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            l0 = mixedgemm.launch_count()
+            with torch.cuda.graph(graph, stream=side):
+                issue_step()
+            launches_per_step = mixedgemm.launch_count() - l0
+            barrier()
+            for _ in range(3):
+                graph.replay()
+            barrier()
+        except Exception as e:  # noqa: BLE001 -- report, then time the eager step instead
+            graph, graph_note = None, f"capture failed: {e!r}"[:200]
+            torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in lins] for _ in range(args.steps)]
+    n_ev = args.steps if graph is None else max(3, min(args.steps, 10))
+    ev = [new_events() for _ in range(n_ev)]
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = mixedgemm.launch_count()
     barrier()
     sampler.active.set()
     t_start.record()
-    for s in range(args.steps):
-        for li, l in enumerate(lins):
-            l.run(stream, ev[s][li])
+    if graph is not None:
+        for s in range(args.steps):
+            graph.replay()
+    else:
+        for s in range(args.steps):
+            issue_step(ev[s])
     t_end.record()
     barrier()
     sampler.active.clear()
-    launches = mixedgemm.launch_count() - launches0
+    launches = (mixedgemm.launch_count() - launches0) if graph is None else launches_per_step * args.steps
     ms_total = t_start.elapsed_time(t_end)
     ms_step = ms_total / args.steps
     if world > 1:
         t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item())
-    # per-kernel device time from the events inside the timed region
-    q_ms = sum(ev[s][li][0].elapsed_time(ev[s][li][1]) for s in range(args.steps) for li in range(len(lins)))
-    g_ms = sum(ev[s][li][1].elapsed_time(ev[s][li][2]) for s in range(args.steps) for li in range(len(lins)))
+    if graph is not None:
+        # per-kernel device times cannot be taken inside a graph replay: an eager, evented pass of the same step
+        for s in range(n_ev):
+            issue_step(ev[s])
+        barrier()
+    # per-kernel device time from the events (N = 1: inside the timed region itself)
+    cells = [(s, c, li) for s in range(n_ev) for c in range(C) for li in range(len(LINEARS))]
+    q_ms = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s, c, li in cells)
+    g_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells)
     per_lin = {}
     for li, l in enumerate(lins):
-        gq = sum(ev[s][li][0].elapsed_time(ev[s][li][1]) for s in range(args.steps)) / args.steps
-        gg = sum(ev[s][li][1].elapsed_time(ev[s][li][2]) for s in range(args.steps)) / args.steps
-        per_lin[l.name] = {"N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
+        gq = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
+        gg = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
+        per_lin[l.name] = {"M": l.M, "N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
                            "quant_gbs": l.qbytes / gq / 1e6, "gemm_tflops": l.flops / gg / 1e9}
-    rank_flops = sum(l.flops for l in lins)
-    gemm_tflops = rank_flops * args.steps / g_ms / 1e9
+    rank_flops = C * sum(l.flops for l in lins)
+    gemm_tflops = rank_flops * n_ev / g_ms / 1e9
     # split-weighted tensor peak: FP4xFP4 at 4x, the FP6/FP8 segments at 2x the MEASURED dense bf16 rate
     p_bf16 = peaks["bf16_tflops"]
-    tmin = sum(2.0 * M * l.N * (l.split[0] / (4 * p_bf16) + (l.split[1] + l.split[2]) / (2 * p_bf16)) for l in lins)
+    tmin = sum(2.0 * M * l.N * (l.split[0] / (4 * p_bf16) + (l.split[1] + l.split[2]) / (2 * p_bf16)) for l in lins)  # C chunks of M/C
     peak_eff = rank_flops / tmin  # TFLOP/s
-    quant_gbs = sum(l.qbytes for l in lins) * args.steps / q_ms / 1e6
+    quant_gbs = C * sum(l.qbytes for l in lins) * n_ev / q_ms / 1e6
     traffic = None
     prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(prof):
@@ -310,7 +387,7 @@ def run_ours(args, rank, world, local_rank):
             traffic = None
 
     # ---- e2e: the plugin call a user makes (QLinearLayer.forward) with HOST buffers, copies inside the timed region
-    e2e = measure_e2e(args, rank, world, dev, lins, total_flops)
+    e2e = None if args.no_e2e else measure_e2e(args, rank, world, dev, chunks, total_flops)
 
     clocks = sampler.summary()
     sampler.stop_flag.set()
@@ -334,20 +411,26 @@ def run_ours(args, rank, world, local_rank):
             "per_linear": per_lin}
     if tp_status is not None:
         line["tp_fused_status"] = tp_status
+    if world > 1:
+        line["tp"] = {"chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
+                      "gemm_ctas": args.gemm_ctas or None,
+                      "per_kernel_times": "eager evented pass after the timed region" if graph is not None
+                      else "events inside the timed region"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         print(json.dumps(line), flush=True)
 
 
-def measure_e2e(args, rank, world, dev, lins, total_flops):
+def measure_e2e(args, rank, world, dev, chunks, total_flops):
     import torch
     import torch.distributed as dist
     import torch.nn as nn
     from micromix_b200 import mixedgemm
     from micromix_b200.qLinearLayer import QLinearLayer
     M = args.tokens
-    layers, xin, yout = [], [], []
+    lins = [l for ch in chunks for l in ch]  # every (token chunk, linear) of the step
+    layers, xin, yout, yrows = [], [], [], []
     for l in lins:
         q = QLinearLayer.__new__(QLinearLayer)  # reuse the already-quantized shard instead of re-quantizing
         nn.Module.__init__(q)
@@ -357,7 +440,11 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
         q.BN, q.BS, q.BO, q.SFBN, q.SFBS, q.SFBO = l.W
         layers.append(q)
         xin.append(l.x.cpu().pin_memory())
-        yout.append(torch.empty((M, l.N), dtype=torch.bfloat16).pin_memory())
+        # a row-parallel result is replicated on every rank after the reduction: each rank returns its 1/N of the rows
+        # (the host holds the whole result once); a column-parallel shard is returned whole
+        r0, r1 = (l.M * rank // world, l.M * (rank + 1) // world) if (world > 1 and l.mode == "row") else (0, l.M)
+        yrows.append((r0, r1))
+        yout.append(torch.empty((r1 - r0, l.N), dtype=torch.bfloat16).pin_memory())
     h2d = sum(x.numel() * 2 for x in xin)
     d2h = sum(y.numel() * 2 for y in yout)
 
@@ -366,7 +453,7 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
 
     def step():
         keep = []
-        for q, x, y, l in zip(layers, xin, yout, lins):
+        for q, x, y, l, (r0, r1) in zip(layers, xin, yout, lins, yrows):
             with torch.cuda.stream(s_in):
                 xd = x.to(dev, non_blocking=True)
                 e_in = torch.cuda.Event()
@@ -377,14 +464,14 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
                     a = mixedgemm.reorder_quantize_x(xd, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
                     yd = l.ws.matmul_allreduce(a, l.W)
                 else:
-                    yd = q(xd.view(1, M, -1))
+                    yd = q(xd.view(1, l.M, -1))
                     if world > 1 and l.mode == "row":
                         dist.all_reduce(yd)
                 e_run = torch.cuda.Event()
                 e_run.record(s_run)
             s_out.wait_event(e_run)
             with torch.cuda.stream(s_out):
-                y.copy_(yd.view(M, -1), non_blocking=True)
+                y.copy_(yd.view(l.M, -1)[r0:r1], non_blocking=True)
             keep.append((xd, yd))  # alive until the step's synchronize: no cross-stream reuse by the allocator
         torch.cuda.synchronize()
 
@@ -403,8 +490,8 @@ def measure_e2e(args, rank, world, dev, lins, total_flops):
         dt = float(t.item())
     return {"value": total_flops / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "tokens_per_s": M / dt,
-            "api": "QLinearLayer.forward on pinned host tensors; per linear: H2D copy, quantize, GEMM, D2H copy, on three "
-                   "streams (copy-in / layers / copy-out)"}
+            "api": "QLinearLayer.forward on pinned host tensors; per linear: H2D copy, quantize, GEMM (+ all-reduce), D2H "
+                   "copy, on three streams (copy-in / layers / copy-out); bytes are per rank"}
 
 
 def cpu_baseline(args):
@@ -427,6 +514,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-tokens", type=int, default=2048, help="token sample for the host-core baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp-chunks", type=int, default=2,
+                    help="N>1: token micro-batches per step; a chunk's all-reduce overlaps the other chunks' kernels")
+    ap.add_argument("--gemm-ctas", type=int, default=0, help="N>1: cap the persistent GEMM grid (SMs left to NCCL)")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
     ap.add_argument("--tp-reduce", default="nccl", choices=["nccl", "fused"],
                     help="row-parallel reduction at N>1: NCCL all-reduce, or our GEMM->all-reduce over NVLink peer memory")
     args = ap.parse_args()

@@ -177,8 +177,13 @@ int64_t mmx_launch_count(void);
  * "gemm_ctas","gemm_cta_group","pdl","tp_reduce_ctas","tp_timeout_ms", ...}. */
 int mmx_set_option(const char* key, int64_t value);
 
-/* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n). */
+/* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n).
+ * Words 40..43: globaltimer (lo, hi) at the start / end of CTA 0's epilogue of the last fused (RS) GEMM. */
 int mmx_gemm_debug_status(uint32_t* out, int n);
+
+/* Timeline probe of the last tile_allreduce_kernel launch (reducer CTA 0, globaltimer ns): entry, first owned tile
+ * complete, last unit reduced, final cross-rank arrival seen.  tools/tp_fused_probe.py; not part of the product path. */
+int mmx_tp_debug_times(uint64_t* out, int n);
 
 #ifdef __cplusplus
 }

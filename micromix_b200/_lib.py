@@ -40,6 +40,7 @@ SYMBOLS = {
     "mmx_launch_count": (_i64, []),
     "mmx_set_option": (_i32, [ctypes.c_char_p, _i64]),
     "mmx_gemm_debug_status": (_i32, [ctypes.POINTER(ctypes.c_uint32), _i32]),
+    "mmx_tp_debug_times": (_i32, [ctypes.POINTER(ctypes.c_uint64), _i32]),
 }
 
 _lib = None

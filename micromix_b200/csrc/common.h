@@ -25,6 +25,7 @@ struct Options {
   int64_t gemm_raster = 0;    // 0: auto, 1: force M-fastest tile order, 2: force N-fastest
   int64_t gemm_cta_group = 0; // 0: auto (pairs when M > 128), 1: force the single-CTA kernel
   int64_t tp_reduce_ctas = 0; // 0: one reducer CTA per SM, else cap the tile_allreduce_kernel grid (single-GPU tests)
+  int64_t tp_debug = 0;       // timing experiments of the fused all-reduce (results wrong): see ReduceParams::dbg
   int64_t tp_timeout_ms = 10000;  // bound on every cross-rank spin of tile_allreduce_kernel (a lost peer cannot hang the GPU)
 };
 Options& options();
@@ -50,6 +51,7 @@ struct RsLaunch {
   int64_t own_tiles_cap;     // staging tiles (256 rows each) per (rank, slot)
   // filled in by matmul_impl: the tile geometry the reducer must mirror
   int cg, m_tiles, n_tiles, n_fastest;
+  int rot_s;                 // owner rotation period, see RsParams in gemm.cu
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,

@@ -58,9 +58,12 @@ static_assert(kSFSlot * kNumSFSlots <= kAccOverlap && kAccOverlap % 32 == 0, "TM
 constexpr int kEpiBuf = 2048;      // 32 rows x 32 bf16 (64-byte rows, 64B swizzle): source of one TMA store
 constexpr int kEpiStage = 2 * kEpiBuf;  // two buffers per epilogue warp: stage chunk i+1 while chunk i is read
 
-template <int CG>
+// RS (fused row-parallel mode): one stage less, so that a tile_allreduce_kernel CTA (no dynamic shared memory, but
+// every resident CTA reserves 1 KB) fits on the SM NEXT TO this kernel's CTA -- with six stages the pair kernel leaves
+// 768 bytes and the reducer could only start once the GEMM had left.
+template <int CG, bool RS = false>
 struct Geo {
-  static constexpr int kStages = (CG == 1) ? 4 : 6;
+  static constexpr int kStages = (CG == 1) ? 4 : (RS ? 5 : 6);
   static constexpr int kBRows = BN / CG;          // B rows this CTA stages
   static constexpr int kStageA = BM * 128;        // 16 KB
   static constexpr int kStageB = kBRows * 128;    // 32 | 16 KB
@@ -112,6 +115,7 @@ struct alignas(64) RsParams {
   CUtensorMap dst[kMaxTp];      // bf16 [own_tiles_cap * tile_rows, 256] views of MY slot in rank d's staging buffer
   uint32_t* tile_flags[kMaxTp];  // rank d's per-owned-tile arrival counters (peer-mapped)
   int tp, rank;
+  int rot_s;  // owner rotation period (a multiple of tp): owner(tile) = (tile + tile / tp * tp / rot_s) % tp
 };
 struct NoRsParams {
   int unused;
@@ -406,7 +410,7 @@ template <int CG, bool WD, bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p,
                   const __grid_constant__ std::conditional_t<RS, RsParams, NoRsParams> rs) {
-  using G = Geo<CG>;
+  using G = Geo<CG, RS>;
   constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -643,6 +647,13 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
     uint32_t n_tiles_done = 0;
     const uint32_t sbuf = smem_base + G::kEpiOff + (uint32_t)(warp - 2) * kEpiStage;
     uint32_t nstore = 0;  // TMA stores issued by this warp: picks the staging buffer
+    uint32_t* prev_flag = nullptr;  // RS: arrival counter of the previous tile, bumped one tile late (lane 0)
+    if (RS && blockIdx.x == 0 && warp == 2 && lane == 0) {  // timeline probe (tools/tp_fused_probe.py)
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[40] = (uint32_t)t;
+      p.dbg[41] = (uint32_t)(t >> 32);
+    }
     for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
       const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
       const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
@@ -657,14 +668,18 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       const bool odd = (tcount & 1u) != 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? kColAcc1 : 0u);
       const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
+      const uint32_t nstore_tile0 = nstore;
       // where this warp's 32-row band goes: C itself, or (RS) the owner rank's staging tile, tile-local coordinates
       const CUtensorMap* cmap = &tmaps.c;
       int st_row0 = row0, st_col_base = n_blk * BN;
       int owner = 0, own_idx = 0;
       if constexpr (RS) {
-        owner = tile % rs.tp;
+        // blocks of tp consecutive tiles go to the tp ranks, rotated by one every rot_s tiles: a CTA group's tiles
+        // (stride = #groups) then go to DIFFERENT owners in turn instead of always the same one, so every SM pushes its
+        // share over NVLink rather than half of them pushing everything (tp = 2, even #groups)
         own_idx = tile / rs.tp;
-        cmap = &rs.dst[owner];
+        owner = (tile + (own_idx * rs.tp) / rs.rot_s) % rs.tp;
+        cmap = &rs.dst[(p.flags & 8u) ? rs.rank : owner];  // flag 8: timing experiment, partials stay local
         st_row0 = own_idx * (CG * BM) + (int)rank * BM + q * 32;
         st_col_base = 0;
       }
@@ -684,7 +699,12 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           stage_chunk(o, buf, lane);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to TMA
           __syncwarp();
-          if (lane == 0 && do_store) tma_store_2d(cmap, buf, st_col_base + sc * 32, st_row0);  // clipped by the map
+          if (lane == 0 && do_store) {
+            // C: clipped at M and N by the map.  RS: the staging slot is BOX-MAJOR -- every 32 x 32 box is 2 KB of
+            // contiguous peer memory (64-byte rows of a row-major tile travel over NVLink at less than half the rate)
+            if constexpr (RS) tma_store_2d(cmap, buf, 0, st_row0 * 8 + sc * 32);
+            else tma_store_2d(cmap, buf, st_col_base + sc * 32, st_row0);
+          }
           ++nstore;
         }
       };
@@ -709,15 +729,24 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         emit(r, chunk_col(i));
       }
       if constexpr (RS) {
-        // this warp's share of the partial tile has LANDED in the owner's memory (wait_group without .read), then a
-        // system-scope release on the owner's counter: 4 * CG arrivals per source rank complete a tile
+        // DEFERRED arrival: once this tile's stores are issued, the stores of the PREVIOUS tile have long LANDED in its
+        // owner's memory (wait_group N without .read = all but the N most recent groups are complete), so the wait costs
+        // no NVLink round trip; then ONE system-scope release on the owner's counter (4 * CG arrivals per source rank
+        // complete a tile).  The last tile's arrival follows the loop.
         if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          __threadfence_system();
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(rs.tile_flags[owner] + own_idx) : "memory");
+          // stores this warp issued for this tile: 8, or 4 on a 128-wide last column block, none for rows past M
+          const int cnt = do_store ? (int)(nstore - nstore_tile0) : 0;
+          if (prev_flag != nullptr) {
+            if (cnt == 8) asm volatile("cp.async.bulk.wait_group 8;" ::: "memory");
+            else if (cnt == 4) asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            if (p.flags & 32u) {  // timing experiment: no arrival at all
+            } else if (p.flags & 16u) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+            else asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+          }
+          prev_flag = rs.tile_flags[owner] + own_idx;
         }
-        __syncwarp();
       }
       tphase ^= 1;
       if (WD) {
@@ -727,6 +756,18 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores done before smem goes away
+    if (RS && blockIdx.x == 0 && warp == 2 && lane == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.dbg[42] = (uint32_t)t;
+      p.dbg[43] = (uint32_t)(t >> 32);
+    }
+    if constexpr (RS) {
+      if (lane == 0 && prev_flag != nullptr) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (!(p.flags & 32u)) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+      }
+    }
     if (WD && blockIdx.x == 0 && warp == 2 && lane == 0) {
       p.dbg[22] = (uint32_t)(t_ewait >> 4);  // epilogue warp: cycles waiting for an accumulator / 16
       p.dbg[23] = (uint32_t)(t_ework >> 4);  // ... draining TMEM and storing C / 16
@@ -882,7 +923,7 @@ static uint32_t make_idesc(int kind, int a_bits, int b_bits, int mma_m) {
 
 template <int CG>
 static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs) {
-  using G = Geo<CG>;
+  const int smem_bytes = rs != nullptr ? Geo<CG, true>::kSmemBytes : Geo<CG, false>::kSmemBytes;
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
@@ -896,7 +937,7 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CG));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = G::kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -911,7 +952,7 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   auto prepare = [&](auto kern, int slot) -> cudaError_t {
     if (attr_done[slot]) return cudaSuccess;
     attr_done[slot] = true;
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   };
   if (rs != nullptr) {
     auto kern = mixed_gemm_kernel<CG, false, true>;
@@ -1016,6 +1057,10 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     }
     rs.tp = rsl->tp;
     rs.rank = rsl->rank;
+    int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / cg : sm_count() / cg;
+    if (groups < 1) groups = 1;
+    rs.rot_s = (int)((groups + rsl->tp - 1) / rsl->tp * rsl->tp);
+    rsl->rot_s = rs.rot_s;
   } else if (int rc = get_c_tmap(c, M, N, &tm.c)) {
     return rc;
   }

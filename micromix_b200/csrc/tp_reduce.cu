@@ -20,6 +20,7 @@
 //
 // Memory: one peer-mapped workspace per rank (mmx_peer_alloc + cudaIpc handles exchanged by the host code):
 //   [flags 256 KB][staging: 2 parities x tp slots x own_tiles_cap tiles of 256x256 bf16][C: 2 parities x M_cap x N_cap]
+// A staging tile is BOX-MAJOR: the 32 x 32 box (band b of 32 rows, column chunk sc) is the 2 KB at ((b * 8 + sc) * 2 KB).
 // Calls alternate the parity, which is all the protection the protocol needs: a rank can run at most one call ahead
 // of its peers (its reducer of call c cannot finish before every peer has pushed call c), so while a slow rank still
 // reads staging[c & 1] a fast rank writes staging[(c+1) & 1].  Counters are reset by their only reader.
@@ -79,10 +80,13 @@ struct ReduceParams {
   uint32_t* err;            // local
   __nv_bfloat16* c[kMaxTp];  // this parity's C on every rank (peer-mapped)
   int64_t M, N;
-  int rank, tile_rows, own_tiles, m_tiles, n_tiles, n_fastest;
+  int rank, tile_rows, own_tiles, m_tiles, n_tiles, n_fastest;  // own_tiles = blocks of tp tiles (the last may be partial)
+  int rot_s, num_tiles;
   uint32_t tile_expect;     // tp * 4 * CG arrivals complete a tile
   uint32_t done_expect;     // reducer CTAs of all ranks
   unsigned long long timeout_ns;
+  uint32_t dbg;             // timing experiments only (results wrong): 1 = no peer stores, 2 = no loads / sums / stores,
+                            // 4 = no tile waits
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -96,10 +100,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // bounded spin: a peer that never arrives (crashed rank, mismatched call sequence) costs a timeout, not the GPU
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// (polls are RELAXED loads -- an acquire per poll is a system-scope fence per poll on an SM that is also running the
+// GEMM's epilogue -- and one acquire fence follows the successful poll)
 __device__ bool spin_until(const uint32_t* flag, uint32_t target, unsigned long long timeout_ns) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
-    if (ld_acquire_sys(flag) >= target) return true;
+    if (ld_relaxed_sys(flag) >= target) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      return true;
+    }
     __nanosleep(64);
     if ((it & 1023u) == 0) {
       const unsigned long long now = global_ns();
@@ -122,6 +136,8 @@ __device__ __forceinline__ void acc_bf16x8(float (&a)[8], const uint4& v) {
   }
 }
 
+__device__ unsigned long long g_tp_times[8];  // timeline probe of reducer CTA 0: entry, first tile ready, last unit done, exit
+
 // Work unit = 64 rows of one owned tile (256 threads: 32 x 16-byte columns, 8 rows per pass).
 template <int TP>
 __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_constant__ ReduceParams p) {
@@ -132,17 +148,23 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
   const int c16 = tid & 31, r0 = tid >> 5;
   const int upt = p.tile_rows >> 6;
   const int units = p.own_tiles * upt;
+  if (blockIdx.x == 0 && tid == 0) g_tp_times[0] = global_ns();
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int own_idx = u / upt, sub = u - own_idx * upt;
-    if (tid == 0 && !spin_until(p.tile_flags + own_idx, p.tile_expect, p.timeout_ns)) atomicOr(p.err, 1u);
+    if (own_idx * TP + ((p.rank - (own_idx * TP) / p.rot_s) % TP + TP) % TP >= p.num_tiles) continue;  // partial last block
+    if (tid == 0 && !(p.dbg & 4u) && !spin_until(p.tile_flags + own_idx, p.tile_expect, p.timeout_ns)) atomicOr(p.err, 1u);
+    if (blockIdx.x == 0 && tid == 0 && u == 0) g_tp_times[1] = global_ns();
     __syncthreads();
-    const int tile = own_idx * TP + p.rank;
+    const int tile = own_idx * TP + ((p.rank - (own_idx * TP) / p.rot_s) % TP + TP) % TP;  // see RsParams::rot_s
     const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
     const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
     const int64_t grow0 = (int64_t)m_blk * p.tile_rows + sub * 64 + r0;
     const int64_t gcol = (int64_t)n_blk * 256 + c16 * 8;
-    const uint4* src = p.stage + ((int64_t)own_idx * p.tile_rows + sub * 64 + r0) * 32 + c16;
-    if (gcol < p.N) {
+    // box-major staging (see the RS epilogue in gemm.cu): box (band, sc) of a tile is 32 rows x 64 bytes, contiguous
+    const int bands = p.tile_rows >> 5;
+    const uint4* src = p.stage + ((((int64_t)own_idx * bands + sub * 2) * 8 + (c16 >> 2)) * 32 + r0) * 4 + (c16 & 3);
+    auto row_off = [](int k) { return (int64_t)((k >> 2) * (8 * 32 * 4) + (k & 3) * (8 * 4)); };  // row r0 + 8k, in uint4
+    if (gcol < p.N && !(p.dbg & 2u)) {
 #pragma unroll 1
       for (int i = 0; i < 8; i += 2) {
         uint4 v[2][TP];
@@ -151,7 +173,7 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
           const bool live = grow0 + 8 * (i + j) < p.M;
 #pragma unroll
           for (int s = 0; s < TP; ++s)
-            v[j][s] = live ? ld_cg_u4(src + (int64_t)s * p.slot_u4 + (i + j) * 8 * 32) : make_uint4(0, 0, 0, 0);
+            v[j][s] = live ? ld_cg_u4(src + (int64_t)s * p.slot_u4 + row_off(i + j)) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -169,7 +191,8 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
             }
             const int64_t off = grow * p.N + gcol;
 #pragma unroll
-            for (int d = 0; d < TP; ++d) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
+            for (int d = 0; d < TP; ++d)
+              if (!(p.dbg & 1u) || d == p.rank) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
           }
         }
       }
@@ -185,14 +208,17 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
     }
   }
   __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) g_tp_times[2] = global_ns();
   if (tid == 0) {
     // everything this CTA wrote into the ranks' C buffers is visible before the arrival
+    // (ONE system-scope fence, then relaxed arrivals: a release per destination would be a fence per destination)
     __threadfence_system();
 #pragma unroll
-    for (int d = 0; d < TP; ++d) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.done[d]) : "memory");
+    for (int d = 0; d < TP; ++d) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.done[d]) : "memory");
     // ... and this rank's C is complete once the reducer CTAs of ALL ranks have arrived here
     if (!spin_until(p.done[p.rank], p.done_expect, p.timeout_ns)) atomicOr(p.err, 2u);
     const uint32_t t = atomicAdd(p.ticket, 1u);
+    if (blockIdx.x == 0) g_tp_times[3] = global_ns();
     if (t == gridDim.x - 1) {  // every local CTA is past its spin: reset for the call after next
       *p.done[p.rank] = 0;
       *p.ticket = 0;
@@ -314,11 +340,11 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
     }
     c->ws[d] = static_cast<uint8_t*>(ws[d]);
   }
-  // my slot (index = my rank) in every destination's staging buffer, as a [rows, 256] bf16 tensor of tile rows
+  // my slot (index = my rank) in every destination's staging buffer, as a [boxes * 32, 32] bf16 tensor: box-major
   for (int par = 0; par < 2; ++par)
     for (int d = 0; d < tp; ++d) {
       uint8_t* base = c->ws[d] + c->L.stage_off + ((int64_t)par * tp + rank) * c->L.slot_bytes;
-      if (int rc = encode_store_tmap(base, c->L.own_tiles_cap * 256, 256, &c->maps[par][d])) {
+      if (int rc = encode_store_tmap(base, c->L.own_tiles_cap * 256 * 8, 32, &c->maps[par][d])) {
         delete c;
         return rc;
       }
@@ -329,6 +355,14 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
 
 MMX_API int mmx_tp_ctx_destroy(void* ctx) {
   delete static_cast<TpCtx*>(ctx);
+  return MMX_OK;
+}
+
+MMX_API int mmx_tp_debug_times(uint64_t* out, int n) {
+  unsigned long long tmp[8];
+  if (!out || n <= 0) return MMX_ERR_INVALID;
+  MMX_CUDA_TRY(cudaMemcpyFromSymbol(tmp, g_tp_times, sizeof(tmp)));
+  for (int i = 0; i < n && i < 8; ++i) out[i] = tmp[i];
   return MMX_OK;
 }
 
@@ -370,7 +404,8 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   if (rc) return rc;
   const int tile_rows = 128 * rsl.cg;
   const int num_tiles = rsl.m_tiles * rsl.n_tiles;
-  auto own_tiles = [&](int r) { return (num_tiles - r + tp - 1) / tp; };
+  // every rank walks ceil(num_tiles / tp) blocks; in a partial last block the ranks without a tile skip it
+  auto own_tiles = [&](int) { return (num_tiles + tp - 1) / tp; };
   uint8_t* me = c->ws[c->rank];
   ReduceParams p;
   memset(&p, 0, sizeof(p));
@@ -394,9 +429,12 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   p.m_tiles = rsl.m_tiles;
   p.n_tiles = rsl.n_tiles;
   p.n_fastest = rsl.n_fastest;
+  p.rot_s = rsl.rot_s;
+  p.num_tiles = num_tiles;
   p.tile_expect = (uint32_t)(tp * 4 * rsl.cg);
   p.done_expect = done_expect;
   p.timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
+  p.dbg = (uint32_t)options().tp_debug;
   const int grid = reducer_grid(p.own_tiles, tile_rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (tp) {
