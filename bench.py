@@ -162,6 +162,7 @@ def workload_config(args, world):
             "tokens": args.tokens, "split_4096": list(split_for(4096)), "split_14336": list(split_for(14336)),
             "parallelism": f"tp{world}" if world > 1 else "single",
             "tp_reduce": (args.tp_reduce if world > 1 and args.impl == "ours" else None),
+            "tp_chunks": (args.tp_chunks if world > 1 and args.impl == "ours" else None),
             "l2": "inputs+weights+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -263,10 +264,20 @@ def run_ours(args, rank, world, local_rank):
     if M % (C * 128):
         C = 1
     Mc = M // C
-    ws = None
+    ws, ws_note = None, None
     if world > 1 and args.tp_reduce == "fused":
         from micromix_b200.parallel_utils import PeerWorkspace
-        ws = PeerWorkspace(Mc, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
+        try:
+            ws = PeerWorkspace(Mc, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
+        except Exception as e:  # noqa: BLE001 -- no peer mapping on this box: every rank must agree on the fallback
+            ws_note = f"peer workspace unavailable ({e!r})"[:200]
+        ok = torch.tensor([1 if ws is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok.item()):
+            if ws is not None:
+                ws.close()
+            ws, args.tp_reduce = None, "nccl"
+            ws_note = ws_note or "peer workspace unavailable on another rank"
     if world > 1 and args.gemm_ctas > 0:
         lib.mmx_set_option(b"gemm_ctas", args.gemm_ctas)  # leave SMs to the concurrent NCCL kernel
     chunks = []
@@ -391,8 +402,9 @@ def run_ours(args, rank, world, local_rank):
 
     clocks = sampler.summary()
     sampler.stop_flag.set()
-    tp_status = None
+    tp_status, ws_mode = None, None
     if ws is not None:
+        ws_mode = ws.mode
         tp_status = ws.status()  # 0 = no reducer wait ever timed out
         ws.close()
     line = {"metric": METRIC, "value": total_flops / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
@@ -412,7 +424,8 @@ def run_ours(args, rank, world, local_rank):
     if tp_status is not None:
         line["tp_fused_status"] = tp_status
     if world > 1:
-        line["tp"] = {"chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
+        line["tp"] = {"reduce": args.tp_reduce, "fused_mode": ws_mode, "fallback_note": ws_note,
+                      "chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
                       "gemm_ctas": args.gemm_ctas or None,
                       "per_kernel_times": "eager evented pass after the timed region" if graph is not None
                       else "events inside the timed region"}
@@ -514,13 +527,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-tokens", type=int, default=2048, help="token sample for the host-core baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tp-chunks", type=int, default=2,
+    ap.add_argument("--tp-chunks", type=int, default=1,
                     help="N>1: token micro-batches per step; a chunk's all-reduce overlaps the other chunks' kernels")
     ap.add_argument("--gemm-ctas", type=int, default=0, help="N>1: cap the persistent GEMM grid (SMs left to NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
-    ap.add_argument("--tp-reduce", default="nccl", choices=["nccl", "fused"],
-                    help="row-parallel reduction at N>1: NCCL all-reduce, or our GEMM->all-reduce over NVLink peer memory")
+    ap.add_argument("--tp-reduce", default="fused", choices=["nccl", "fused"],
+                    help="row-parallel reduction at N>1: our GEMM->all-reduce over NVLink peer / NVSwitch multicast memory "
+                         "(default; falls back to NCCL, and says so, if the peer workspace cannot be mapped), or mmx_matmul "
+                         "+ NCCL all-reduce")
     args = ap.parse_args()
     args.steps_ref = max(1, min(args.steps, 3))
     args.warmup_ref = max(1, min(args.warmup, 1))

@@ -163,6 +163,14 @@ int mmx_peer_close(void* ptr);
 int mmx_peer_free(void* ptr);
 int64_t mmx_tp_workspace_bytes(int64_t M_cap, int64_t N_cap, int tp);
 int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, void** ctx);
+/* Optional: mc_ws = an NVSwitch MULTICAST mapping of the same workspaces (cuMulticast*; the Python host code gets it from
+ * torch's symmetric-memory rendezvous).
+ *   in_switch_reduce = 0: the reducer writes each result tile with one multimem.st instead of tp peer stores (same bits).
+ *   in_switch_reduce = 1: partial tiles stay in every rank's own C; the owner's reducer sums them INSIDE the switch
+ *     (multimem.ld_reduce, fp32 accumulation) and multicasts the bf16 result: per rank and direction NVLink carries the
+ *     output once instead of 2(tp-1)/tp times.  All ranks receive identical bits; the summation order is the switch's,
+ *     so the result may differ from the rank-ordered fp32 sum in the last bf16 bit. */
+int mmx_tp_ctx_set_multicast(void* ctx, void* mc_ws, int in_switch_reduce);
 int mmx_tp_ctx_destroy(void* ctx);
 int mmx_tp_status(void* ctx, uint32_t* out);
 int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,

@@ -33,6 +33,7 @@ SYMBOLS = {
     "mmx_peer_free": (_i32, [_vp]),
     "mmx_tp_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "mmx_tp_ctx_create": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, ctypes.POINTER(_vp)]),
+    "mmx_tp_ctx_set_multicast": (_i32, [_vp, _vp, _i32]),
     "mmx_tp_ctx_destroy": (_i32, [_vp]),
     "mmx_tp_status": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
     "mmx_matmul_allreduce": (_i32, [_vp] + [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp,

@@ -52,6 +52,8 @@ struct RsLaunch {
   // filled in by matmul_impl: the tile geometry the reducer must mirror
   int cg, m_tiles, n_tiles, n_fastest;
   int rot_s;                 // owner rotation period, see RsParams in gemm.cu
+  int pull;                  // 1: in-switch reduction -- the epilogue stores the partial tile into c_local (this rank's own
+  void* c_local;             //    C of the call's parity, ordinary [M, N] coordinates) and only the arrival goes to the owner
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,

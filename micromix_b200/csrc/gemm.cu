@@ -116,6 +116,7 @@ struct alignas(64) RsParams {
   uint32_t* tile_flags[kMaxTp];  // rank d's per-owned-tile arrival counters (peer-mapped)
   int tp, rank;
   int rot_s;  // owner rotation period (a multiple of tp): owner(tile) = (tile + tile / tp * tp / rot_s) % tp
+  int pull;   // 1: partial tiles go into this rank's own C (tmaps.c) and are reduced in the switch by the owner
 };
 struct NoRsParams {
   int unused;
@@ -679,9 +680,11 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         // share over NVLink rather than half of them pushing everything (tp = 2, even #groups)
         own_idx = tile / rs.tp;
         owner = (tile + (own_idx * rs.tp) / rs.rot_s) % rs.tp;
-        cmap = &rs.dst[(p.flags & 8u) ? rs.rank : owner];  // flag 8: timing experiment, partials stay local
-        st_row0 = own_idx * (CG * BM) + (int)rank * BM + q * 32;
-        st_col_base = 0;
+        if (!rs.pull) {
+          cmap = &rs.dst[(p.flags & 8u) ? rs.rank : owner];  // flag 8: timing experiment, partials stay local
+          st_row0 = own_idx * (CG * BM) + (int)rank * BM + q * 32;
+          st_col_base = 0;
+        }
       }
       // 32-column chunks, the columns shared with the other accumulator first: the top ones of acc0, the bottom
       // ones of acc1.  Once those are in registers the MMA warp may start the next tile.
@@ -702,7 +705,9 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           if (lane == 0 && do_store) {
             // C: clipped at M and N by the map.  RS: the staging slot is BOX-MAJOR -- every 32 x 32 box is 2 KB of
             // contiguous peer memory (64-byte rows of a row-major tile travel over NVLink at less than half the rate)
-            if constexpr (RS) tma_store_2d(cmap, buf, 0, st_row0 * 8 + sc * 32);
+            bool box_major = false;
+            if constexpr (RS) box_major = !rs.pull;
+            if (box_major) tma_store_2d(cmap, buf, 0, st_row0 * 8 + sc * 32);
             else tma_store_2d(cmap, buf, st_col_base + sc * 32, st_row0);
           }
           ++nstore;
@@ -1061,6 +1066,10 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     if (groups < 1) groups = 1;
     rs.rot_s = (int)((groups + rsl->tp - 1) / rsl->tp * rsl->tp);
     rsl->rot_s = rs.rot_s;
+    rs.pull = rsl->pull;
+    if (rsl->pull) {
+      if (int rc = get_c_tmap(rsl->c_local, M, N, &tm.c)) return rc;
+    }
   } else if (int rc = get_c_tmap(c, M, N, &tm.c)) {
     return rc;
   }

@@ -67,6 +67,8 @@ struct TpCtx {
   uint8_t* ws[kMaxTp];
   TpLayout L;
   CUtensorMap maps[2][kMaxTp];  // [parity][destination rank]
+  uint8_t* mc;                  // NVSwitch multicast mapping of the whole workspace (all ranks), or null
+  int pull;                     // reduce in the switch (multimem.ld_reduce) instead of pushing partials to owner slots
   uint64_t calls;
 };
 
@@ -79,9 +81,11 @@ struct ReduceParams {
   uint32_t* ticket;         // local
   uint32_t* err;            // local
   __nv_bfloat16* c[kMaxTp];  // this parity's C on every rank (peer-mapped)
+  __nv_bfloat16* mc_c;       // ... and its multicast address (one multimem.st reaches every rank), or null
   int64_t M, N;
   int rank, tile_rows, own_tiles, m_tiles, n_tiles, n_fastest;  // own_tiles = blocks of tp tiles (the last may be partial)
   int rot_s, num_tiles;
+  int pull;                 // 1: partials live in every rank's own C, reduced in the switch (needs mc_c)
   uint32_t tile_expect;     // tp * 4 * CG arrivals complete a tile
   uint32_t done_expect;     // reducer CTAs of all ranks
   unsigned long long timeout_ns;
@@ -164,7 +168,36 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
     const int bands = p.tile_rows >> 5;
     const uint4* src = p.stage + ((((int64_t)own_idx * bands + sub * 2) * 8 + (c16 >> 2)) * 32 + r0) * 4 + (c16 & 3);
     auto row_off = [](int k) { return (int64_t)((k >> 2) * (8 * 32 * 4) + (k & 3) * (8 * 4)); };  // row r0 + 8k, in uint4
-    if (gcol < p.N && !(p.dbg & 2u)) {
+    if (p.pull) {
+      // IN-SWITCH reduction: every rank's GEMM wrote its partial tile into ITS OWN C (same offsets everywhere); one
+      // multimem.ld_reduce makes the NVSwitch read the tp copies and return their sum (fp32 accumulation), one
+      // multimem.st writes the bf16 result back over all tp copies.  Per rank and direction the wire carries the
+      // output once instead of 2(tp-1)/tp times; every rank receives the same bits.
+      if (gcol < p.N && !(p.dbg & 2u)) {
+#pragma unroll 1
+        for (int i = 0; i < 8; i += 4) {
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t grow = grow0 + 8 * (i + j);
+            if (grow < p.M)
+              asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
+                           : "l"(p.mc_c + grow * p.N + gcol)
+                           : "memory");
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t grow = grow0 + 8 * (i + j);
+            if (grow < p.M && !(p.dbg & 1u))
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc_c + grow * p.N + gcol),
+                           "f"(__uint_as_float(v[j].x)), "f"(__uint_as_float(v[j].y)), "f"(__uint_as_float(v[j].z)),
+                           "f"(__uint_as_float(v[j].w))
+                           : "memory");
+          }
+        }
+      }
+    } else if (gcol < p.N && !(p.dbg & 2u)) {
 #pragma unroll 1
       for (int i = 0; i < 8; i += 2) {
         uint4 v[2][TP];
@@ -190,9 +223,17 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
               ow[e] = *reinterpret_cast<uint32_t*>(&h);
             }
             const int64_t off = grow * p.N + gcol;
+            if (p.mc_c != nullptr && !(p.dbg & 1u)) {
+              // the switch replicates the store to every rank's C (own included): 1/tp of the NVLink egress
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc_c + off),
+                           "f"(__uint_as_float(o.x)), "f"(__uint_as_float(o.y)), "f"(__uint_as_float(o.z)),
+                           "f"(__uint_as_float(o.w))
+                           : "memory");
+            } else {
 #pragma unroll
-            for (int d = 0; d < TP; ++d)
-              if (!(p.dbg & 1u) || d == p.rank) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
+              for (int d = 0; d < TP; ++d)
+                if (!(p.dbg & 1u) || d == p.rank) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
+            }
           }
         }
       }
@@ -353,6 +394,17 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
   return MMX_OK;
 }
 
+MMX_API int mmx_tp_ctx_set_multicast(void* ctx, void* mc_ws, int in_switch_reduce) {
+  TpCtx* c = static_cast<TpCtx*>(ctx);
+  if (!c || ((uintptr_t)mc_ws & 255) || (in_switch_reduce && !mc_ws)) {
+    set_error("mmx_tp_ctx_set_multicast: null context, misaligned multicast pointer, or in-switch reduce without one");
+    return MMX_ERR_INVALID;
+  }
+  c->mc = static_cast<uint8_t*>(mc_ws);
+  c->pull = in_switch_reduce ? 1 : 0;
+  return MMX_OK;
+}
+
 MMX_API int mmx_tp_ctx_destroy(void* ctx) {
   delete static_cast<TpCtx*>(ctx);
   return MMX_OK;
@@ -399,6 +451,8 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   rsl.tp = tp;
   rsl.rank = c->rank;
   rsl.own_tiles_cap = c->L.own_tiles_cap;
+  rsl.pull = c->pull;
+  rsl.c_local = c->ws[c->rank] + c->L.out_off + (int64_t)par * c->L.out_bytes;
   int rc = matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, nullptr,
                        stream, &rsl);
   if (rc) return rc;
@@ -419,6 +473,7 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   for (int d = 0; d < tp; ++d) {
     p.done[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffDone + 128 * par);
     p.c[d] = reinterpret_cast<__nv_bfloat16*>(c->ws[d] + c->L.out_off + (int64_t)par * c->L.out_bytes);
+    if (c->mc) p.mc_c = reinterpret_cast<__nv_bfloat16*>(c->mc + c->L.out_off + (int64_t)par * c->L.out_bytes);
     done_expect += (uint32_t)reducer_grid(own_tiles(d), tile_rows);
   }
   p.M = M;
@@ -431,6 +486,7 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   p.n_fastest = rsl.n_fastest;
   p.rot_s = rsl.rot_s;
   p.num_tiles = num_tiles;
+  p.pull = c->pull;
   p.tile_expect = (uint32_t)(tp * 4 * rsl.cg);
   p.done_expect = done_expect;
   p.timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;

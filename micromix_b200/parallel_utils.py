@@ -92,8 +92,17 @@ class PeerWorkspace:
     loads / stores / reductions over NVLink.
     """
 
-    def __init__(self, M_cap: int, N_cap: int, group=None, device=None, _sim=None):
+    def __init__(self, M_cap: int, N_cap: int, group=None, device=None, _sim=None, mode: Optional[str] = None):
+        """mode: "push" (partials pushed to owner slots over peer mappings, rank-ordered fp32 sum),
+        "switch" (partials reduced inside the NVSwitch through a multicast mapping), or None = "auto": the environment
+        variable MMX_TP_MODE if set, else "switch" for tp >= 4 when the box offers multicast memory, "push" otherwise
+        (at tp = 2 the switch path loops every result back to its sender and moves more bytes than the push path)."""
         import ctypes
+        import os
+        mode = mode or os.environ.get("MMX_TP_MODE", "auto")
+        if mode not in ("auto", "push", "switch", "push_mc"):
+            raise ValueError(f"PeerWorkspace mode {mode!r}: expected auto, push, switch or push_mc")
+        self.multicast_ptr, self._symm_buf = 0, None
         from . import _lib
         self.lib = lib = _lib.load()
         self._ctypes = ctypes
@@ -112,32 +121,64 @@ class PeerWorkspace:
             self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
             if self.nbytes <= 0:
                 raise ValueError(f"tensor-parallel degree {self.tp} is not supported by the fused path (1, 2, 4, 8)")
-            with torch.cuda.device(self.device):
-                own = ctypes.c_void_p()
-                handle = ctypes.create_string_buffer(64)
-                _lib.check(lib.mmx_peer_alloc(self.nbytes, ctypes.byref(own), handle), "mmx_peer_alloc")
-                self.own = own.value
-                handles = [None] * self.tp
-                dist.all_gather_object(handles, bytes(handle.raw), group=group)
-                ptrs = []
-                for r, h in enumerate(handles):
-                    if r == self.rank:
-                        ptrs.append(self.own)
-                        continue
-                    p = ctypes.c_void_p()
-                    _lib.check(lib.mmx_peer_open(h, ctypes.byref(p)), f"mmx_peer_open(rank {r})")
-                    self.peers.append(p.value)
-                    ptrs.append(p.value)
+            if mode == "auto":
+                mode = "switch" if self.tp >= 4 else "push"
+            ptrs = self._map_symmetric(group) if mode in ("switch", "push_mc") else None
+            if ptrs is None:
+                if mode == "switch" and os.environ.get("MMX_TP_MODE") == "switch":
+                    raise RuntimeError("MMX_TP_MODE=switch, but this box / torch build offers no multicast memory")
+                mode = "push"
+                with torch.cuda.device(self.device):
+                    own = ctypes.c_void_p()
+                    handle = ctypes.create_string_buffer(64)
+                    _lib.check(lib.mmx_peer_alloc(self.nbytes, ctypes.byref(own), handle), "mmx_peer_alloc")
+                    self.own = own.value
+                    handles = [None] * self.tp
+                    dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                    ptrs = []
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            ptrs.append(self.own)
+                            continue
+                        p = ctypes.c_void_p()
+                        _lib.check(lib.mmx_peer_open(h, ctypes.byref(p)), f"mmx_peer_open(rank {r})")
+                        self.peers.append(p.value)
+                        ptrs.append(p.value)
         arr = (ctypes.c_void_p * self.tp)(*ptrs)
         ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(lib.mmx_tp_ctx_create(arr, self.tp, self.rank, self.M_cap, self.N_cap, ctypes.byref(ctx)),
                        "mmx_tp_ctx_create")
         self.ctx = ctx
+        self.mode = mode if _sim is None else "push"
+        if self.multicast_ptr:
+            _lib.check(lib.mmx_tp_ctx_set_multicast(ctx, self.multicast_ptr, 1 if self.mode == "switch" else 0),
+                       "mmx_tp_ctx_set_multicast")
         self._base = ptrs[self.rank]
         self._views = {}
         if _sim is None:
             dist.barrier(group)  # every rank's workspace is zeroed and mapped before anyone's first kernel
+
+    def _map_symmetric(self, group):
+        """Workspace from torch's symmetric-memory allocator (plumbing: allocation + handle exchange): the same peer
+        mappings as the cudaIpc path PLUS an NVSwitch multicast address of the whole workspace, which lets the reducer
+        write a result tile to every rank with ONE multimem.st instead of tp peer stores.  Returns the per-rank
+        pointers, or None when this box / torch build has no multicast (the cudaIpc path is used then)."""
+        try:
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            buf = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            h = symm.rendezvous(buf, pg.group_name)
+            mc = int(getattr(h, "multicast_ptr", 0) or 0)
+            ptrs = [int(x) for x in h.buffer_ptrs]
+            if not mc or len(ptrs) != self.tp or ptrs[self.rank] != buf.data_ptr():
+                return None
+            buf.zero_()
+            torch.cuda.synchronize(self.device)
+            self._symm_buf, self._symm_handle, self.multicast_ptr = buf, h, mc
+            return ptrs
+        except Exception:  # noqa: BLE001 -- no symmetric memory here: fall back to cudaIpc peer mappings
+            return None
 
     @classmethod
     def simulate(cls, tp: int, M_cap: int, N_cap: int):

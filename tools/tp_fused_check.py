@@ -78,10 +78,21 @@ def main():
             want += p_.float()
         want = want.to(torch.bfloat16)
         ok = True
+        ulp_off = 0.0
         for call in range(3):
             y = fused(x).view(M, N)
             torch.cuda.synchronize()
-            ok = ok and bool(torch.equal(y, want)) and ws.status() == 0
+            if ws.mode == "switch":
+                # the switch sums in its own order (fp32 accumulation): identical bits on every rank, and within one
+                # bf16 rounding step of the rank-ordered sum
+                y0 = y.clone()
+                dist.broadcast(y0, src=0)
+                d = (y.float() - want.float()).abs()
+                tol = want.float().abs() * 2.0 ** -7 + 1e-30
+                ulp_off = max(ulp_off, float((d > 0).float().mean()))
+                ok = ok and bool(torch.equal(y, y0)) and bool((d <= tol).all()) and ws.status() == 0
+            else:
+                ok = ok and bool(torch.equal(y, want)) and ws.status() == 0
         y_nccl = plain(x).view(M, N).float()
         dn = float((y_nccl - want.float()).abs().max() / want.float().abs().max())
         flag = torch.tensor([1 if ok else 0], device=dev)
@@ -92,7 +103,8 @@ def main():
         t_plain = timed(lambda: plain(x), args.iters, 5, dev)
         t_local = timed(lambda: fused.linear(x), args.iters, 5, dev)
         if rank == 0:
-            print(json.dumps({"tp": world, "M": M, "N": N, "K": K, "K_local": k1 - k0, "bit_exact_all_ranks": bool(flag.item()),
+            print(json.dumps({"tp": world, "mode": ws.mode, "M": M, "N": N, "K": K, "K_local": k1 - k0, "bit_exact_all_ranks": bool(flag.item()),
+                              "frac_elems_off_by_one_rounding": ulp_off,
                               "nccl_vs_exact_max_rel": dn, "fused_us": round(t_fused, 1), "gemm_plus_nccl_us": round(t_plain, 1),
                               "local_quant_gemm_us": round(t_local, 1),
                               "exposed_reduce_us_fused": round(t_fused - t_local, 1),

@@ -51,7 +51,7 @@ def main():
         x = torch.randn(M, k1 - k0, generator=g, device=dev).to(torch.bfloat16)
         A = mixedgemm.reorder_quantize_x(x, lidx, p4, p6, p8)
         out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-        res = {"tp": world, "M": M, "N": N, "K_local": k1 - k0}
+        res = {"tp": world, "M": M, "N": N, "K_local": k1 - k0, "mode": ws.mode}
         res["gemm_local_us"] = timed(lambda: mixedgemm.matmul(A[0], W[0], A[1], W[1], A[2], W[2], A[3], W[3], A[4], W[4],
                                                                A[5], W[5], out=out), 20, dev)
         res["nccl_allreduce_us"] = timed(lambda: dist.all_reduce(out), 20, dev)
