@@ -24,6 +24,7 @@ struct Options {
   int64_t pdl = 1;            // 1: kernels are launched with programmatic stream serialization (prologue overlap)
   int64_t gemm_raster = 0;    // 0: auto, 1: force M-fastest tile order, 2: force N-fastest
   int64_t gemm_cta_group = 0; // 0: auto (pairs when M > 128), 1: force the single-CTA kernel
+  int64_t gemm_splitk = 0;    // M <= 128: 0 auto, 1 never split K, 2 | 4 | 8 force that cluster size (if it fits)
   int64_t tp_reduce_ctas = 0; // 0: one reducer CTA per SM, else cap the tile_allreduce_kernel grid (single-GPU tests)
   int64_t tp_debug = 0;       // timing experiments of the fused all-reduce (results wrong): see ReduceParams::dbg
   int64_t tp_timeout_ms = 10000;  // bound on every cross-rank spin of tile_allreduce_kernel (a lost peer cannot hang the GPU)

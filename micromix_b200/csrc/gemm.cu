@@ -407,10 +407,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <int CG, bool WD, bool RS>
+// SK > 1 (small M, single-CTA tiles only): SPLIT-K over a cluster of SK CTAs.  A 128 x 256 tile of a decode-sized GEMM
+// is bound by streaming its B panel, and N / 256 CTAs cannot pull the weights at HBM rate; here SK CTAs each accumulate a
+// contiguous 1/SK of the tile's K stages in their own TMEM, park the fp32 accumulator in their (now idle) stage buffers,
+// and CTA r of the cluster sums column slice r of all SK copies through distributed shared memory -- in CTA order, so the
+// result does not depend on timing -- and writes bf16.  One tile per cluster, no global workspace, no atomics.
+template <int CG, bool WD, bool RS, int SK = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p,
                   const __grid_constant__ std::conditional_t<RS, RsParams, NoRsParams> rs) {
+  static_assert(SK == 1 || (CG == 1 && !WD && !RS), "split-K is a variant of the plain single-CTA kernel");
   using G = Geo<CG, RS>;
   constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
@@ -426,9 +432,19 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
-  const int group = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
-  const int ngroups = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+  const int group = (CG == 2) ? (blockIdx.x >> 1) : (SK > 1 ? (int)(blockIdx.x / SK) : (int)blockIdx.x);
+  const int ngroups = (CG == 2) ? (gridDim.x >> 1) : (SK > 1 ? (int)(gridDim.x / SK) : (int)gridDim.x);
   const int num_tiles = p.m_tiles * p.n_tiles;
+  // split-K: this CTA's share [sk_lo, sk_hi) of the tile's concatenated stage list (all segments, in order)
+  int sk_lo = 0, sk_hi = 0x7fffffff;
+  uint32_t krank = 0;
+  if constexpr (SK > 1) {
+    krank = cluster_ctarank();
+    int total = 0;
+    for (int s = 0; s < p.nseg; ++s) total += p.seg[s].ktiles;
+    sk_lo = (int)((long long)krank * total / SK);
+    sk_hi = (int)((long long)(krank + 1) * total / SK);
+  }
 
   // programmatic dependent launch: the next kernel in the stream may start its prologue as SMs free up
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -476,10 +492,14 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
         const int a_row = (m_blk * CG + (int)rank) * BM;          // this CTA's A rows
         const int b_row = n_blk * BN + (int)rank * G::kBRows;      // this CTA's share of the B rows
+        int seg_off = 0;  // split-K: stages of the segments before this one
         for (int s = 0; s < p.nseg && ok; ++s) {
           const GemmSeg& sg = p.seg[s];
           const uint32_t sf_bytes = (uint32_t)sg.atoms_per_tile * 512u * 3u;  // SFA + two SFB row blocks
-          for (int kt = 0; kt < sg.ktiles; ++kt) {
+          const int kt_lo = SK > 1 ? max(0, sk_lo - seg_off) : 0;
+          const int kt_hi = SK > 1 ? min(sg.ktiles, sk_hi - seg_off) : sg.ktiles;
+          seg_off += sg.ktiles;
+          for (int kt = kt_lo; kt < kt_hi; ++kt) {
             const long long tw0 = WD ? clk() : 0;
             if (!mbar_wait<WD>(empty_bar(stage), phase ^ 1)) {
               if (WD) atomicOr(&p.dbg[0], 0x1u | (uint32_t)(stage << 8) | (uint32_t)(s << 16) | (rank << 24));
@@ -605,6 +625,27 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         if (WD) t_tmem += clk() - tt0;
         tc_fence_after();
         const uint32_t d_acc = tmem_base + ((tcount & 1u) ? kColAcc1 : 0u);
+        if constexpr (SK > 1) {
+          // this CTA's slice of the stage list; per-stage dispatch is fine here (the kernel streams weights)
+          int seg_off = 0, issued = 0;
+          const int mine = sk_hi - sk_lo;
+          for (int sidx = 0; sidx < p.nseg && ok; ++sidx) {
+            const GemmSeg& sg = p.seg[sidx];
+            const int kt_lo = max(0, sk_lo - seg_off), kt_hi = min(sg.ktiles, sk_hi - seg_off);
+            seg_off += sg.ktiles;
+            for (int kt = kt_lo; kt < kt_hi && ok; ++kt, ++issued) {
+              const bool first = issued == 0, last = issued == mine - 1;
+              if (sg.kind == 0) {
+                if (kt == sg.ktiles - 1 && sg.last_atoms == 1)
+                  issue_stage(integral_constant<int, 0>{}, integral_constant<int, 1>{}, sg.idesc, d_acc, first, last);
+                else
+                  issue_stage(integral_constant<int, 0>{}, integral_constant<int, 2>{}, sg.idesc, d_acc, first, last);
+              } else {
+                issue_stage(integral_constant<int, 1>{}, integral_constant<int, 1>{}, sg.idesc, d_acc, first, last);
+              }
+            }
+          }
+        } else
         for (int sidx = 0; sidx < p.nseg && ok; ++sidx) {
           const GemmSeg& sg = p.seg[sidx];
           const int ktiles = sg.ktiles;
@@ -668,6 +709,32 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       const int row0 = (m_blk * CG + (int)rank) * BM + q * 32;  // first C row of this warp's 32-row band
       const bool odd = (tcount & 1u) != 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (odd ? kColAcc1 : 0u);
+      if constexpr (SK > 1) {
+        // park the fp32 partial accumulator in the stage buffers (every MMA has read them: tmem_full follows the last
+        // commit): row r = 1 KB, 16-byte chunk c at (c ^ (r & 7)) -- conflict-free for the row-per-lane writes here
+        // and for the chunk-per-lane reads of the reduction
+        const uint32_t srow = smem_base + (uint32_t)(q * 32 + lane) * 1024u;
+        const uint32_t sw = (uint32_t)lane & 7u;
+        const bool row_live = row0 + lane < p.M;  // decode: most of the 128 rows do not exist and are never reduced
+        if (row0 < p.M) {                         // warp-uniform (tcgen05.ld is warp-collective)
+#pragma unroll 1
+          for (int i = 0; i < BN / 32; ++i) {
+            if (n_blk * BN + i * 32 >= p.N) break;
+            uint32_t r[32];
+            tmem_ld32(tbase + (uint32_t)(i * 32), r);
+            tmem_ld_wait();
+            if (row_live) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((uint32_t)(i * 8 + v)) ^ sw) << 4)),
+                             "r"(r[4 * v]), "r"(r[4 * v + 1]), "r"(r[4 * v + 2]), "r"(r[4 * v + 3])
+                             : "memory");
+            }
+          }
+        }
+        tc_fence_before();
+        break;  // one tile per cluster; the reduction follows the role branches
+      }
       const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
       const uint32_t nstore_tile0 = nstore;
       // where this warp's 32-row band goes: C itself, or (RS) the owner rank's staging tile, tile-local coordinates
@@ -780,6 +847,50 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
     }
   }
 
+  if constexpr (SK > 1) {
+    cluster_sync_all();  // every CTA of the cluster has parked its partial tile
+    if (warp >= 2 && group < num_tiles) {
+      constexpr int CH = (BN / SK) / 4;  // 16-byte fp32 chunks per row of this CTA's column slice
+      const int m_blk = p.n_fastest ? group / p.n_tiles : group % p.m_tiles;
+      const int n_blk = p.n_fastest ? group % p.n_tiles : group / p.m_tiles;
+      const int live_rows = (int)min((int64_t)BM, p.M - (int64_t)m_blk * BM);
+      for (int idx = (int)threadIdx.x - 64; idx < live_rows * CH; idx += kThreads - 64) {
+        const int row = idx / CH;
+        const int c = (int)krank * CH + idx % CH;  // chunk index inside the 256-column row
+        const int64_t grow = (int64_t)m_blk * BM + row;
+        const int gcol = n_blk * BN + c * 4;
+        if (grow >= p.M || gcol >= p.N) continue;
+        const uint32_t local = smem_base + (uint32_t)row * 1024u + ((((uint32_t)c) ^ ((uint32_t)row & 7u)) << 4);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int sidx = 0; sidx < SK; ++sidx) {  // CTA order: the sum does not depend on timing
+          float x0, x1, x2, x3;
+          asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3)
+                       : "r"(mapa_rank(local, (uint32_t)sidx)));
+          a0 += x0;
+          a1 += x1;
+          a2 += x2;
+          a3 += x3;
+        }
+        uint32_t w0 = pack_bf16(a0, a1), w1 = pack_bf16(a2, a3);
+        if (p.bias != nullptr) {  // y = bf16(acc); y = bf16(y + bias), as in pack_chunk
+          const uint2 bv = __ldg(reinterpret_cast<const uint2*>(p.bias + gcol));
+          w0 = pack_bf16(__uint_as_float(w0 << 16) + __uint_as_float(bv.x << 16),
+                         __uint_as_float(w0 & 0xffff0000u) + __uint_as_float(bv.x & 0xffff0000u));
+          w1 = pack_bf16(__uint_as_float(w1 << 16) + __uint_as_float(bv.y << 16),
+                         __uint_as_float(w1 & 0xffff0000u) + __uint_as_float(bv.y & 0xffff0000u));
+        }
+        *reinterpret_cast<uint2*>(p.c + grow * p.N + gcol) = make_uint2(w0, w1);
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its shared memory
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc<CG>(tmem_base, kTmemCols);
+    }
+    return;
+  }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -973,6 +1084,65 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   return MMX_OK;
 }
 
+// Split-K launch (M <= 128): one cluster of SK CTAs per 128 x 256 tile.
+template <int SK>
+static int launch_gemm_splitk(const TmapSet& tm, GemmParams& p, cudaStream_t st, bool probe_only, int* max_clusters) {
+  using G = Geo<1, false>;
+  auto kern = mixed_gemm_kernel<1, false, false, SK>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+    attr_done = true;
+  }
+  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(tiles * SK));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = G::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = SK;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  if (probe_only) {  // how many clusters of this size can be resident at once (cached by the caller)
+    cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(SK * 64));
+    int n = 0;
+    MMX_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    *max_clusters = n;
+    return MMX_OK;
+  }
+  const NoRsParams none = {0};
+  MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, none));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MMX_OK;
+}
+
+// Largest split (8, 4, 2) whose clusters -- one per tile -- are all resident in ONE wave and get at least two stages each.
+static int choose_splitk(const TmapSet& tm, GemmParams& p, int64_t tiles, int total_stages) {
+  const int64_t forced = options().gemm_splitk;
+  if (forced == 1) return 1;
+  static int cap[9] = {0, 0, -1, 0, -1, 0, 0, 0, -1};  // resident clusters per size, -1 = not probed yet
+  for (int sk = 8; sk >= 2; sk >>= 1) {
+    if (forced > 1 && forced != sk) continue;
+    if (total_stages < 2 * sk && forced != sk) continue;
+    if (total_stages < sk) continue;
+    if (cap[sk] < 0) {
+      int n = 0;
+      const int rc = sk == 8 ? launch_gemm_splitk<8>(tm, p, nullptr, true, &n)
+                             : (sk == 4 ? launch_gemm_splitk<4>(tm, p, nullptr, true, &n) : launch_gemm_splitk<2>(tm, p, nullptr, true, &n));
+      cap[sk] = rc == MMX_OK ? n : 0;
+    }
+    if (tiles <= cap[sk]) return sk;
+  }
+  return 1;
+}
+
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
                 const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
@@ -1084,6 +1254,19 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   p.flags = (uint32_t)options().gemm_debug_flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const RsParams* rsp = rsl != nullptr ? &rs : nullptr;
+  if (cg == 1 && rsl == nullptr && options().gemm_watchdog == 0) {
+    // decode-sized M: split K over a cluster when the tiles alone cannot occupy the machine
+    p.m_tiles = (int)((M + BM - 1) / BM);
+    p.n_tiles = (int)((N + BN - 1) / BN);
+    p.n_fastest = 1;
+    int total_stages = 0;
+    for (int i = 0; i < ns; ++i) total_stages += p.seg[i].ktiles;
+    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+    const int sk = tiles * 2 <= sm_count() ? choose_splitk(tm, p, tiles, total_stages) : 1;
+    if (sk == 8) return launch_gemm_splitk<8>(tm, p, st, false, nullptr);
+    if (sk == 4) return launch_gemm_splitk<4>(tm, p, st, false, nullptr);
+    if (sk == 2) return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
+  }
   const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp) : launch_gemm<1>(tm, p, st, rsp);
   if (rc == MMX_OK && rsl != nullptr) {
     rsl->cg = cg;

@@ -69,6 +69,7 @@ extern "C" __attribute__((visibility("default"))) int mmx_set_option(const char*
   else if (!std::strcmp(key, "quant_ctas")) o.quant_ctas = value;
   else if (!std::strcmp(key, "gemm_ctas")) o.gemm_ctas = value;
   else if (!std::strcmp(key, "tp_debug")) o.tp_debug = value;
+  else if (!std::strcmp(key, "gemm_splitk")) o.gemm_splitk = value;
   else if (!std::strcmp(key, "gemm_cta_group")) o.gemm_cta_group = value;
   else if (!std::strcmp(key, "gemm_debug_flags")) o.gemm_debug_flags = value;
   else if (!std::strcmp(key, "gemm_raster")) o.gemm_raster = value;

@@ -188,3 +188,31 @@ def test_errors(cuda):
         mixedgemm.matmul(u(4, 64), u(100, 64), u(4, 0), u(100, 0), u(4, 0), u(100, 0), u(512), u(512), u(0), u(0), u(0), u(0))
     with pytest.raises(ValueError):  # SF buffer too small
         mixedgemm.matmul(u(4, 64), u(128, 64), u(4, 0), u(128, 0), u(4, 0), u(128, 0), u(16), u(512), u(0), u(0), u(0), u(0))
+
+
+@pytest.mark.parametrize("sk", [0, 2, 4, 8])
+@pytest.mark.parametrize("M,N,split", [(1, 4096, (2560, 1024, 512)), (16, 1024, (384, 128, 128)), (128, 512, (640, 256, 128)),
+                                       (77, 384, (2688, 0, 1408)), (5, 256, (0, 1024, 0)), (128, 4096, (8960, 3584, 1792))])
+def test_splitk_decode_shapes(cuda, mmx_lib, sk, M, N, split):
+    """M <= 128: split-K over a CTA cluster (DSMEM reduction in CTA order).  Against the oracle within the GEMM tolerance,
+    against the unsplit kernel within fp32 re-association (a couple of bf16 steps), deterministic run to run, with and
+    without bias.  sk = 0 is the automatic choice."""
+    K = sum(split)
+    idx = H.make_index(K, seed=sk + M)
+    x, w = H.make_activations(M, K, idx, seed=31 + M), H.make_weights(N, K, seed=47 + N)
+    a, b = _quantize(cuda, x, w, idx, split, False)
+    bias = (torch.randn(N, device=cuda) * 0.5).to(torch.bfloat16)
+    try:
+        mmx_lib.mmx_set_option(b"gemm_splitk", 1)
+        c1, c1b = _mm(a, b), _mm(a, b, bias=bias)
+        mmx_lib.mmx_set_option(b"gemm_splitk", sk)
+        c, cb, c_again = _mm(a, b), _mm(a, b, bias=bias), _mm(a, b)
+        torch.cuda.synchronize()
+    finally:
+        mmx_lib.mmx_set_option(b"gemm_splitk", 0)
+    mx, mean = H.rel_err(H.bits(c), _oracle(a, b))
+    assert mx <= TOL_MAX and mean <= TOL_MEAN, (mx, mean)
+    assert torch.equal(c, c_again)
+    mx1, _ = H.rel_err(H.bits(c), H.bits(c1))
+    mxb, _ = H.rel_err(H.bits(cb), H.bits(c1b))
+    assert mx1 <= TOL_MAX and mxb <= TOL_MAX, (mx1, mxb)

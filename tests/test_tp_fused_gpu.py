@@ -109,3 +109,23 @@ def test_fused_allreduce_alternating_shapes(cuda, mmx_lib):
     finally:
         mmx_lib.mmx_set_option(b"tp_reduce_ctas", 0)
         mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)
+
+
+@pytest.mark.parametrize("mode", ["push", "switch"])
+def test_fused_allreduce_multiprocess(cuda, mode):
+    """Real ranks, real NVLink: tools/tp_fused_check.py under torchrun on two GPUs of this box (skipped on a one-GPU box).
+    push: bit-exact against the rank-ordered fp32 sum.  switch: the NVSwitch sums (multimem.ld_reduce) -- identical bits on
+    every rank, within one bf16 rounding step of the rank-ordered sum (the tool exits non-zero otherwise)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MMX_TP_MODE=mode)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29650 + (mode == "switch")), os.path.join(root, "tools", "tp_fused_check.py"),
+           "--tokens", "1000", "--iters", "3", "--shapes", "512x1024,1280x4096"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert f'"mode": "{mode}"' in r.stdout and '"bit_exact_all_ranks": true' in r.stdout

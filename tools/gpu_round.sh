@@ -10,6 +10,7 @@ if [ "${2:-tests}" = "tests" ]; then
 fi
 timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref.json 2>> $OUT/bench.err
+timeout 200 python tools/m_sweep.py > $OUT/m_sweep.log 2>&1   # BASELINE config 2: M = 1 .. 8192 per linear
 # launch list of the bench command itself (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
