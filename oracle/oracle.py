@@ -254,3 +254,35 @@ def fake_quant_linear(x_bits, w_bits, idx, KN, KS, KO, chain=True):
     a = reorder_quantize(x_bits, idx, KN, KS, KO, "x")
     b = reorder_quantize(w_bits, idx, KN, KS, KO, "w4")
     return matmul(a[0], b[0], a[1], b[1], a[2], b[2], a[3], b[3], a[4], b[4], a[5], b[5], chain=chain)
+
+
+# ---------------------------------------------------------------------------------------------------- calibration
+def calibrate_reference(calls, lamda=1.0):
+    """/root/reference/reorder_indices.py:40-113 restated literally for ONE linear input: `calls` is the list of
+    activation tensors its forward hook saw.  Keeps and concatenates every |x| row, exactly as the reference does.
+    Returns (reorder_index, p8_num, p6_num, p4_num) -- p4_num unguarded, as in the reference."""
+    import math
+    import torch
+    act_scale, total = None, []
+    for tensor in calls:
+        hidden_dim = tensor.shape[-1]
+        tensor = tensor.view(-1, hidden_dim).float().detach().cpu().abs()      # :42
+        comming_scales = torch.mean(tensor, dim=0).float()                      # :43
+        if act_scale is not None:
+            total.append(tensor)
+            act_scale = torch.max(act_scale, comming_scales)                    # :45-46
+        else:
+            total = [tensor]
+            act_scale = comming_scales
+    _, sorted_index = torch.sort(act_scale, descending=False)                   # :66
+    value = torch.cat(total, dim=0)                                             # :100
+    _, in_features = value.shape
+    p4_threshold = value.max(dim=-1, keepdim=True)[0] * 448 / 6 / math.pow(2, 10) * lamda    # :103
+    p6_threshold = value.max(dim=-1, keepdim=True)[0] * 448 / 28 / math.pow(2, 6) * lamda    # :104
+    p4_ratio = (value < p4_threshold).sum() / value.numel()                     # :106
+    p6_ratio = (value < p6_threshold).sum() / value.numel() - p4_ratio          # :107
+    p8_ratio = 1 - p4_ratio - p6_ratio                                          # :108
+    p6_num = math.ceil(in_features * p6_ratio / 128) * 128                      # :109
+    p8_num = math.ceil(in_features * p8_ratio / 128) * 128                      # :110
+    p4_num = in_features - p8_num - p6_num                                      # :111
+    return sorted_index, p8_num, p6_num, p4_num
