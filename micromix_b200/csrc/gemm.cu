@@ -1124,18 +1124,22 @@ static int launch_gemm_splitk(const TmapSet& tm, GemmParams& p, cudaStream_t st,
 }
 
 // Largest split (8, 4, 2) whose clusters -- one per tile -- are all resident in ONE wave and get at least two stages each.
-static int choose_splitk(const TmapSet& tm, GemmParams& p, int64_t tiles, int total_stages) {
+static int choose_splitk(int64_t tiles, int total_stages) {
   const int64_t forced = options().gemm_splitk;
   if (forced == 1) return 1;
   static int cap[9] = {0, 0, -1, 0, -1, 0, 0, 0, -1};  // resident clusters per size, -1 = not probed yet
+  TmapSet tm_none;
+  GemmParams p_none;
+  memset(&p_none, 0, sizeof(p_none));
   for (int sk = 8; sk >= 2; sk >>= 1) {
     if (forced > 1 && forced != sk) continue;
     if (total_stages < 2 * sk && forced != sk) continue;
     if (total_stages < sk) continue;
     if (cap[sk] < 0) {
       int n = 0;
-      const int rc = sk == 8 ? launch_gemm_splitk<8>(tm, p, nullptr, true, &n)
-                             : (sk == 4 ? launch_gemm_splitk<4>(tm, p, nullptr, true, &n) : launch_gemm_splitk<2>(tm, p, nullptr, true, &n));
+      const int rc = sk == 8 ? launch_gemm_splitk<8>(tm_none, p_none, nullptr, true, &n)
+                             : (sk == 4 ? launch_gemm_splitk<4>(tm_none, p_none, nullptr, true, &n)
+                                        : launch_gemm_splitk<2>(tm_none, p_none, nullptr, true, &n));
       cap[sk] = rc == MMX_OK ? n : 0;
     }
     if (tiles <= cap[sk]) return sk;
@@ -1164,7 +1168,17 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     set_error("matmul: this library only runs on sm_100 (B200) devices");
     return MMX_ERR_ARCH;
   }
-  const int cg = (M > 128 && options().gemm_cta_group != 1) ? 2 : 1;  // CTA pairs unless one 128-row tile covers M
+  // Small problems (M <= 512 and fewer 128-row tiles than half the SMs): single-CTA tiles with K split over a cluster,
+  // so that the whole machine streams the operands; everything else: CTA pairs (one 128-row tile: the single-CTA kernel).
+  int sk = 1;
+  if (rsl == nullptr && options().gemm_watchdog == 0 && M <= 512 && options().gemm_cta_group != 2) {
+    const int64_t tiles1 = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int stages = (KN + 255) / 256 + KS / 128 + KO / 128;
+    // measured (profiles/r01_config2_m_sweep.log): above one row of tiles the split only pays for long K (down_proj,
+    // 62 stages: 28.0 -> 16.4 us at M = 256); at K = 4096 the pair kernel is as fast or faster
+    if (tiles1 * 2 <= sm_count() && (M <= BM || stages >= 40 || options().gemm_splitk > 1)) sk = choose_splitk(tiles1, stages);
+  }
+  const int cg = (M > 128 && options().gemm_cta_group != 1 && sk == 1) ? 2 : 1;
   const uint8_t* A[3] = {an, as, ao};
   const uint8_t* B[3] = {bn, bs, bo};
   const uint8_t* SA[3] = {sfan, sfas, sfao};
@@ -1254,18 +1268,13 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   p.flags = (uint32_t)options().gemm_debug_flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const RsParams* rsp = rsl != nullptr ? &rs : nullptr;
-  if (cg == 1 && rsl == nullptr && options().gemm_watchdog == 0) {
-    // decode-sized M: split K over a cluster when the tiles alone cannot occupy the machine
+  if (sk > 1) {
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.n_tiles = (int)((N + BN - 1) / BN);
     p.n_fastest = 1;
-    int total_stages = 0;
-    for (int i = 0; i < ns; ++i) total_stages += p.seg[i].ktiles;
-    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-    const int sk = tiles * 2 <= sm_count() ? choose_splitk(tm, p, tiles, total_stages) : 1;
     if (sk == 8) return launch_gemm_splitk<8>(tm, p, st, false, nullptr);
     if (sk == 4) return launch_gemm_splitk<4>(tm, p, st, false, nullptr);
-    if (sk == 2) return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
+    return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
   }
   const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp) : launch_gemm<1>(tm, p, st, rsp);
   if (rc == MMX_OK && rsl != nullptr) {

@@ -192,9 +192,10 @@ def test_errors(cuda):
 
 @pytest.mark.parametrize("sk", [0, 2, 4, 8])
 @pytest.mark.parametrize("M,N,split", [(1, 4096, (2560, 1024, 512)), (16, 1024, (384, 128, 128)), (128, 512, (640, 256, 128)),
-                                       (77, 384, (2688, 0, 1408)), (5, 256, (0, 1024, 0)), (128, 4096, (8960, 3584, 1792))])
+                                       (77, 384, (2688, 0, 1408)), (5, 256, (0, 1024, 0)), (128, 4096, (8960, 3584, 1792)),
+                                       (300, 512, (640, 256, 128)), (512, 1024, (2560, 1024, 512))])
 def test_splitk_decode_shapes(cuda, mmx_lib, sk, M, N, split):
-    """M <= 128: split-K over a CTA cluster (DSMEM reduction in CTA order).  Against the oracle within the GEMM tolerance,
+    """M <= 512: split-K over a CTA cluster (DSMEM reduction in CTA order).  Against the oracle within the GEMM tolerance,
     against the unsplit kernel within fp32 re-association (a couple of bf16 steps), deterministic run to run, with and
     without bias.  sk = 0 is the automatic choice."""
     K = sum(split)
