@@ -106,6 +106,10 @@ int mmx_rmsnorm_quantize_x(const void* x, const void* w, float eps, int64_t M, i
  */
 int mmx_activate_quantize_x(const void* a, const void* b, int64_t M, int KN, int KS, int KO, uint8_t* xn, uint8_t* xs,
                             uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+/* The same op on column slices of a wider matrix (extension; the reference op takes dense tensors only): row r of a / b
+ * starts at a + r * ld elements, ld >= K, ld % 8 == 0.  Used on the fused gate_up GEMM output [M, 2 * intermediate]. */
+int mmx_activate_quantize_x_strided(const void* a, const void* b, int64_t ld, int64_t M, int KN, int KS, int KO, uint8_t* xn,
+                                    uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
 
 /*
  * mixedgemm.downproj_quantize_w(W, KN, KS, KO)                          bindings.cpp:336-360

@@ -24,6 +24,7 @@ SYMBOLS = {
     "mmx_reorder_quantize_w4": (_i32, _QUANT_ARGS),
     "mmx_rmsnorm_quantize_x": (_i32, [_vp, _vp, ctypes.c_float, _i64, _i32, _vp, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_activate_quantize_x": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_activate_quantize_x_strided": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_downproj_quantize_w": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_downproj_quantize_w4": (_i32, [_vp, _i64, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_matmul": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

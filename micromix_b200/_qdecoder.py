@@ -6,6 +6,11 @@ constructors and forward signatures and changes what the hot path costs:
 
   * q/k/v (and gate/up) read the same activation with the same reorder_index and split, so they are ONE QLinearLayer
     over the row-concatenated weight: one reorder+quantize and one mixed GEMM instead of three (two);
+  * `fused=True` (extension, off by default = the reference's op sequence): the two RMSNorms run inside the quantizer
+    (`rmsnorm_quantize_x`: no normalised [M, hidden] round trip through HBM) and SiLU(gate) * up runs inside the quantizer of
+    down_proj (`activate_quantize_x` on the two halves of the gate_up GEMM output, read in place); for that the rows of
+    gate_proj / up_proj are stored in down_proj's channel order at construction, so the intermediate activation is born
+    permuted (the reference's abandoned `out_reorder_index` idea, qLinearLayer.py:27, qLlamaLayer.py:341,354);
   * with a `tp_group`, qkv / gate_up are column-parallel (no collective) and o / down row-parallel with an NCCL all-reduce
     (micromix_b200.parallel_utils); heads are sharded so every rank runs attention on its own heads only.
 """
@@ -18,6 +23,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import mixedgemm
 from .parallel_utils import RowParallelQLinear
 from .qLinearLayer import QLinearLayer
 
@@ -62,8 +68,17 @@ class FusedQLinear(nn.Module):
         self.in_features, self.out_features = weight.shape[1], weight.shape[0]
 
     @torch.no_grad()
-    def forward(self, x):
-        y = self.inner(x)
+    def forward(self, x, norm=None):
+        """norm = (weight bf16 [K], eps): x is the UN-normalised input and RMSNorm runs inside the quantizer."""
+        if norm is None:
+            y = self.inner(x)
+        else:
+            lin = self.inner
+            bsz, q_len, _ = x.shape
+            a = mixedgemm.rmsnorm_quantize_x(x.reshape(bsz * q_len, -1).contiguous(), norm[0], norm[1], lin.reorder_index,
+                                             lin.p4_num, lin.p6_num, lin.p8_num)
+            y = mixedgemm.matmul(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS, a[5], lin.SFBO,
+                                 bias=lin.bias).reshape(bsz, q_len, -1)
         return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
 
 
@@ -80,11 +95,24 @@ def build_input_group(linears, keys, p8_nums, p6_nums, reorder_index, row_slices
                           for i, (l, k) in enumerate(zip(linears, keys))])
 
 
-def run_input_group(group, x):
+def run_input_group(group, x, norm=None):
     outs = []
     for m in group:
-        outs.extend(m(x))
+        outs.extend(m(x, norm))
     return outs
+
+
+def fusable_rmsnorm(norm):
+    """(weight, eps) if `norm` is a plain RMSNorm (HF Llama / Qwen2 / Mixtral RMSNorm or model_shapes.RMSNorm), else None."""
+    w = getattr(norm, "weight", None)
+    if w is None or getattr(norm, "bias", None) is not None or "RMSNorm" not in type(norm).__name__:
+        return None
+    if w.dtype != torch.bfloat16 or not w.is_cuda:
+        return None
+    eps = getattr(norm, "variance_epsilon", None)
+    if eps is None:
+        eps = getattr(norm, "eps", None)
+    return None if eps is None else (w.detach().contiguous(), float(eps))
 
 
 def tp_info(group):
@@ -154,7 +182,7 @@ class QAttention(nn.Module):
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         past_key_value = kwargs.get("past_key_values", past_key_value)
         bsz, q_len, _ = hidden_states.size()
-        q, k, v = run_input_group(self.qkv_proj, hidden_states)
+        q, k, v = run_input_group(self.qkv_proj, hidden_states, kwargs.pop("mmx_norm", None))
         q = q.view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         v = v.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
@@ -184,12 +212,32 @@ class QGatedMLP(nn.Module):
 
     def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
                                                                                                'down_proj'),
-                 key_fmt=None):
+                 key_fmt=None, fused_act=False):
         super().__init__()
         self.tp, self.rank = tp_info(tp_group)
         gate, up, down = (getattr(originalMLP, n) for n in names)
         key = key_fmt or (lambda n: NAME.format(i, 'mlp', n, 'input'))
         inter = gate.out_features
+        self.act_fn = getattr(originalMLP, "act_fn", F.silu)
+        is_silu = self.act_fn is F.silu or isinstance(self.act_fn, nn.SiLU) or type(self.act_fn).__name__ in ("SiLU", "SiLUActivation")
+        self.fused_act = bool(fused_act) and self.tp == 1 and is_silu
+        if self.fused_act:
+            # gate / up rows in down_proj's channel order: the intermediate activation is born permuted and
+            # SiLU(gate) * up is quantized in place by activate_quantize_x; down_proj's columns follow the same order
+            kd = key(names[2])
+            perm = reorder_index[kd].to(torch.int64)
+            pw = lambda l: _meta_linear(l.weight.data[perm.to(l.weight.device)],
+                                        None if l.bias is None else l.bias.data[perm.to(l.bias.device)])
+            self.gate_up_proj = build_input_group([pw(gate), pw(up)], [key(names[0]), key(names[1])], p8_nums, p6_nums,
+                                                  reorder_index, None)
+            self.d_p8, self.d_p6 = int(p8_nums[kd]), int(p6_nums[kd])
+            self.d_p4 = inter - self.d_p8 - self.d_p6
+            wd = down.weight.data.to(device='cuda', dtype=torch.bfloat16)[:, perm.cuda()].contiguous()
+            self.dW = mixedgemm.downproj_quantize_w4(wd, self.d_p4, self.d_p6, self.d_p8)
+            del wd
+            self.d_bias = None if down.bias is None else down.bias.detach().to(device='cuda', dtype=torch.bfloat16).contiguous()
+            self.down_proj = None
+            return
         slices = None
         if self.tp > 1:
             per = inter // self.tp
@@ -201,20 +249,27 @@ class QGatedMLP(nn.Module):
             self.down_proj = RowParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group)
         else:
             self.down_proj = QLinearLayer(down, p8_nums[kd], p6_nums[kd], reorder_index[kd])
-        self.act_fn = getattr(originalMLP, "act_fn", F.silu)
 
     @torch.no_grad()
-    def forward(self, x):
-        g, u = run_input_group(self.gate_up_proj, x)
-        return self.down_proj(self.act_fn(g) * u)
+    def forward(self, x, norm=None):
+        g, u = run_input_group(self.gate_up_proj, x, norm)
+        if not self.fused_act:
+            return self.down_proj(self.act_fn(g) * u)
+        bsz, q_len, inter = g.shape
+        a = mixedgemm.activate_quantize_x(g.reshape(bsz * q_len, inter), u.reshape(bsz * q_len, inter), self.d_p4, self.d_p6,
+                                          self.d_p8)
+        W = self.dW
+        y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias)
+        return y.reshape(bsz, q_len, -1)
 
 
 class QDecoderLayer(nn.Module):
     """norm -> attention -> residual -> norm -> MLP -> residual, the reference's forward contract
     (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
 
-    def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None):
+    def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False):
         super().__init__()
+        self.fused = bool(fused)
         self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
         self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
                                     tp_group)
@@ -223,21 +278,28 @@ class QDecoderLayer(nn.Module):
         self.post_attention_layernorm = originalLayer.post_attention_layernorm
 
     def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
-        return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
+        return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused_act=self.fused)
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         residual = hidden_states
-        hidden_states = self.input_layernorm(hidden_states)
+        norm1 = fusable_rmsnorm(self.input_layernorm) if self.fused else None
+        if norm1 is None:
+            hidden_states = self.input_layernorm(hidden_states)
+        else:
+            kwargs["mmx_norm"] = norm1  # RMSNorm runs inside the qkv quantizer
         hidden_states, attn_weights, present = self.self_attn(
             hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
             past_key_value=past_key_value, output_attentions=output_attentions, use_cache=use_cache,
             cache_position=cache_position, position_embeddings=position_embeddings, **kwargs)
         hidden_states = residual + hidden_states
         residual = hidden_states
-        hidden_states = self.post_attention_layernorm(hidden_states)
-        hidden_states = self.mlp(hidden_states)
+        norm2 = fusable_rmsnorm(self.post_attention_layernorm) if (self.fused and isinstance(self.mlp, QGatedMLP)) else None
+        if norm2 is None:
+            hidden_states = self.mlp(self.post_attention_layernorm(hidden_states))
+        else:
+            hidden_states = self.mlp(hidden_states, norm2)
         if isinstance(hidden_states, tuple):  # MoE blocks return (hidden_states, router_logits)
             hidden_states = hidden_states[0]
         hidden_states = residual + hidden_states

@@ -210,7 +210,26 @@ def _rowwise(fn_name, tensors, names, KN, KS, KO, widths):
 
 def activate_quantize_x(A, B, KN, KS, KO):
     """SiLU(A) * B -> MX quantize without a permutation (bindings.cpp:307-334): A = gate, B = up, both bf16 [M, K]
-    already in down_proj's channel order -> (XN, XS, XO, SFXN, SFXS, SFXO)."""
+    already in down_proj's channel order -> (XN, XS, XO, SFXN, SFXS, SFXO).
+    Extension: A and B may be column slices of one wider row-major matrix (same row stride, unit column stride), e.g. the
+    two halves of a fused gate_up GEMM output; they are then read in place."""
+    if (A.dim() == 2 and B.dim() == 2 and not (A.is_contiguous() and B.is_contiguous()) and A.shape == B.shape
+            and A.stride(1) == 1 and B.stride(1) == 1 and A.stride(0) == B.stride(0) and A.stride(0) % 8 == 0
+            and A.is_cuda and B.is_cuda and A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+            and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0):
+        lib = _lib.load()
+        rows, K = A.shape
+        KN, KS, KO = _check_split(K, KN, KS, KO)
+        opts = dict(dtype=torch.uint8, device=A.device)
+        with torch.cuda.device(A.device):
+            q = [torch.empty((rows, w), **opts) for w in (KN // 2, KS // 4 * 3, KO)]
+            sf = [torch.empty((int(lib.mmx_sf_bytes_act(rows, k)),), **opts) for k in (KN, KS, KO)]
+            rc = 0
+            if rows > 0:
+                rc = lib.mmx_activate_quantize_x_strided(A.data_ptr(), B.data_ptr(), A.stride(0), rows, KN, KS, KO, _ptr(q[0]),
+                                                         _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
+        _lib.check(rc, "mmx_activate_quantize_x_strided")
+        return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
     return _rowwise("mmx_activate_quantize_x", (A, B), ("A", "B"), KN, KS, KO,
                     lambda kn, ks, ko: (kn // 2, ks // 4 * 3, ko))
 

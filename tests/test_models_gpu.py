@@ -110,3 +110,38 @@ def test_unshared_calibration_falls_back_to_separate_linears(cuda):
     cos, sin = S.rope_tables(TINY, 1, 40, cuda)
     ref = _unfused_layer(layer, TINY, idx, p6, p8, 0, x, cos, sin)
     assert torch.equal(q(x, position_embeddings=(cos, sin))[0], ref)
+
+
+@pytest.mark.parametrize("cls_path,bias", [('micromix_b200.qLlamaLayer.QLlamaDecoderLayer', False),
+                                           ('micromix_b200.qQwenLayer.QQwen2DecoderLayer', True)])
+def test_fused_norm_and_activation_mode(cuda, cls_path, bias):
+    """fused=True: RMSNorm inside the quantizer (rmsnorm_quantize_x) and SiLU(gate) * up inside down_proj's quantizer
+    (activate_quantize_x on the halves of the gate_up output, gate / up rows stored in down_proj's channel order).
+    Same function as the unfused layer up to where the roundings sit (norm rounded once instead of twice, fp32 product):
+    compared against a float64 reference of the layer built from the DEQUANTISED op sequence is overkill here -- the two
+    modes must agree within a few bf16 steps of the layer output's scale."""
+    import importlib
+    from micromix_b200 import mixedgemm
+    from micromix_b200 import model_shapes as S
+    cfg = dict(TINY, qkv_bias=bias)
+    layer = S.make_layer(cfg, cuda, seed=3)
+    idx, p6, p8 = S.make_calibration(cfg, 1, seed=5)
+    mod, name = cls_path.rsplit('.', 1)
+    cls = getattr(importlib.import_module(mod), name)
+    plain = cls(layer, False, p8, p6, idx, 1)
+    fused = cls(layer, False, p8, p6, idx, 1, fused=True)
+    assert fused.mlp.fused_act and fused.mlp.down_proj is None
+    g = torch.Generator(device=cuda).manual_seed(11)
+    x = torch.randn(2, 96, cfg['hidden_size'], generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
+    cos, sin = S.rope_tables(cfg, 2, 96, cuda)
+    n0 = mixedgemm.launch_count()
+    a = plain(x, position_embeddings=(cos, sin))[0]
+    n1 = mixedgemm.launch_count()
+    b = fused(x, position_embeddings=(cos, sin))[0]
+    n2 = mixedgemm.launch_count()
+    torch.cuda.synchronize()
+    assert n1 - n0 == 8 and n2 - n1 == 8  # four quantize + four GEMM launches either way; the elementwise kernels are gone
+    assert torch.isfinite(b.float()).all()
+    d = (a.float() - b.float()).abs()
+    scale = a.float().pow(2).mean().sqrt()
+    assert float(d.max()) <= 0.05 * float(scale) and float(d.mean()) <= 0.005 * float(scale), (float(d.max()), float(d.mean()), float(scale))

@@ -75,7 +75,7 @@ def prefill(args, rank, world, dev):
     for i in range(args.layers):
         layer = S.make_layer(cfg, dev, seed=i)
         idx, p6, p8 = S.make_calibration(cfg, i)
-        layers.append(QLlamaDecoderLayer(layer, False, p8, p6, idx, i, tp_group=group))
+        layers.append(QLlamaDecoderLayer(layer, False, p8, p6, idx, i, tp_group=group, fused=args.fused))
         del layer
     torch.cuda.empty_cache()
     b, s = args.batch, args.seq
@@ -99,6 +99,7 @@ def prefill(args, rank, world, dev):
                       f"batch {b} x seq {s}", "layers_run": args.layers, "ms_per_prefill": ms * scale,
             "tokens_per_s": tokens / (ms * scale) * 1e3, "linear_tflops": layer_flops(cfg, tokens) * args.layers / ms / 1e9,
             "n_gpus": world, "parallelism": f"tp{world}" if world > 1 else "single", "mmx_launches_per_forward": launches,
+            "fused_norm_act": bool(args.fused),
             "note": "decoder layers only (no embedding / lm_head, as in the reference's layer-wise eval); attention = SDPA"}
 
 
@@ -149,6 +150,7 @@ def main():
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--tokens", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--fused", action="store_true", help="prefill: RMSNorm and SiLU*up run inside the quantizers (QDecoderLayer(fused=True))")
     args = ap.parse_args()
     rank, world, dev = setup()
     try:
