@@ -23,9 +23,10 @@ _KEY = 'layers.{}.{}.{}.{}.{}.{}'  # qMixtralLayer.py:467
 class QMixtralBlockSparseTop2MLP(QGatedMLP):
     """One expert: w2(act(w1 x) * w3 x) (qMixtralLayer.py:454-519)."""
 
-    def __init__(self, originalBlock, p8_nums, p6_nums, reorder_index, layer_idx, moe_idx):
+    def __init__(self, originalBlock, p8_nums, p6_nums, reorder_index, layer_idx, moe_idx, fused=False):
         super().__init__(originalBlock, p8_nums, p6_nums, reorder_index, layer_idx, None, names=('w1', 'w3', 'w2'),
-                         key_fmt=lambda n: _KEY.format(layer_idx, 'block_sparse_moe', 'experts', moe_idx, n, 'input'))
+                         key_fmt=lambda n: _KEY.format(layer_idx, 'block_sparse_moe', 'experts', moe_idx, n, 'input'),
+                         fused_act=fused)
 
     @torch.no_grad()
     def forward(self, x):  # x: [tokens, hidden]
@@ -33,7 +34,7 @@ class QMixtralBlockSparseTop2MLP(QGatedMLP):
 
 
 class QMixtralSparseMoeBlock(nn.Module):
-    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None):
+    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False):
         super().__init__()
         self.num_experts = getattr(originalSparseMoeBlock, "num_experts", len(originalSparseMoeBlock.experts))
         self.top_k = originalSparseMoeBlock.top_k
@@ -44,7 +45,7 @@ class QMixtralSparseMoeBlock(nn.Module):
         for j in range(self.num_experts):
             if j % self.ep == self.rank:
                 self.experts[str(j)] = QMixtralBlockSparseTop2MLP(originalSparseMoeBlock.experts[j], p8_nums, p6_nums,
-                                                                  reorder_index, i, j)
+                                                                  reorder_index, i, j, fused=fused)
 
     @torch.no_grad()
     def forward(self, hidden_states):
@@ -55,11 +56,23 @@ class QMixtralSparseMoeBlock(nn.Module):
         w, sel = torch.topk(w, self.top_k, dim=-1)
         w = (w / w.sum(dim=-1, keepdim=True)).to(x.dtype)
         out = torch.zeros_like(x)
-        for name, expert in self.experts.items():
-            tok, slot = torch.where(sel == int(name))
-            if tok.numel() == 0:
+        # group the (token, slot) pairs by expert ONCE: a stable sort keeps tokens ascending inside an expert (the order
+        # torch.where gives the reference's loop, qMixtralLayer.py:437-450) and one host read of the counts replaces a
+        # device->host synchronisation per expert
+        flat = sel.reshape(-1)
+        order = torch.argsort(flat, stable=True)
+        counts = torch.bincount(flat, minlength=self.num_experts).tolist()
+        tok_sorted = torch.div(order, self.top_k, rounding_mode="floor")
+        w_sorted = w.reshape(-1)[order]
+        off = 0
+        for j in range(self.num_experts):
+            n, lo = counts[j], off
+            off += n
+            expert = self.experts[str(j)] if str(j) in self.experts else None
+            if expert is None or n == 0:
                 continue
-            y = expert(x.index_select(0, tok)) * w[tok, slot, None]
+            tok = tok_sorted[lo:lo + n]
+            y = expert(x.index_select(0, tok)) * w_sorted[lo:lo + n, None]
             out.index_add_(0, tok, y.to(x.dtype))
         if self.ep > 1:
             dist.all_reduce(out, group=self.ep_group)
@@ -68,14 +81,14 @@ class QMixtralSparseMoeBlock(nn.Module):
 
 class QMixtralDecoderLayer(QDecoderLayer):
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None,
-                 ep_group=None):
+                 ep_group=None, fused=False):
         self._ep_group = ep_group
-        super().__init__(originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
+        super().__init__(originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused)
         self.block_sparse_moe = self.mlp
 
     def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
         moe = getattr(originalLayer, "block_sparse_moe", None) or originalLayer.mlp
-        return QMixtralSparseMoeBlock(moe, p8_nums, p6_nums, reorder_index, layer_idx, self._ep_group)
+        return QMixtralSparseMoeBlock(moe, p8_nums, p6_nums, reorder_index, layer_idx, self._ep_group, fused=self.fused)
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,

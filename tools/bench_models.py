@@ -129,7 +129,7 @@ def mixtral_ep(args, rank, world, dev):
     group = dist.group.WORLD if world > 1 else None
     layer = S.make_layer(cfg, dev, seed=0, moe=True)
     idx, p6, p8 = S.make_calibration(cfg, 0, moe=True)
-    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, ep_group=group)
+    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, ep_group=group, fused=args.fused)
     del layer
     torch.cuda.empty_cache()
     tokens = args.tokens
@@ -139,7 +139,7 @@ def mixtral_ep(args, rank, world, dev):
     flops = 2.0 * tokens * cfg["num_experts_per_tok"] * 3 * cfg["hidden_size"] * cfg["intermediate_size"]
     return {"config": f"Mixtral-8x7B expert FFN (8 experts, top-2), {tokens} tokens, expert parallel {world}",
             "ms_per_block": ms, "tokens_per_s": tokens / ms * 1e3, "expert_tflops": flops / ms / 1e9, "n_gpus": world,
-            "mmx_launches_per_forward": launches}
+            "mmx_launches_per_forward": launches, "fused_act": bool(args.fused)}
 
 
 def main():
