@@ -30,6 +30,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "mixed-MX GEMM TFLOPS & prefill tokens/s, Llama-3-8B linears, 1/2/4/8 B200"
+_RESULT_FD = None  # the process's original stdout; fd 1 itself is pointed at stderr while the bench runs (see main)
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 # (name, N, K, parallel mode)
 LINEARS = [("qkv", 6144, 4096, "col"), ("o", 4096, 4096, "row"), ("gate_up", 28672, 4096, "col"),
            ("down", 4096, 14336, "row")]
@@ -103,10 +114,10 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank, world):
-    """The reference's algorithm on the host cores (oracle port; `kind`: "port").  Rank 0 only."""
+def run_reference(args, rank, world, emit_line=True):
+    """The reference's algorithm on the host cores (oracle port; `kind`: "port").  Rank 0 only.  Returns the line."""
     if rank != 0:
-        return
+        return None
     import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -152,7 +163,9 @@ def run_reference(args, rank, world):
             "config": workload_config(args, world),
             "cpu_baseline": {"value": tflops, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tflops, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    if emit_line:
+        emit(line)
+    return line
 
 
 def workload_config(args, world):
@@ -442,7 +455,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 def measure_e2e(args, rank, world, dev, chunks, total_flops):
@@ -518,14 +531,9 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
 
 
 def cpu_baseline(args):
-    import io
-    import contextlib
     a = argparse.Namespace(**vars(args))
     a.steps_ref, a.warmup_ref = 2, 1
-    buf = io.StringIO()
-    with contextlib.redirect_stdout(buf):
-        run_reference(a, 0, 1)
-    return json.loads(buf.getvalue().strip().splitlines()[-1])["cpu_baseline"]
+    return run_reference(a, 0, 1, emit_line=False)["cpu_baseline"]
 
 
 def main():
@@ -557,6 +565,12 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         os.execv(sys.executable, cmd)
+    # stdout carries the JSON line and nothing else: native libraries print there too (NCCL's version banner), so fd 1
+    # is pointed at stderr for the duration and the line goes to a private duplicate of the original stdout
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
