@@ -9,9 +9,13 @@ A "step" = one pass of the hot path over that batch: for each linear, mmx_reorde
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--tokens M] [--impl ours|reference]
 
-N > 1 (launched by torchrun, one rank per GPU over NCCL): tensor parallel as in BASELINE north_star --
-qkv/gate_up column-parallel (no collective), o/down row-parallel with an all-reduce of the bf16 [M,4096] partials.
-Total work is fixed as N grows ("scaling": "strong"); value = whole-job TFLOP/s = 2*M*sum(N*K) / max-over-ranks time.
+N > 1 (launched by torchrun, one rank per GPU; NCCL is the plumbing): tensor parallel as in BASELINE north_star --
+qkv/gate_up column-parallel (no collective), o/down row-parallel with the bf16 [M,4096] partials summed over the ranks.
+The sum is fused into the GEMM by default (`--tp-reduce fused`: micromix_b200/csrc/tp_reduce.cu, peer pushes at tp=2,
+in-switch multimem reduction at tp>=4); `--tp-reduce nccl` is mmx_matmul + ncclAllReduce, the baseline it is measured
+against.  The step is replayed from a CUDA graph (eager launches from N Python processes would bound a step whose kernels
+are 15-70 us each).  Total work is fixed as N grows ("scaling": "strong"); value = whole-job TFLOP/s =
+2*M*sum(N*K) / max-over-ranks time.  stdout carries exactly one JSON line.
 
 `--impl reference` times the reference's algorithm on the host cores (the CPU oracle port: the reference has no CPU
 implementation of its own and its GEMM cannot run on sm_100) on a bounded token sample.

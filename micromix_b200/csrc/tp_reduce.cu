@@ -4,27 +4,35 @@
 // BASELINE.json's north_star asks for row-parallel o_proj / down_proj whose bf16 partials are summed across the
 // ranks of one NVSwitch box.  The plain way is mmx_matmul followed by ncclAllReduce.  This file is the fused way:
 //
-//   rank r:  mixed_gemm_kernel<.., RS=true>   the epilogue TMA-stores every partial tile straight into the staging
-//                                             buffer of the rank that OWNS the tile (owner = tile % tp; a peer-mapped
-//                                             address, the bytes cross NVLink while the tensor cores run the next
-//                                             tile) and bumps the owner's per-tile counter (red.release.sys);
-//            tile_allreduce_kernel            launched behind the GEMM with programmatic dependent launch, so its
-//                                             CTAs are co-resident with the GEMM's from the start: for each owned
-//                                             tile, wait until tp * (4 * CG) arrivals, sum the tp slots in fp32 in
-//                                             rank order (every rank gets the SAME bits), round to bf16 once and
-//                                             write the result into C on every rank (peer stores).  A final counter
+//   rank r:  mixed_gemm_kernel<.., RS=true>   the epilogue hands every partial tile to the rank that OWNS the tile (owners
+//                                             rotate over consecutive tiles) and bumps the owner's per-tile counter with
+//                                             ONE system-scope release per warp -- one tile late, after the next tile's
+//                                             stores have been issued, so that it never waits an NVLink round trip;
+//            tile_allreduce_kernel            launched behind the GEMM with programmatic dependent launch and resident
+//                                             NEXT TO it (the RS GEMM keeps one pipeline stage less so that a second CTA
+//                                             fits on the SM): for each owned tile, wait until tp * (4 * CG) arrivals,
+//                                             reduce, and write the bf16 result into C on every rank.  A final counter
 //                                             tells each rank that all owners have filled its C.
 //
-// Per rank the NVLink traffic is (tp-1)/tp of C out (partials) + (tp-1)/tp of C out (results) -- the same bytes as a
-// reduce-scatter + all-gather, but the first half hides behind the MMAs and no rank ever waits for a ring step.
+// Two data paths (mmx_tp_ctx_set_multicast picks; the Python host code chooses push for tp = 2, switch for tp >= 4):
+//   push    the epilogue TMA-stores the partial tile into the owner's staging slot (peer-mapped: the bytes cross NVLink
+//           while the tensor cores run the next tile); the reducer sums the tp slots in fp32 IN RANK ORDER (every rank
+//           gets the same bits, equal to bf16(sum_rank fp32(partial))) and stores the tile to the tp ranks.
+//           NVLink egress per rank: (tp-1)/tp of C for the partials + (tp-1)/tp of C for the results.
+//   switch  partial tiles stay in every rank's own C; the reducer issues multimem.ld_reduce on the NVSwitch MULTICAST
+//           address of the tile -- the switch reads the tp copies and returns their fp32-accumulated sum -- and one
+//           multimem.st writes the bf16 result over all tp copies.  Each direction carries C once.  All ranks get the same
+//           bits; the summation order is the switch's.
 //
-// Memory: one peer-mapped workspace per rank (mmx_peer_alloc + cudaIpc handles exchanged by the host code):
+// Memory: one workspace per rank, peer-mapped on every other rank (cudaIpc handles from mmx_peer_alloc, or torch's
+// symmetric-memory allocator, which also provides the multicast mapping):
 //   [flags 256 KB][staging: 2 parities x tp slots x own_tiles_cap tiles of 256x256 bf16][C: 2 parities x M_cap x N_cap]
 // A staging tile is BOX-MAJOR: the 32 x 32 box (band b of 32 rows, column chunk sc) is the 2 KB at ((b * 8 + sc) * 2 KB).
 // Calls alternate the parity, which is all the protection the protocol needs: a rank can run at most one call ahead
-// of its peers (its reducer of call c cannot finish before every peer has pushed call c), so while a slow rank still
+// of its peers (its reducer of call c cannot finish before every peer has delivered call c), so while a slow rank still
 // reads staging[c & 1] a fast rank writes staging[(c+1) & 1].  Counters are reset by their only reader.
 // Every rank must issue the same sequence of calls (same shapes) on one stream -- the usual SPMD contract.
+// Every cross-rank wait is bounded (option tp_timeout_ms): a lost peer costs an error word, not the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -93,11 +101,6 @@ struct ReduceParams {
                             // 4 = no tile waits
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -11,9 +11,11 @@ NCCL all-reduce over NVLink 5 / NVSwitch.
     [r*K/tp, (r+1)*K/tp), a RANK-LOCAL permutation of that slice (the global importance order filtered to the slice)
     and its own (p4,p6,p8), all multiples of 128.  Local quantize + local three-segment GEMM give a partial [M,N];
     partials are summed
-      - fused (`workspace=` a PeerWorkspace): by libmicromix_b200's own GEMM -> all-reduce over NVLink peer memory
-        (csrc/tp_reduce.cu): the GEMM epilogue pushes each partial tile to its owner rank while the next tile's MMAs
-        run, a co-resident reducer kernel sums and broadcasts tiles as they complete;
+      - fused (`workspace=` a PeerWorkspace): by libmicromix_b200's own GEMM -> all-reduce (csrc/tp_reduce.cu), tile by
+        tile while the GEMM is still running: "push" mode (tp = 2) -- the epilogue pushes each partial tile to its owner
+        rank over NVLink peer memory, a co-resident reducer sums in rank order and broadcasts; "switch" mode (tp >= 4) --
+        partial tiles stay local, the owner's reducer sums them inside the NVSwitch (multimem.ld_reduce on a multicast
+        mapping) and multicasts the result;
       - plain: with an NCCL all_reduce (bf16).  `overlap_chunks > 1` splits M so the all-reduce of chunk i overlaps
         the quantize+GEMM of chunk i+1 (NCCL runs on its own stream).
 

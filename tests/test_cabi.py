@@ -101,3 +101,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), f
+
+
+def test_tp_entry_points_validate_without_a_gpu(mmx_lib):
+    """Argument checks of the tensor-parallel entry points that need no device."""
+    import ctypes
+    assert mmx_lib.mmx_tp_workspace_bytes(8192, 4096, 3) > 0 or mmx_lib.mmx_tp_workspace_bytes(8192, 4096, 3) == -1
+    assert mmx_lib.mmx_tp_workspace_bytes(0, 4096, 2) == -1
+    assert mmx_lib.mmx_tp_workspace_bytes(8192, 4096, 9) == -1
+    b2, b8 = mmx_lib.mmx_tp_workspace_bytes(8192, 4096, 2), mmx_lib.mmx_tp_workspace_bytes(8192, 4096, 8)
+    assert b2 > 2 * 8192 * 4096 * 2 and b8 > 2 * 8192 * 4096 * 2  # two parities of C + staging + flags
+    assert mmx_lib.mmx_tp_ctx_set_multicast(None, None, 0) != 0
+    assert b"mmx_tp_ctx_set_multicast" in mmx_lib.mmx_last_error()
+    ctx = ctypes.c_void_p()
+    arr = (ctypes.c_void_p * 2)(None, None)
+    assert mmx_lib.mmx_tp_ctx_create(arr, 2, 0, 8192, 4096, ctypes.byref(ctx)) != 0  # null workspaces
+    assert mmx_lib.mmx_tp_ctx_create(arr, 3, 0, 8192, 4096, ctypes.byref(ctx)) != 0  # tp must be 1, 2, 4 or 8
+    out = (ctypes.c_uint64 * 8)()
+    assert mmx_lib.mmx_tp_debug_times(out, 0) != 0
