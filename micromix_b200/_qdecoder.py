@@ -148,7 +148,7 @@ def apply_rope(q, k, cos, sin):
 class QAttention(nn.Module):
     """Llama / Qwen2 / Mixtral attention with quantized projections (qLlamaLayer.py:196-321, qQwenLayer.py:205-327)."""
 
-    def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None):
+    def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None, workspace=None):
         super().__init__()
         cfg = originalAttn.config
         self.config = cfg
@@ -173,7 +173,8 @@ class QAttention(nn.Module):
                                           p6_nums, reorder_index, slices)
         ko = NAME.format(i, 'self_attn', 'o_proj', 'input')
         if self.tp > 1:
-            self.o_proj = RowParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group)
+            self.o_proj = RowParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group,
+                                             workspace=workspace)
         else:
             self.o_proj = QLinearLayer(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko])
 
@@ -212,7 +213,7 @@ class QGatedMLP(nn.Module):
 
     def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
                                                                                                'down_proj'),
-                 key_fmt=None, fused_act=False):
+                 key_fmt=None, fused_act=False, workspace=None):
         super().__init__()
         self.tp, self.rank = tp_info(tp_group)
         gate, up, down = (getattr(originalMLP, n) for n in names)
@@ -246,7 +247,8 @@ class QGatedMLP(nn.Module):
                                               reorder_index, slices)
         kd = key(names[2])
         if self.tp > 1:
-            self.down_proj = RowParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group)
+            self.down_proj = RowParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group,
+                                                workspace=workspace)
         else:
             self.down_proj = QLinearLayer(down, p8_nums[kd], p6_nums[kd], reorder_index[kd])
 
@@ -267,18 +269,23 @@ class QDecoderLayer(nn.Module):
     """norm -> attention -> residual -> norm -> MLP -> residual, the reference's forward contract
     (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
 
-    def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False):
+    def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
+                 workspace=None):
+        """`workspace` (extension): a parallel_utils.PeerWorkspace shared by the model's row-parallel linears -- o_proj and
+        down_proj then run as GEMMs fused with their all-reduce instead of GEMM + NCCL all-reduce."""
         super().__init__()
         self.fused = bool(fused)
+        self._workspace = workspace
         self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
         self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
-                                    tp_group)
+                                    tp_group, workspace)
         self.mlp = self._build_mlp(originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
         self.input_layernorm = originalLayer.input_layernorm
         self.post_attention_layernorm = originalLayer.post_attention_layernorm
 
     def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
-        return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused_act=self.fused)
+        return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused_act=self.fused,
+                         workspace=self._workspace)
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,

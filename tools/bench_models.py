@@ -109,7 +109,12 @@ def qwen_tp(args, rank, world, dev):
     group = dist.group.WORLD if world > 1 else None
     layer = S.make_layer(cfg, dev, seed=0)
     idx, p6, p8 = S.make_calibration(cfg, 0)
-    q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group)
+    b, s = max(1, args.tokens // 2048), 2048
+    ws = None
+    if world > 1 and args.tp_reduce == "fused":
+        from micromix_b200.parallel_utils import PeerWorkspace
+        ws = PeerWorkspace(b * s, cfg["hidden_size"], group=group, device=dev)
+    q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws)
     del layer
     torch.cuda.empty_cache()
     b, s = max(1, args.tokens // 2048), 2048
@@ -119,7 +124,8 @@ def qwen_tp(args, rank, world, dev):
     ms, launches = timed(lambda: q(x0, position_embeddings=pos), args.iters, 3, world, dev)
     tokens = b * s
     return {"config": f"Qwen2.5-32B-shaped decoder layer, {tokens} tokens, tensor parallel {world} (column qkv/gate_up, "
-                      "row o/down + NCCL all-reduce)", "ms_per_layer": ms, "tokens_per_s_per_layer": tokens / ms * 1e3,
+                      f"row o/down + {'fused GEMM->all-reduce (' + ws.mode + ')' if ws is not None else 'NCCL all-reduce'})",
+            "ms_per_layer": ms, "tokens_per_s_per_layer": tokens / ms * 1e3,
             "linear_tflops": layer_flops(cfg, tokens) / ms / 1e9, "n_gpus": world, "mmx_launches_per_forward": launches}
 
 
@@ -150,6 +156,7 @@ def main():
     ap.add_argument("--seq", type=int, default=2048)
     ap.add_argument("--tokens", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--tp-reduce", default="fused", choices=["fused", "nccl"], help="qwen_tp: row-parallel reduction")
     ap.add_argument("--fused", action="store_true", help="prefill: RMSNorm and SiLU*up run inside the quantizers (QDecoderLayer(fused=True))")
     args = ap.parse_args()
     rank, world, dev = setup()
