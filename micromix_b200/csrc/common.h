@@ -44,6 +44,16 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 
 constexpr int kMaxTp = 8;  // ranks of one NVSwitch box
 
+// Function attributes and __device__ symbol addresses are PER DEVICE: a process that drives several GPUs (the
+// reference's own model/parallel_utils.py places decoder layers on different GPUs of one process) needs them cached per
+// device, not per process.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
+
 // Fused row-parallel GEMM -> all-reduce: what tp_reduce.cu hands to gemm.cu's matmul_impl (see RsParams in gemm.cu).
 struct RsLaunch {
   const void* dst_maps;      // CUtensorMap[tp]: MY slot in rank d's staging buffer as bf16 [own_tiles_cap * 256, 256]

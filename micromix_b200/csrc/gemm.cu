@@ -1064,10 +1064,11 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static bool attr_done[3] = {false, false, false};
+  static bool attr_done[kMaxDevices][3] = {};
+  const int dev = current_device_slot();
   auto prepare = [&](auto kern, int slot) -> cudaError_t {
-    if (attr_done[slot]) return cudaSuccess;
-    attr_done[slot] = true;
+    if (attr_done[dev][slot]) return cudaSuccess;
+    attr_done[dev][slot] = true;
     return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   };
   if (rs != nullptr) {
@@ -1089,10 +1090,11 @@ template <int SK>
 static int launch_gemm_splitk(const TmapSet& tm, GemmParams& p, cudaStream_t st, bool probe_only, int* max_clusters) {
   using G = Geo<1, false>;
   auto kern = mixed_gemm_kernel<1, false, false, SK>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};
+  const int dev = current_device_slot();
+  if (!attr_done[dev]) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   cudaLaunchConfig_t cfg = {};

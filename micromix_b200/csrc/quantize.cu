@@ -618,10 +618,11 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   const bool exact = (int64_t)NLD * T * 8 == p.K && (int64_t)NP * T * 16 == p.K;
   auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM>
                     : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM>;
-  static size_t attr_set[2] = {0, 0};
-  if (smem > attr_set[exact]) {
+  static size_t attr_set[kMaxDevices][2] = {};
+  const int dev = current_device_slot();
+  if (smem > attr_set[dev][exact]) {
     MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[exact] = smem;
+    attr_set[dev][exact] = smem;
   }
   static int occ_cached = 0;
   static size_t occ_smem = 0;
@@ -642,10 +643,10 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   if (options().quant_ctas > 0) grid = options().quant_ctas;
   if (grid > items) grid = items;
   if (grid < 1) return MMX_OK;
-  static unsigned int* sched_base = nullptr;
-  if (!sched_base) MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base), g_quant_sched));
+  static unsigned int* sched_base[kMaxDevices] = {};  // the symbol's address differs from device to device
+  if (!sched_base[dev]) MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base[dev]), g_quant_sched));
   static std::atomic<unsigned int> seq{0};
-  p.sched = sched_base + 2 * (seq.fetch_add(1, std::memory_order_relaxed) & 63u);
+  p.sched = sched_base[dev] + 2 * (seq.fetch_add(1, std::memory_order_relaxed) & 63u);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)T);
