@@ -33,6 +33,18 @@ class QMixtralBlockSparseTop2MLP(QGatedMLP):
         return super().forward(x.unsqueeze(0)).squeeze(0)
 
 
+def group_tokens_by_expert(sel: torch.Tensor, num_experts: int):
+    """sel [tokens, top_k] expert ids -> (order, tok_sorted, counts): `order` lists the flattened (token, slot) pairs
+    grouped by expert with tokens ascending inside an expert (stable sort = the order torch.where(sel == e) gives the
+    reference's per-expert loop, qMixtralLayer.py:437-450), tok_sorted = the token of each pair, counts[e] = pairs of
+    expert e (ONE device->host read for all experts)."""
+    flat = sel.reshape(-1)
+    order = torch.argsort(flat, stable=True)
+    counts = torch.bincount(flat, minlength=num_experts).tolist()
+    tok_sorted = torch.div(order, sel.shape[-1], rounding_mode="floor")
+    return order, tok_sorted, counts
+
+
 class QMixtralSparseMoeBlock(nn.Module):
     def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False):
         super().__init__()
@@ -59,10 +71,7 @@ class QMixtralSparseMoeBlock(nn.Module):
         # group the (token, slot) pairs by expert ONCE: a stable sort keeps tokens ascending inside an expert (the order
         # torch.where gives the reference's loop, qMixtralLayer.py:437-450) and one host read of the counts replaces a
         # device->host synchronisation per expert
-        flat = sel.reshape(-1)
-        order = torch.argsort(flat, stable=True)
-        counts = torch.bincount(flat, minlength=self.num_experts).tolist()
-        tok_sorted = torch.div(order, self.top_k, rounding_mode="floor")
+        order, tok_sorted, counts = group_tokens_by_expert(sel, self.num_experts)
         w_sorted = w.reshape(-1)[order]
         off = 0
         for j in range(self.num_experts):

@@ -56,3 +56,23 @@ def test_signatures_match_reference_sources():
         ours_fwd = _args(ours.forward)
         assert [a for a in ref_fwd if a in ours_fwd] == ref_fwd, (cls, ref_fwd, ours_fwd)
     assert _args(moe.__init__)[:5] == _ref_args(os.path.join(REF, "qMixtralLayer.py"), "QMixtralSparseMoeBlock", "__init__")
+
+
+def test_moe_token_grouping_matches_the_reference_loop():
+    """group_tokens_by_expert == the reference's per-expert torch.where (qMixtralLayer.py:437-450), on CPU."""
+    import torch
+    from micromix_b200.qMixtralLayer import group_tokens_by_expert
+    g = torch.Generator().manual_seed(3)
+    for tokens, E, k in ((1, 8, 2), (37, 8, 2), (500, 4, 2), (64, 8, 1), (9, 3, 3)):
+        scores = torch.rand(tokens, E, generator=g)
+        w, sel = torch.topk(scores, k, dim=-1)
+        order, tok_sorted, counts = group_tokens_by_expert(sel, E)
+        assert sum(counts) == tokens * k and len(counts) == E
+        off = 0
+        for e in range(E):
+            tok, slot = torch.where(sel == e)
+            n = counts[e]
+            assert n == tok.numel()
+            assert torch.equal(tok_sorted[off:off + n], tok)
+            assert torch.equal(w.reshape(-1)[order][off:off + n], w[tok, slot])
+            off += n
