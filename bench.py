@@ -402,7 +402,6 @@ def run_ours(args, rank, world, local_rank):
         per_lin[l.name] = {"M": l.M, "N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
                            "gemm_includes_allreduce": l.ws is not None,
                            "quant_gbs": l.qbytes / gq / 1e6, "gemm_tflops": l.flops / gg / 1e9}
-    rank_flops = C * sum(l.flops for l in lins)
     # the GEMM roofline counts launches that are GEMMs only: in fused mode a row-parallel "GEMM" interval is
     # GEMM + all-reduce (reported per linear, not against the tensor peak)
     pure = [li for li, l in enumerate(lins) if l.ws is None]
