@@ -151,6 +151,8 @@ int mmx_matmul(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const ui
  *
  *   mmx_peer_alloc / _open / _close / _free   one zero-filled device workspace per rank + its 64-byte cudaIpc handle;
  *       the host code exchanges the handles (torch.distributed all_gather_object) and opens the peers' workspaces.
+ *       (Any other allocator that yields peer-mapped pointers works too: the Python host code uses torch's symmetric
+ *       memory when it also wants the multicast mapping, see mmx_tp_ctx_set_multicast.)
  *   mmx_tp_workspace_bytes(M_cap, N_cap, tp)   size of that workspace for outputs up to M_cap x N_cap.
  *   mmx_tp_ctx_create(ws, tp, rank, ...)       ws[d] = rank d's workspace as mapped in THIS process (ws[rank] = own).
  *   mmx_matmul_allreduce(ctx, <mmx_matmul operands of this rank's K shard>, M, N, KN, KS, KO, w4, bias, &c, stream)
@@ -185,8 +187,10 @@ int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
 int64_t mmx_launch_count(void);
 
-/* Debug/bring-up knobs (tests only): key in {"gemm_watchdog","gemm_tx_mode","quant_rows",
- * "gemm_ctas","gemm_cta_group","pdl","tp_reduce_ctas","tp_timeout_ms", ...}. */
+/* Tuning / bring-up knobs: key in {"gemm_ctas" (cap the persistent GEMM grid), "gemm_cta_group", "gemm_splitk" (M <= 512:
+ * 0 auto, 1 never, 2|4|8 force), "pdl", "tp_timeout_ms", "tp_reduce_ctas"} and, for tests / timing experiments only (results
+ * may be wrong): {"gemm_watchdog", "gemm_tx_mode", "gemm_debug_flags", "gemm_raster", "quant_rows", "quant_variant",
+ * "quant_ctas", "tp_debug"}.  Returns non-zero for an unknown key. */
 int mmx_set_option(const char* key, int64_t value);
 
 /* After a GEMM launched with the watchdog on: copies the kernel's status words (0 = clean) to out[0..n).
