@@ -123,12 +123,14 @@ class PeerWorkspace:
             self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
             if self.nbytes <= 0:
                 raise ValueError(f"tensor-parallel degree {self.tp} is not supported by the fused path (1, 2, 4, 8)")
+            explicit = mode != "auto"
             if mode == "auto":
                 mode = "switch" if self.tp >= 4 else "push"
             ptrs = self._map_symmetric(group) if mode in ("switch", "push_mc") else None
             if ptrs is None:
-                if mode == "switch" and os.environ.get("MMX_TP_MODE") == "switch":
-                    raise RuntimeError("MMX_TP_MODE=switch, but this box / torch build offers no multicast memory")
+                if explicit and mode in ("switch", "push_mc"):  # asked for by name: do not silently change the data path
+                    raise RuntimeError(f"PeerWorkspace mode {mode!r} needs NVSwitch multicast memory (torch symmetric "
+                                       "memory with a multicast mapping), which this box / torch build does not offer")
                 mode = "push"
                 with torch.cuda.device(self.device):
                     own = ctypes.c_void_p()

@@ -104,3 +104,15 @@ def test_world_size_2_gloo_row_and_column_parallel():
     e_tp, e_1 = H.rel_err(ret["row"], exact)[1], H.rel_err(full, exact)[1]
     assert e_tp <= 1.5 * e_1 + 1e-3
     assert np.array_equal(ret["col"], full)  # column parallel is exactly the unsharded result
+
+
+def test_peer_workspace_argument_errors_need_no_gpu():
+    """Constructor checks that run before any device work."""
+    import pytest
+    from micromix_b200.parallel_utils import PeerWorkspace
+    with pytest.raises(ValueError, match="mode"):
+        PeerWorkspace(128, 128, mode="bogus")
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        with pytest.raises(RuntimeError, match="process group"):
+            PeerWorkspace(128, 128, mode="push")
