@@ -575,6 +575,10 @@ def main():
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
+        # the host-core arm uses every core it can: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the
+        # OpenMP loops of the C oracle (and MKL) to one thread -- undo that before any OpenMP runtime is loaded
+        for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            os.environ[var] = str(os.cpu_count() or 1)
         run_reference(args, rank, world)
         return
     if world > 1:
