@@ -184,6 +184,77 @@ int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const 
                          const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
                          int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out, void* stream);
 
+/*
+ * Sequence-parallel form of the same tensor parallelism (Megatron "SP"; no reference counterpart either).  The all-reduce
+ * above leaves the whole bf16 [M, N] on every rank, after which every rank repeats the same residual / RMSNorm / quantize.
+ * Here the row-parallel linear ends in a REDUCE-SCATTER and the next column-parallel linear starts with an ALL-GATHER of
+ * PACKED MX CODES:
+ *   mmx_tp_shard_rows(M, tp)            rows per rank: ceil(ceil(M/256)/tp)*256 (whole 256-row GEMM tiles)
+ *   mmx_matmul_reduce_scatter(...)       like mmx_matmul_allreduce, but rank r ends with rows
+ *       [r*shard, min(M,(r+1)*shard)) only: *c_out points at its first row (inside the own workspace), *row0 / *rows
+ *       say which rows.  In switch mode the owner pulls its rows through multimem.ld_reduce and nothing is sent back
+ *       (NVLink ingress per rank: C/tp instead of C); tiles are walked owner-interleaved so that all owners' rows complete
+ *       at an even pace while the GEMM is still running.
+ *   mmx_tp_quantize_allgather(ctx, x_shard, M, K, idx, KN, KS, KO, norm_w, eps, views, stream)
+ *       mmx_reorder_quantize_x (norm_w == NULL) or mmx_rmsnorm_quantize_x on THIS rank's rows of the [M, K] activation
+ *       (x_shard = its first row); every store goes to the NVSwitch multicast address of the context's gather channel,
+ *       so the codes and scales of all M rows land in every rank's workspace: 0.53-0.66 bytes per element on the wire
+ *       instead of 2.  views[0..5] receive the LOCAL addresses of (XN, XS, XO, SFXN, SFXS, SFXO) of the gathered
+ *       activation.  Needs a context created with mmx_tp_ctx_create_ex(..., ag_M, ag_K) and a multicast mapping.
+ *   mmx_tp_matmul_gathered(ctx, <weights>, M, N, KN, KS, KO, w4, bias, c, stream)
+ *       mmx_matmul whose A operand is the gathered activation: the TMA producer waits, m-tile by m-tile, for the arrival
+ *       counter of the rank that quantized those rows; the last CTA tells every rank that the channel may be reused.
+ *       Exactly ONE gathered matmul must follow each gather on every rank.
+ * All counters of this protocol live in device memory and only ever count up: the sequence is CUDA-graph replayable.
+ */
+int64_t mmx_tp_workspace_bytes_ex(int64_t M_cap, int64_t N_cap, int tp, int64_t ag_M, int64_t ag_K);
+int mmx_tp_ctx_create_ex(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, int64_t ag_M, int64_t ag_K,
+                         void** ctx);
+int64_t mmx_tp_shard_rows(int64_t M, int tp);
+int mmx_matmul_reduce_scatter(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                              const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                              const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
+                              int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out, int64_t* row0,
+                              int64_t* rows, void* stream);
+int mmx_tp_quantize_allgather(void* ctx, const void* x_shard, int64_t M, int K, const int16_t* idx, int KN, int KS, int KO,
+                              const void* norm_w, float eps, void** views, void* stream);
+int mmx_tp_matmul_gathered(void* ctx, const uint8_t* bn, const uint8_t* bs, const uint8_t* bo, const uint8_t* sfbn,
+                           const uint8_t* sfbs, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                           const void* bias, void* c, void* stream);
+
+/*
+ * Grouped forms for Mixtral's experts (extension).  The reference runs one Python iteration per expert -- quantize,
+ * matmul, quantize, matmul, index_add_ (model/qMixtralLayer.py:437-450, 502-519).  Here the (token, slot) pairs are sorted
+ * by expert once, each expert's rows padded to whole m-tiles, and ONE quantize launch + ONE GEMM launch serve all experts:
+ *   mmx_reorder_quantize_x_grouped   x bf16 [M, K] (sorted, padded), idx int16 [groups, K] (one permutation per group, the
+ *       same (KN, KS, KO) for all), grp_rowblk int32 [ceil(M/128)] in DEVICE memory = group of each 128-row block
+ *       (padding blocks carry any valid group); row_src int32 [M] (optional, DEVICE memory): sorted row r is row
+ *       row_src[r] of x, i.e. the gather of the routed tokens is fused into the quantizer's loads (padding rows carry any
+ *       valid row).  Outputs as mmx_reorder_quantize_x.
+ *   mmx_matmul_grouped               B tensors = the groups' weights stacked on N ([groups*N, Kseg*bits/8], scales likewise);
+ *       grp_mblk int32 [M / tile_rows] in DEVICE memory = group of each m-tile or -1 (padding tile: skipped);
+ *       tile_rows = 256 (CTA pairs) or 128; C bf16 [M, N].  No host synchronisation anywhere: the tables are written on
+ *       the stream by the router.
+ */
+int mmx_reorder_quantize_x_grouped(const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk,
+                                   const int32_t* row_src, int KN, int KS, int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo,
+                                   uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+/* out[t] = sum over the top_k slots of token t, in ascending expert order, of bf16(y[row[t,s]] * w[t,s]) with a bf16
+ * rounding after every add -- exactly what the reference's per-expert `index_add_` loop leaves in its bf16 buffer
+ * (model/qMixtralLayer.py:446-450).  row int32 [T, top_k] = row of y holding the pair's expert output, or -1 (expert not on
+ * this rank: skipped); expert int32 [T, top_k]; w bf16 [T, top_k]; y bf16 [*, H]; out bf16 [T, H]. */
+int mmx_moe_combine(const void* y, const int32_t* row, const int32_t* expert, const void* w, int64_t T, int top_k, int H,
+                    void* out, void* stream);
+int mmx_matmul_grouped(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                       const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                       const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                       int groups, int tile_rows, const int32_t* grp_mblk, void* c, void* stream);
+
+/* Tensor-pipe peak probe (measurement tool behind bench.py's roofline denominator): every SM issues `stages` x 4
+ * back-to-back block-scaled MMAs (M=128, N=256) on shared-memory-resident operands; kind 0 = kind::mxf4 (K=64),
+ * 1 = kind::mxf8f6f4 E3M2 x E2M1, 2 = kind::mxf8f6f4 E4M3 x E2M1 (K=32).  Best of `reps`; synchronises the device. */
+int mmx_debug_mma_peak(int kind, int stages, int sf_copies, int reps, double* tflops, double* ms);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */
 int64_t mmx_launch_count(void);
 

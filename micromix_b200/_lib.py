@@ -39,6 +39,20 @@ SYMBOLS = {
     "mmx_tp_status": (_i32, [_vp, ctypes.POINTER(ctypes.c_uint32)]),
     "mmx_matmul_allreduce": (_i32, [_vp] + [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp,
                                                        ctypes.POINTER(_vp), _vp]),
+    "mmx_tp_workspace_bytes_ex": (_i64, [_i64, _i64, _i32, _i64, _i64]),
+    "mmx_tp_ctx_create_ex": (_i32, [ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _i64, _i64, ctypes.POINTER(_vp)]),
+    "mmx_tp_shard_rows": (_i64, [_i64, _i32]),
+    "mmx_matmul_reduce_scatter": (_i32, [_vp] + [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp,
+                                                            ctypes.POINTER(_vp), ctypes.POINTER(_i64),
+                                                            ctypes.POINTER(_i64), _vp]),
+    "mmx_tp_quantize_allgather": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, ctypes.c_float,
+                                         ctypes.POINTER(_vp), _vp]),
+    "mmx_tp_matmul_gathered": (_i32, [_vp] + [_vp] * 6 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_reorder_quantize_x_grouped": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_moe_combine": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "mmx_matmul_grouped": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_debug_mma_peak": (_i32, [_i32, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_double)]),
     "mmx_launch_count": (_i64, []),
     "mmx_set_option": (_i32, [ctypes.c_char_p, _i64]),
     "mmx_gemm_debug_status": (_i32, [ctypes.POINTER(ctypes.c_uint32), _i32]),

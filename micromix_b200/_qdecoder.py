@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import mixedgemm
-from .parallel_utils import RowParallelQLinear
+from .parallel_utils import RowParallelQLinear, forward_row_shard
 from .qLinearLayer import QLinearLayer
 
 NAME = 'layers.{}.{}.{}.{}'  # the key template of the reference's calibration dicts (qLlamaLayer.py:211)
@@ -79,6 +79,18 @@ class FusedQLinear(nn.Module):
                                              lin.p4_num, lin.p6_num, lin.p8_num)
             y = mixedgemm.matmul(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS, a[5], lin.SFBO,
                                  bias=lin.bias).reshape(bsz, q_len, -1)
+        return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
+
+    @torch.no_grad()
+    def forward_gathered(self, x_shard, M, workspace, norm=None):
+        """Sequence-parallel form: x_shard = THIS rank's rows of the [M, K] activation.  The rank quantizes only those
+        (RMSNorm fused when `norm` is given), the packed codes are multicast into every rank's gather channel, and the
+        column-parallel GEMM runs on the gathered operand -> [M, N/tp] splits."""
+        lin = self.inner
+        a = workspace.quantize_allgather(x_shard, M, lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num, norm=norm)
+        del a  # (the GEMM reads the channel directly)
+        y = workspace.matmul_gathered(M, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), lin.p4_num, lin.p6_num,
+                                      lin.p8_num, bias=lin.bias)
         return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
 
 
@@ -148,8 +160,11 @@ def apply_rope(q, k, cos, sin):
 class QAttention(nn.Module):
     """Llama / Qwen2 / Mixtral attention with quantized projections (qLlamaLayer.py:196-321, qQwenLayer.py:205-327)."""
 
-    def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None, workspace=None):
+    def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None, workspace=None,
+                 sequence_parallel=False):
         super().__init__()
+        self.sp = bool(sequence_parallel)
+        self.workspace = workspace
         cfg = originalAttn.config
         self.config = cfg
         self.q_kv_cache = kv_cache
@@ -182,8 +197,14 @@ class QAttention(nn.Module):
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         past_key_value = kwargs.get("past_key_values", past_key_value)
-        bsz, q_len, _ = hidden_states.size()
-        q, k, v = run_input_group(self.qkv_proj, hidden_states, kwargs.pop("mmx_norm", None))
+        if self.sp:
+            # hidden_states = this rank's token rows [1, rows, hidden]; the batch shape comes from the rotary tables
+            bsz, q_len = position_embeddings[0].shape[0], position_embeddings[0].shape[1]
+            q, k, v = self.qkv_proj[0].forward_gathered(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(),
+                                                        bsz * q_len, self.workspace, kwargs.pop("mmx_norm", None))
+        else:
+            bsz, q_len, _ = hidden_states.size()
+            q, k, v = run_input_group(self.qkv_proj, hidden_states, kwargs.pop("mmx_norm", None))
         q = q.view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         v = v.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
@@ -205,6 +226,9 @@ class QAttention(nn.Module):
                                              is_causal=mask is None and q_len > 1,
                                              enable_gqa=self.num_key_value_groups > 1)
         out = out.transpose(1, 2).reshape(bsz, q_len, -1)
+        if self.sp:
+            y, _ = forward_row_shard(self.o_proj, out)  # reduce-scatter: this rank's rows only
+            return y.unsqueeze(0), None, past_key_value
         return self.o_proj(out), None, past_key_value
 
 
@@ -213,8 +237,10 @@ class QGatedMLP(nn.Module):
 
     def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
                                                                                                'down_proj'),
-                 key_fmt=None, fused_act=False, workspace=None):
+                 key_fmt=None, fused_act=False, workspace=None, sequence_parallel=False):
         super().__init__()
+        self.sp = bool(sequence_parallel)
+        self.workspace = workspace
         self.tp, self.rank = tp_info(tp_group)
         gate, up, down = (getattr(originalMLP, n) for n in names)
         key = key_fmt or (lambda n: NAME.format(i, 'mlp', n, 'input'))
@@ -253,7 +279,13 @@ class QGatedMLP(nn.Module):
             self.down_proj = QLinearLayer(down, p8_nums[kd], p6_nums[kd], reorder_index[kd])
 
     @torch.no_grad()
-    def forward(self, x, norm=None):
+    def forward(self, x, norm=None, tokens=None):
+        if self.sp:
+            # x = this rank's token rows [1, rows, hidden] of `tokens` in total
+            g, u = self.gate_up_proj[0].forward_gathered(x.reshape(-1, x.shape[-1]).contiguous(), int(tokens), self.workspace,
+                                                         norm)
+            y, _ = forward_row_shard(self.down_proj, (self.act_fn(g) * u).unsqueeze(0))
+            return y.unsqueeze(0)
         g, u = run_input_group(self.gate_up_proj, x, norm)
         if not self.fused_act:
             return self.down_proj(self.act_fn(g) * u)
@@ -270,27 +302,62 @@ class QDecoderLayer(nn.Module):
     (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
 
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
-                 workspace=None):
+                 workspace=None, sequence_parallel=False):
         """`workspace` (extension): a parallel_utils.PeerWorkspace shared by the model's row-parallel linears -- o_proj and
-        down_proj then run as GEMMs fused with their all-reduce instead of GEMM + NCCL all-reduce."""
+        down_proj then run as GEMMs fused with their all-reduce instead of GEMM + NCCL all-reduce.
+        `sequence_parallel` (extension, needs a workspace with a gather channel): the layer takes and returns THIS rank's
+        token rows only ([1, rows, hidden], rows = workspace.shard_range(b*s)): o_proj / down_proj end in a reduce-scatter,
+        residual + RMSNorm + quantize run on the shard, and the packed MX codes (not bf16 activations) are all-gathered
+        into the column-parallel GEMMs through NVSwitch multicast."""
         super().__init__()
         self.fused = bool(fused)
+        self.sp = bool(sequence_parallel)
+        if self.sp and (workspace is None or tp_info(tp_group)[0] < 2 or not workspace.gather[0]):
+            raise ValueError("sequence_parallel needs tp >= 2 and a PeerWorkspace(..., gather=(tokens, hidden))")
         self._workspace = workspace
         self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
         self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
-                                    tp_group, workspace)
+                                    tp_group, workspace, sequence_parallel=self.sp)
+        if self.sp and len(self.self_attn.qkv_proj) != 1:
+            raise ValueError("sequence_parallel needs q/k/v to share one (reorder_index, p6, p8): one gather feeds ONE GEMM")
         self.mlp = self._build_mlp(originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
         self.input_layernorm = originalLayer.input_layernorm
         self.post_attention_layernorm = originalLayer.post_attention_layernorm
 
     def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
         return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused_act=self.fused,
-                         workspace=self._workspace)
+                         workspace=self._workspace, sequence_parallel=self.sp)
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         residual = hidden_states
+        if self.sp:
+            # the RMSNorms always run inside the quantizer of the shard when they can: that IS the sequence-parallel hand-over
+            norm1 = fusable_rmsnorm(self.input_layernorm)
+            if norm1 is None:
+                hidden_states = self.input_layernorm(hidden_states)
+            else:
+                kwargs["mmx_norm"] = norm1
+            hidden_states, attn_weights, present = self.self_attn(
+                hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                past_key_value=past_key_value, output_attentions=output_attentions, use_cache=use_cache,
+                cache_position=cache_position, position_embeddings=position_embeddings, **kwargs)
+            hidden_states = residual + hidden_states
+            residual = hidden_states
+            tokens = position_embeddings[0].shape[0] * position_embeddings[0].shape[1]
+            norm2 = fusable_rmsnorm(self.post_attention_layernorm)
+            if norm2 is None:
+                hidden_states = self.mlp(self.post_attention_layernorm(hidden_states), None, tokens)
+            else:
+                hidden_states = self.mlp(hidden_states, norm2, tokens)
+            hidden_states = residual + hidden_states
+            outputs = (hidden_states,)
+            if output_attentions:
+                outputs += (attn_weights,)
+            if use_cache:
+                outputs += (present,)
+            return outputs
         norm1 = fusable_rmsnorm(self.input_layernorm) if self.fused else None
         if norm1 is None:
             hidden_states = self.input_layernorm(hidden_states)

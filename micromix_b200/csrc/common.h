@@ -65,11 +65,42 @@ struct RsLaunch {
   int rot_s;                 // owner rotation period, see RsParams in gemm.cu
   int pull;                  // 1: in-switch reduction -- the epilogue stores the partial tile into c_local (this rank's own
   void* c_local;             //    C of the call's parity, ordinary [M, N] coordinates) and only the arrival goes to the owner
+  int shard;                 // 1: REDUCE-SCATTER -- owner-interleaved tile order (GemmParams::n_fastest == 2), rank o owns the
+  int m_per;                 //    m-tiles [o * m_per, (o+1) * m_per) (filled in by matmul_impl) and keeps only those rows
+};
+
+// Optional extras of matmul_impl (all null / zero = the plain GEMM).
+struct MatmulExtra {
+  // grouped GEMM: A rows sorted by group and padded per group to whole m-tiles of `grp_tile_rows` (128 | 256) rows, B = the
+  // groups' weights stacked on N (grp_n rows each); grp_mblk[m-tile] = group or -1 (device memory, written on the stream)
+  const int* grp_mblk = nullptr;
+  int grp_n = 0;
+  int grp_count = 0;
+  int grp_tile_rows = 0;
+  // gathered A (sequence-parallel hand-over): see GemmParams::ag_*
+  const uint32_t* ag_arrived = nullptr;
+  uint32_t* ag_taken = nullptr;
+  int ag_rows = 0;
+  uint32_t* ag_ticket = nullptr;
+  uint32_t* ag_consumed[kMaxTp] = {};
+  int ag_tp = 0;
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
                 const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
-                const void* bias, void* c, void* stream, RsLaunch* rsl);
+                const void* bias, void* c, void* stream, RsLaunch* rsl, const MatmulExtra* ex = nullptr);
+// Sequence-parallel hand-over: the quantizer's outputs are multicast addresses; see QuantParams::ag_* in quantize.cu.
+struct QuantGather {
+  const uint32_t* consumed;  // local: bumped once per rank when that rank is done reading the previous gather
+  uint32_t* issued;          // local: gathers this rank has issued so far
+  uint32_t* arrived[kMaxTp]; // rank d's (peer-mapped) count of gathers whose rows from THIS rank have landed there
+  int tp;
+};
+// quantize.cu: the reorder+quantize launcher behind mmx_reorder_quantize_* (fmt = bits per segment; norm_w: fused RMSNorm)
+int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO, const int fmt[3],
+                     uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1, uint8_t* s2, void* stream,
+                     const void* norm_w, float eps, bool norm, const QuantGather* ag, const int* grp_rowblk = nullptr,
+                     const int* row_src = nullptr);
 int encode_store_tmap(void* ptr, int64_t rows, int64_t cols, void* out /* CUtensorMap* */);
 
 int sm_count();       // cached multiprocessor count of the current device

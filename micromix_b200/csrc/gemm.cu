@@ -90,7 +90,26 @@ struct GemmParams {
   GemmSeg seg[3];
   int nseg;
   int m_tiles, n_tiles;  // in units of (CG*128) x 256
-  int n_fastest;         // tile order: 1 = consecutive tiles walk N (all of B stays L2-resident per wave), 0 = walk M
+  int n_fastest;         // tile order: 1 = consecutive tiles walk N (all of B stays L2-resident per wave), 0 = walk M,
+                         // 2 = OWNER-INTERLEAVED (reduce-scatter): tile t belongs to rank t % own_tp, whose j = t / own_tp-th
+                         // tile is (m_blk = o * m_per + j / n_tiles, n_blk = j % n_tiles) -- every rank walks the same order,
+                         // so all owners' tiles complete at an even pace and every owner's rows are contiguous
+  int own_tp, m_per;     // raster 2: ranks and m-tiles per rank (ceil); tiles with m_blk >= m_tiles do not exist
+  int num_tiles;         // loop bound of the tile walk (raster 2: own_tp * m_per * n_tiles, else m_tiles * n_tiles)
+  // GROUPED GEMM (Mixtral experts): A = token rows sorted by group and padded per group to whole m-tiles; the B tensors
+  // hold the groups' weights stacked on N.  grp_mblk[m_blk] = group of that m-tile, or -1 = padding tile (skipped).
+  const int* grp_mblk;
+  int grp_n;             // B rows per group
+  // GATHERED A (sequence-parallel hand-over, tp_reduce.cu): the A rows of source rank s = row / ag_rows are valid once
+  // ag_arrived[s] has reached ag_taken[0] + 1 (the peers' quantizers multicast them and then bump the counter)
+  const uint32_t* ag_arrived;
+  uint32_t* ag_taken;
+  int ag_rows;
+  // ... and once the LAST CTA of this grid is done with A it bumps ag_taken and tells every rank (ag_consumed[d], peer
+  // mapped) that this rank no longer reads the gathered buffers, so that the next gather may overwrite them
+  uint32_t* ag_ticket;
+  uint32_t* ag_consumed[kMaxTp];
+  int ag_tp;
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
@@ -123,6 +142,24 @@ struct NoRsParams {
 };
 
 __device__ uint32_t g_gemm_dbg[64];
+
+// tile index -> (m_blk, n_blk, group); false = the tile does not exist (raster-2 round-up, grouped padding tile)
+__device__ __forceinline__ bool tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk, int& grp) {
+  grp = 0;
+  if (p.n_fastest == 2) {
+    const int o = tile % p.own_tp, j = tile / p.own_tp;
+    m_blk = o * p.m_per + j / p.n_tiles;
+    n_blk = j % p.n_tiles;
+    return m_blk < p.m_tiles;
+  }
+  m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
+  n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+  if (p.grp_mblk != nullptr) {
+    grp = __ldg(p.grp_mblk + m_blk);
+    return grp >= 0;
+  }
+  return true;
+}
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -434,7 +471,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int group = (CG == 2) ? (blockIdx.x >> 1) : (SK > 1 ? (int)(blockIdx.x / SK) : (int)blockIdx.x);
   const int ngroups = (CG == 2) ? (gridDim.x >> 1) : (SK > 1 ? (int)(gridDim.x / SK) : (int)gridDim.x);
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = p.num_tiles;
   // split-K: this CTA's share [sk_lo, sk_hi) of the tile's concatenated stage list (all segments, in order)
   int sk_lo = 0, sk_hi = 0x7fffffff;
   uint32_t krank = 0;
@@ -487,11 +524,40 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       uint32_t phase = 0;
       bool ok = true;
       long long t_wait = 0, t_begin = WD ? clk() : 0;
+      uint32_t ag_target = 0;
+      if (p.ag_arrived != nullptr) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(ag_target) : "l"(p.ag_taken) : "memory");
+        ag_target += 1u;
+      }
+      uint32_t ag_ok_mask = 0;  // gathered A: source ranks whose arrival this CTA has already observed
       for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
-        const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
-        const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+        int m_blk, n_blk, grp;
+        if (!tile_coords(p, tile, m_blk, n_blk, grp)) continue;
         const int a_row = (m_blk * CG + (int)rank) * BM;          // this CTA's A rows
-        const int b_row = n_blk * BN + (int)rank * G::kBRows;      // this CTA's share of the B rows
+        const int b_row = grp * p.grp_n + n_blk * BN + (int)rank * G::kBRows;  // this CTA's share of the B rows
+        const int sfb_blk = (grp * p.grp_n) / 128 + n_blk * 2;
+        if (p.ag_arrived != nullptr) {
+          // the rows of this m-tile were quantized by rank a_row / ag_rows: wait (once per source) until they have landed
+          const int src = a_row / p.ag_rows;
+          if (!((ag_ok_mask >> src) & 1u)) {
+            uint32_t v;
+            unsigned long long t0 = 0;
+            for (uint32_t it = 1;; ++it) {
+              asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + src) : "memory");
+              if ((int32_t)(v - ag_target) >= 0) break;
+              __nanosleep(64);
+              if ((it & 1023u) == 0) {  // bounded: a lost peer costs wrong rows (flagged), never a hung GPU
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 10000000000ull) { atomicOr(&p.dbg[3], 1u << src); break; }
+              }
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA loads below read what the peers wrote
+            ag_ok_mask |= 1u << src;
+          }
+        }
         int seg_off = 0;  // split-K: stages of the segments before this one
         for (int s = 0; s < p.nseg && ok; ++s) {
           const GemmSeg& sg = p.seg[s];
@@ -515,7 +581,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
             tma_load_2d<CG>(sbase + G::kStageA, &tmaps.b[s], bar, kt * sg.kelems, b_row);
             const int ka = kt * sg.atoms_per_tile;
             tma_load_3d<CG>(sbase + G::kStageA + G::kStageB, &tmaps.sfa[s], bar, 0, ka, m_blk * CG + (int)rank);
-            tma_load_3d<CG>(sbase + G::kStageA + G::kStageB + G::kStageSFA, &tmaps.sfb[s], bar, 0, ka, n_blk * 2);
+            tma_load_3d<CG>(sbase + G::kStageA + G::kStageB + G::kStageSFA, &tmaps.sfb[s], bar, 0, ka, sfb_blk);
             if (++stage == kStages) {
               stage = 0;
               phase ^= 1;
@@ -615,6 +681,10 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       };
       using std::integral_constant;
       for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
+        {
+          int m_blk, n_blk, grp;
+          if (!tile_coords(p, tile, m_blk, n_blk, grp)) continue;
+        }
         // the epilogue must have drained the columns this tile's accumulator shares with the previous one
         const long long tt0 = WD ? clk() : 0;
         if (!mbar_wait<WD>(tmem_empty_bar, tphase ^ 1)) {
@@ -696,9 +766,9 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       p.dbg[40] = (uint32_t)t;
       p.dbg[41] = (uint32_t)(t >> 32);
     }
-    for (int tile = group; tile < num_tiles; tile += ngroups, ++tcount) {
-      const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
-      const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+    for (int tile = group; tile < num_tiles; tile += ngroups) {
+      int m_blk, n_blk, grp;
+      if (!tile_coords(p, tile, m_blk, n_blk, grp)) continue;
       const long long te0 = WD ? clk() : 0;
       if (!mbar_wait<WD>(tmem_full_bar, tphase)) {
         if (WD && lane == 0) atomicOr(&p.dbg[2], 0x8u | (uint32_t)(q << 8) | (rank << 24));
@@ -821,6 +891,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         }
       }
       tphase ^= 1;
+      ++tcount;
       if (WD) {
         t_ewait += te1 - te0;
         t_ework += clk() - te1;
@@ -896,6 +967,18 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+  if (p.ag_arrived != nullptr && threadIdx.x == 0) {
+    // every TMA load of this CTA has completed (its full-barriers were consumed); the last CTA releases the gather
+    __threadfence();
+    if (atomicInc(p.ag_ticket, gridDim.x - 1) == gridDim.x - 1) {
+      uint32_t taken;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(taken) : "l"(p.ag_taken) : "memory");
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.ag_taken), "r"(taken + 1u) : "memory");
+      __threadfence_system();
+      for (int d = 0; d < p.ag_tp; ++d)
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.ag_consumed[d]) : "memory");
+    }
   }
 }
 
@@ -981,8 +1064,43 @@ static int get_tmap(const void* ptr, int64_t rows, int kseg, int bits, bool unpa
   return MMX_OK;
 }
 
+// Scale-factor and output maps are cached like the operand maps (an encode costs ~1 us of host time per map and a
+// decode-sized GEMM is only a few us): key = (kind, pointer, three shape words).
+struct AuxKey {
+  int kind;
+  const void* ptr;
+  int64_t a, b, c;
+  bool operator==(const AuxKey& o) const { return kind == o.kind && ptr == o.ptr && a == o.a && b == o.b && c == o.c; }
+};
+struct AuxKeyHash {
+  size_t operator()(const AuxKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr) ^ (size_t)k.kind * 0x9e3779b97f4a7c15ULL;
+    h ^= std::hash<int64_t>()(k.a * 1000003 + k.b * 8191 + k.c) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+static std::unordered_map<AuxKey, CUtensorMap, AuxKeyHash>& aux_cache() {
+  static std::unordered_map<AuxKey, CUtensorMap, AuxKeyHash> c;
+  return c;
+}
+static std::mutex g_aux_mu;
+static bool aux_lookup(const AuxKey& key, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  auto it = aux_cache().find(key);
+  if (it == aux_cache().end()) return false;
+  *out = it->second;
+  return true;
+}
+static void aux_store(const AuxKey& key, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  if (aux_cache().size() > 8192) aux_cache().clear();
+  aux_cache().emplace(key, m);
+}
+
 // scale-factor map: the 512-byte atoms of one SF buffer viewed as u32[rblocks][katoms][128]; box = nrb x atoms x 128
 static int get_sf_tmap(const void* ptr, int64_t rblocks, int katoms, int box_atoms, int box_rblocks, CUtensorMap* out) {
+  const AuxKey key{1, ptr, rblocks, katoms, box_atoms * 16 + box_rblocks};
+  if (aux_lookup(key, out)) return MMX_OK;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -1000,11 +1118,14 @@ static int get_sf_tmap(const void* ptr, int64_t rblocks, int katoms, int box_ato
               (long long)rblocks, katoms);
     return MMX_ERR_CUDA;
   }
+  aux_store(key, *out);
   return MMX_OK;
 }
 
 // output map: bf16 C[M, N] row-major, box = 32 columns x 32 rows, 64B swizzle (matches stage_chunk's layout)
 static int get_c_tmap(void* ptr, int64_t M, int64_t N, CUtensorMap* out) {
+  const AuxKey key{2, ptr, M, N, 0};
+  if (aux_lookup(key, out)) return MMX_OK;
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -1020,6 +1141,7 @@ static int get_c_tmap(void* ptr, int64_t M, int64_t N, CUtensorMap* out) {
     set_error("cuTensorMapEncodeTiled (C) failed (%d) ptr=%p M=%lld N=%lld", (int)r, ptr, (long long)M, (long long)N);
     return MMX_ERR_CUDA;
   }
+  aux_store(key, *out);
   return MMX_OK;
 }
 
@@ -1042,9 +1164,17 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   const int smem_bytes = rs != nullptr ? Geo<CG, true>::kSmemBytes : Geo<CG, false>::kSmemBytes;
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
-  const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
-  // one wave of CTAs should re-use the SMALLER operand panel from L2 and stream the other exactly once
-  p.n_fastest = options().gemm_raster == 1 ? 0 : (options().gemm_raster == 2 ? 1 : (p.n_tiles <= p.m_tiles ? 1 : 0));
+  int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+  if (p.n_fastest == 2) {  // reduce-scatter raster, requested by the caller (own_tp set)
+    p.m_per = (p.m_tiles + p.own_tp - 1) / p.own_tp;
+    tiles = (int64_t)p.own_tp * p.m_per * p.n_tiles;
+  } else if (p.grp_mblk != nullptr) {
+    p.n_fastest = 1;  // a group's B panel stays L2-resident while its m-tiles are walked
+  } else {
+    // one wave of CTAs should re-use the SMALLER operand panel from L2 and stream the other exactly once
+    p.n_fastest = options().gemm_raster == 1 ? 0 : (options().gemm_raster == 2 ? 1 : (p.n_tiles <= p.m_tiles ? 1 : 0));
+  }
+  p.num_tiles = (int)tiles;
   int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / CG : sm_count() / CG;
   if (groups < 1) groups = 1;
   if (groups > tiles) groups = tiles;
@@ -1065,11 +1195,14 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   static bool attr_done[kMaxDevices][3] = {};
+  static std::mutex attr_mu;
   const int dev = current_device_slot();
   auto prepare = [&](auto kern, int slot) -> cudaError_t {
+    std::lock_guard<std::mutex> lk(attr_mu);
     if (attr_done[dev][slot]) return cudaSuccess;
-    attr_done[dev][slot] = true;
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) attr_done[dev][slot] = true;
+    return e;
   };
   if (rs != nullptr) {
     auto kern = mixed_gemm_kernel<CG, false, true>;
@@ -1091,10 +1224,14 @@ static int launch_gemm_splitk(const TmapSet& tm, GemmParams& p, cudaStream_t st,
   using G = Geo<1, false>;
   auto kern = mixed_gemm_kernel<1, false, false, SK>;
   static bool attr_done[kMaxDevices] = {};
+  static std::mutex attr_mu;
   const int dev = current_device_slot();
-  if (!attr_done[dev]) {
-    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
-    attr_done[dev] = true;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    if (!attr_done[dev]) {
+      MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes));
+      attr_done[dev] = true;
+    }
   }
   const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
   cudaLaunchConfig_t cfg = {};
@@ -1129,7 +1266,17 @@ static int launch_gemm_splitk(const TmapSet& tm, GemmParams& p, cudaStream_t st,
 static int choose_splitk(int64_t tiles, int total_stages) {
   const int64_t forced = options().gemm_splitk;
   if (forced == 1) return 1;
-  static int cap[9] = {0, 0, -1, 0, -1, 0, 0, 0, -1};  // resident clusters per size, -1 = not probed yet
+  // resident clusters per size and device, -1 = not probed yet
+  static int caps[kMaxDevices][9];
+  static bool caps_init = false;
+  static std::mutex caps_mu;
+  std::lock_guard<std::mutex> lk(caps_mu);
+  if (!caps_init) {
+    for (auto& c : caps)
+      for (int i = 0; i < 9; ++i) c[i] = (i == 2 || i == 4 || i == 8) ? -1 : 0;
+    caps_init = true;
+  }
+  int* cap = caps[current_device_slot()];
   TmapSet tm_none;
   GemmParams p_none;
   memset(&p_none, 0, sizeof(p_none));
@@ -1152,7 +1299,7 @@ static int choose_splitk(int64_t tiles, int total_stages) {
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
                 const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
-                const void* bias, void* c, void* stream, RsLaunch* rsl) {
+                const void* bias, void* c, void* stream, RsLaunch* rsl, const MatmulExtra* ex) {
   if (M < 0 || N <= 0 || KN < 0 || KS < 0 || KO < 0 || (KN % 128) || (KS % 128) || (KO % 128) || KN + KS + KO == 0) {
     set_error("matmul: bad shape M=%lld N=%lld (KN,KS,KO)=(%d,%d,%d)", (long long)M, (long long)N, KN, KS, KO);
     return MMX_ERR_INVALID;
@@ -1173,14 +1320,24 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   // Small problems (M <= 512 and fewer 128-row tiles than half the SMs): single-CTA tiles with K split over a cluster,
   // so that the whole machine streams the operands; everything else: CTA pairs (one 128-row tile: the single-CTA kernel).
   int sk = 1;
-  if (rsl == nullptr && options().gemm_watchdog == 0 && M <= 512 && options().gemm_cta_group != 2) {
+  const bool grouped = ex != nullptr && ex->grp_mblk != nullptr;
+  const bool gathered = ex != nullptr && ex->ag_arrived != nullptr;
+  if (grouped && (ex->grp_n <= 0 || ex->grp_count <= 0 || ex->grp_n != N || (ex->grp_n % 256) || (ex->grp_tile_rows != 128 && ex->grp_tile_rows != 256) ||
+                  (M % ex->grp_tile_rows))) {
+    set_error("matmul (grouped): rows per group of B must be a multiple of 256, the padded M a multiple of the m-tile");
+    return MMX_ERR_INVALID;
+  }
+  if (rsl == nullptr && !grouped && !gathered && options().gemm_watchdog == 0 && M <= 512 &&
+      options().gemm_cta_group != 2) {
     const int64_t tiles1 = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int stages = (KN + 255) / 256 + KS / 128 + KO / 128;
     // measured (profiles/r01_config2_m_sweep.log): above one row of tiles the split only pays for long K (down_proj,
     // 62 stages: 28.0 -> 16.4 us at M = 256); at K = 4096 the pair kernel is as fast or faster
     if (tiles1 * 2 <= sm_count() && (M <= BM || stages >= 40 || options().gemm_splitk > 1)) sk = choose_splitk(tiles1, stages);
   }
-  const int cg = (M > 128 && options().gemm_cta_group != 1 && sk == 1) ? 2 : 1;
+  int cg = (M > 128 && options().gemm_cta_group != 1 && sk == 1) ? 2 : 1;
+  if (grouped) cg = ex->grp_tile_rows / BM;  // the caller padded the groups to this m-tile
+  if (rsl != nullptr && rsl->shard) cg = 2;  // reduce-scatter ownership is defined on 256-row m-tiles
   const uint8_t* A[3] = {an, as, ao};
   const uint8_t* B[3] = {bn, bs, bo};
   const uint8_t* SA[3] = {sfan, sfas, sfao};
@@ -1223,18 +1380,23 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     g.tx_b = (uint32_t)b_rows * row_tx(bbits[s]);
     int rc = get_tmap(A[s], M, ks[s], abits[s], unpack, BM, &tm.a[ns]);
     if (rc) return rc;
-    rc = get_tmap(B[s], N, ks[s], bbits[s], unpack, b_rows, &tm.b[ns]);
+    const int64_t n_b = grouped ? (int64_t)ex->grp_n * ex->grp_count : N;  // grouped: the groups' weights stacked on N
+    rc = get_tmap(B[s], n_b, ks[s], bbits[s], unpack, b_rows, &tm.b[ns]);
     if (rc) return rc;
     rc = get_sf_tmap(SA[s], (M + 127) / 128, katoms, g.atoms_per_tile, 1, &tm.sfa[ns]);
     if (rc) return rc;
-    rc = get_sf_tmap(SB[s], (N + 127) / 128, katoms, g.atoms_per_tile, 2, &tm.sfb[ns]);
+    rc = get_sf_tmap(SB[s], (n_b + 127) / 128, katoms, g.atoms_per_tile, 2, &tm.sfb[ns]);
     if (rc) return rc;
     ++ns;
   }
   RsParams rs;
   if (rsl != nullptr) {
     // fused row-parallel mode: the epilogue stores into the owners' staging tiles (maps prepared by tp_reduce.cu)
-    const int64_t tiles = ((M + BM * cg - 1) / (BM * cg)) * ((N + BN - 1) / BN);
+    int64_t tiles = ((M + BM * cg - 1) / (BM * cg)) * ((N + BN - 1) / BN);
+    if (rsl->shard && rsl->tp >= 1) {
+      const int64_t mt = (M + BM * cg - 1) / (BM * cg);
+      tiles = (mt + rsl->tp - 1) / rsl->tp * rsl->tp * ((N + BN - 1) / BN);
+    }
     if (rsl->tp < 1 || rsl->tp > kMaxTp || (tiles + rsl->tp - 1) / rsl->tp * (BM * cg) > rsl->own_tiles_cap * 256) {
       set_error("matmul_allreduce: %lld tiles over tp=%d exceed the workspace (%lld tiles per rank)", (long long)tiles,
                 rsl->tp, (long long)rsl->own_tiles_cap);
@@ -1251,6 +1413,11 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     int64_t groups = options().gemm_ctas > 0 ? options().gemm_ctas / cg : sm_count() / cg;
     if (groups < 1) groups = 1;
     rs.rot_s = (int)((groups + rsl->tp - 1) / rsl->tp * rsl->tp);
+    if (rsl->shard) {
+      rs.rot_s = 1 << 30;  // no owner rotation: owner(tile) = tile % tp, the raster itself interleaves the owners
+      p.n_fastest = 2;
+      p.own_tp = rsl->tp;
+    }
     rsl->rot_s = rs.rot_s;
     rs.pull = rsl->pull;
     if (rsl->pull) {
@@ -1264,9 +1431,28 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   p.N = N;
   p.c = static_cast<__nv_bfloat16*>(c);
   p.bias = static_cast<const __nv_bfloat16*>(bias);
-  uint32_t* dbg = nullptr;
-  MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&dbg), g_gemm_dbg));
-  p.dbg = dbg;
+  static uint32_t* dbg_addr[kMaxDevices] = {};  // the symbol's address differs from device to device
+  {
+    const int dev = current_device_slot();
+    uint32_t* dbg = dbg_addr[dev];
+    if (!dbg) {
+      MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&dbg), g_gemm_dbg));
+      dbg_addr[dev] = dbg;
+    }
+    p.dbg = dbg;
+  }
+  if (grouped) {
+    p.grp_mblk = ex->grp_mblk;
+    p.grp_n = ex->grp_n;
+  }
+  if (gathered) {
+    p.ag_arrived = ex->ag_arrived;
+    p.ag_taken = ex->ag_taken;
+    p.ag_rows = ex->ag_rows;
+    p.ag_ticket = ex->ag_ticket;
+    p.ag_tp = ex->ag_tp;
+    for (int d = 0; d < ex->ag_tp && d < kMaxTp; ++d) p.ag_consumed[d] = ex->ag_consumed[d];
+  }
   p.flags = (uint32_t)options().gemm_debug_flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const RsParams* rsp = rsl != nullptr ? &rs : nullptr;
@@ -1274,6 +1460,7 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.n_tiles = (int)((N + BN - 1) / BN);
     p.n_fastest = 1;
+    p.num_tiles = p.m_tiles * p.n_tiles;
     if (sk == 8) return launch_gemm_splitk<8>(tm, p, st, false, nullptr);
     if (sk == 4) return launch_gemm_splitk<4>(tm, p, st, false, nullptr);
     return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
@@ -1284,6 +1471,7 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     rsl->m_tiles = p.m_tiles;
     rsl->n_tiles = p.n_tiles;
     rsl->n_fastest = p.n_fastest;
+    rsl->m_per = p.m_per;
   }
   return rc;
 }
@@ -1301,6 +1489,145 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul(const uint8_t* 
                           int64_t N, int KN, int KS, int KO, int w4, const void* bias, void* c, void* stream) {
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c,
                           stream, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ tensor-pipe peak probe
+// The roofline denominator of mixed_gemm_kernel, MEASURED: one CTA per SM issues back-to-back block-scaled MMAs of the
+// shapes the GEMM uses (M = 128, N = 256; kind::mxf4 K = 64 or kind::mxf8f6f4 K = 32) on operands that never leave
+// shared memory -- no TMA, no epilogue, nothing but the tensor pipe (and the power cap).  kind: 0 = mxf4 (E2M1 x E2M1),
+// 1 = mxf8f6f4 E3M2 x E2M1, 2 = mxf8f6f4 E4M3 x E2M1.  sf_copies: also issue the GEMM's per-stage tcgen05.cp of the scales.
+namespace mmx {
+__global__ void __launch_bounds__(128, 1) mma_peak_kernel(int kind, int stages, int sf_copies, uint32_t idesc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  constexpr int kA = BM * 128, kB = BN * 128, kSF = 3 * 1024;  // one stage of the single-CTA GEMM
+  const uint32_t bar = smem_base + kA + kB + kSF, tmem_slot = bar + 8;
+  const int warp = threadIdx.x >> 5;
+  // operands: pseudo-random bytes without Inf/NaN patterns (E4M3: exponent 1111 + mantissa 111); scales 2^0
+  for (int i = threadIdx.x; i < (kA + kB) / 4; i += blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    reinterpret_cast<uint32_t*>(smem_raw)[i] = h & 0xb7b7b7b7u;
+  }
+  for (int i = threadIdx.x; i < kSF / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + kA + kB)[i] = 0x7f7f7f7fu;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1) tmem_alloc<1>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t a_lo = (smem_base >> 4) & 0x3fffu, b_lo = ((smem_base + kA) >> 4) & 0x3fffu;
+      const uint32_t sf_lo = ((smem_base + kA + kB) >> 4) & 0x3fffu;
+      const uint32_t t_sfa = tmem_base + 256, t_sfb = t_sfa + 8;
+      const int natoms = kind == 0 ? 2 : 1;
+      auto copy_sf = [&]() {
+        for (int a = 0; a < natoms; ++a) {
+          tc_cp_sf<1>(t_sfa + 4 * a, desc_from_lo(sf_lo + 32u * a, kDescHiSF));
+          tc_cp_sf<1>(t_sfb + 8 * a, desc_from_lo(sf_lo + 64u + 32u * a, kDescHiSF));
+          tc_cp_sf<1>(t_sfb + 8 * a + 4, desc_from_lo(sf_lo + 64u + 32u * (natoms + a), kDescHiSF));
+        }
+      };
+      copy_sf();
+      for (int s = 0; s < stages; ++s) {
+        if (sf_copies && s) copy_sf();
+        if (kind == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t sid = (j & 1) ? ((2u << 29) | (2u << 4)) : 0u;
+            mma_mxf4<1>(tmem_base, desc_from_lo(a_lo + 2u * j, kDescHiOp), desc_from_lo(b_lo + 2u * j, kDescHiOp), idesc | sid,
+                        t_sfa + 4 * (j >> 1), t_sfb + 8 * (j >> 1), (s | j) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma_mxf8f6f4<1>(tmem_base, desc_from_lo(a_lo + 2u * j, kDescHiOp), desc_from_lo(b_lo + 2u * j, kDescHiOp),
+                            idesc | ((uint32_t)j << 29) | ((uint32_t)j << 4), t_sfa, t_sfb, (s | j) ? 1u : 0u);
+        }
+      }
+      tc_commit<1>(bar);
+    }
+    __syncwarp();
+    while (!mbar_try_wait(bar, 0)) {
+    }
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+}  // namespace mmx
+
+// Runs the probe on every SM and returns the achieved dense TFLOP/s in *tflops (2 * 128 * 256 * K flops per MMA,
+// 4 MMAs per stage).  Synchronises the device: a measurement tool (bench.py's roofline peak), not part of the hot path.
+extern "C" __attribute__((visibility("default"))) int mmx_debug_mma_peak(int kind, int stages, int sf_copies, int reps,
+                                                                      double* tflops, double* ms_out) {
+  using namespace mmx;
+  if (kind < 0 || kind > 2 || stages <= 0 || reps <= 0 || !tflops) {
+    set_error("mmx_debug_mma_peak: bad arguments");
+    return MMX_ERR_INVALID;
+  }
+  if (!device_is_sm100()) {
+    set_error("mmx_debug_mma_peak: this library only runs on sm_100 (B200) devices");
+    return MMX_ERR_ARCH;
+  }
+  const int smem = 160 * 1024;  // one CTA per SM (each CTA takes the whole TMEM)
+  MMX_CUDA_TRY(cudaFuncSetAttribute(mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t idesc = make_idesc(kind == 0 ? 0 : 1, kind == 0 ? 4 : (kind == 1 ? 6 : 8), 4, BM);
+  cudaEvent_t e0, e1;
+  MMX_CUDA_TRY(cudaEventCreate(&e0));
+  MMX_CUDA_TRY(cudaEventCreate(&e1));
+  const int grid = sm_count();
+  mma_peak_kernel<<<grid, 128, smem>>>(kind, 64, sf_copies, idesc);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0);
+    mma_peak_kernel<<<grid, 128, smem>>>(kind, stages, sf_copies, idesc);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      return cuda_fail(e, "mma_peak_kernel");
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double k_per_mma = kind == 0 ? 64.0 : 32.0;
+  const double flops = 2.0 * BM * BN * k_per_mma * 4.0 * stages * grid;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return MMX_OK;
+}
+
+// Grouped mixed GEMM (Mixtral experts, extension; the reference loops over the experts in Python,
+// model/qMixtralLayer.py:437-450): ONE persistent launch over all groups.
+extern "C" __attribute__((visibility("default"))) int mmx_matmul_grouped(
+    const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
+    const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+    const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, int groups, int tile_rows,
+    const int32_t* grp_mblk, void* c, void* stream) {
+  if (!grp_mblk || groups <= 0) {
+    mmx::set_error("matmul_grouped: null group table or no groups");
+    return MMX_ERR_INVALID;
+  }
+  mmx::MatmulExtra ex;
+  ex.grp_mblk = grp_mblk;
+  ex.grp_n = (int)N;
+  ex.grp_count = groups;
+  ex.grp_tile_rows = tile_rows;
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, nullptr, c, stream,
+                          nullptr, &ex);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_gemm_debug_status(uint32_t* out, int n) {

@@ -21,26 +21,34 @@ Options& options() {
   return o;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+// Per-device facts, cached per device slot (one process may drive several GPUs, common.h) behind one mutex.
+namespace {
+struct DevInfo {
+  int sms = 0;
+  int major = -1;
+};
+DevInfo g_dev[kMaxDevices];
+std::mutex g_dev_mu;
 
-bool device_is_sm100() {
-  static int major = -1;
-  if (major < 0) {
-    int dev = 0;
+const DevInfo& dev_info() {
+  const int slot = current_device_slot();
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevInfo& d = g_dev[slot];
+  if (d.major < 0) {
+    int dev = 0, n = 0, major = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) major = 0;
+    d.sms = n;
+    d.major = major;
   }
-  return major == 10;
+  return d;
 }
+}  // namespace
+
+int sm_count() { return dev_info().sms; }
+
+bool device_is_sm100() { return dev_info().major == 10; }
 
 }  // namespace mmx
 

@@ -26,6 +26,9 @@
 //     so a warp writes 256 / 384 / 512 contiguous bytes per row -- full sectors, no staging pass.
 #include <cuda_bf16.h>
 
+#include <cstring>
+#include <mutex>
+
 #include "common.h"
 
 namespace mmx {
@@ -45,6 +48,20 @@ struct QuantParams {
   uint8_t* sf[3];
   const uint16_t* nw;  // RMSNorm weight (bf16 [K], ORIGINAL channel order); NORM kernels only
   float eps;
+  // MC kernels (sequence-parallel hand-over, tp_reduce.cu): q[] / sf[] are NVSwitch MULTICAST addresses -- every store
+  // lands in the same place of every rank's gather buffer.  The kernel first waits until all ranks are done reading the
+  // previous gather (ag_consumed >= ag_tp * ag_issued) and, after its last store, bumps ag_arrived[] on every rank.
+  const uint32_t* ag_consumed;
+  uint32_t* ag_issued;
+  uint32_t* ag_arrived[kMaxTp];
+  int ag_tp;
+  // GROUPED (Mixtral experts): rows are sorted by group, every 128-row block belongs to one group, and group g permutes
+  // its rows with idx + g * K (same split for all groups).  grp_rowblk[row / 128] = group (device memory, written on the
+  // stream by the router); a CTA rebuilds its scatter table when the group of its next item changes.
+  const int* grp_rowblk;
+  // ... and row r of the sorted matrix is row row_src[r] of x (the token of that (token, slot) pair; padding rows carry
+  // any valid token): the gather of the routed tokens happens in this kernel's loads, not in a staging copy
+  const int* row_src;
 };
 
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
@@ -66,14 +83,31 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
   return v;
 }
+// MC = the destination is a multicast address: multimem.st (one store, replicated to every rank by the switch)
+template <bool MC = false>
 __device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  if constexpr (MC)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(a)),
+                 "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+                 : "memory");
+  else
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+template <bool MC = false>
 __device__ __forceinline__ void stg_v2(void* p, uint32_t a, uint32_t b) {
-  asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+  if constexpr (MC)
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(__uint_as_float(a)),
+                 "f"(__uint_as_float(b))
+                 : "memory");
+  else
+    asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
+template <bool MC = false>
 __device__ __forceinline__ void stg_b32(void* p, uint32_t a) {
-  asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
+  if constexpr (MC)
+    asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
+  else
+    asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(a) : "memory");
 }
 
 // max(|a|, |b|) on both bf16 halves; the sign bits of the result are garbage (xor of the input signs)
@@ -136,18 +170,18 @@ __device__ __forceinline__ uint32_t squeeze4_fp6(uint32_t w) {
 }
 
 // One row of a thread's 16 channels: 16 floats -> packed codes -> global memory (8 | 12 | 16 contiguous bytes).
-template <int FMT>
+template <int FMT, bool MC>
 __device__ __forceinline__ void convert_store_row(const float (&f)[16], uint8_t* dst) {
   if constexpr (FMT == 4) {
-    stg_v2(dst, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
+    stg_v2<MC>(dst, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
   } else if constexpr (FMT == 6) {
     const uint32_t y0 = squeeze4_fp6(cvt4_e3m2(&f[0])), y1 = squeeze4_fp6(cvt4_e3m2(&f[4]));
     const uint32_t y2 = squeeze4_fp6(cvt4_e3m2(&f[8])), y3 = squeeze4_fp6(cvt4_e3m2(&f[12]));
-    stg_b32(dst, __byte_perm(y0, y1, 0x4210));
-    stg_b32(dst + 4, __byte_perm(y1, y2, 0x5421));
-    stg_b32(dst + 8, __byte_perm(y2, y3, 0x6542));
+    stg_b32<MC>(dst, __byte_perm(y0, y1, 0x4210));
+    stg_b32<MC>(dst + 4, __byte_perm(y1, y2, 0x5421));
+    stg_b32<MC>(dst + 8, __byte_perm(y2, y3, 0x6542));
   } else {
-    stg_v4(dst, cvt4_e4m3(&f[0]), cvt4_e4m3(&f[4]), cvt4_e4m3(&f[8]), cvt4_e4m3(&f[12]));
+    stg_v4<MC>(dst, cvt4_e4m3(&f[0]), cvt4_e4m3(&f[4]), cvt4_e4m3(&f[8]), cvt4_e4m3(&f[12]));
   }
 }
 
@@ -155,7 +189,7 @@ __device__ __forceinline__ void convert_store_row(const float (&f)[16], uint8_t*
 //   g[c][k]  : channel c, row pair k (rows 2k | 2k+1 in the low | high half), bf16 bits
 //   mult[k]  : bf16x2 multiplier 2^(127-byte) per row -> x * mult is exact (power of two), so HMUL2.BF16 is bit-safe
 //   dst      : first row's destination; row j lives at dst + j * row_stride; rows >= nstore are not stored
-template <int FMT, int R, bool FULL>
+template <int FMT, int R, bool FULL, bool MC>
 __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], const uint32_t (&mult)[R / 2], uint8_t* dst,
                                               int64_t row_stride, int nstore) {
 #pragma unroll
@@ -172,7 +206,7 @@ __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], co
       float f[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(half ? (h[c] & 0xffff0000u) : (h[c] << 16));
-      if (FULL || 2 * k + half < nstore) convert_store_row<FMT>(f, dst);
+      if (FULL || 2 * k + half < nstore) convert_store_row<FMT, MC>(f, dst);
       dst += row_stride;
     }
   }
@@ -213,7 +247,7 @@ struct UnitPtrs {
 // each aligned 8-channel chunk (exactly the 16 bytes one thread loads), then a perfect binary tree over the chunk
 // index -- five shuffle levels inside a warp, the warp sums through shared memory, seven more levels redone by every
 // warp.  y = bf16((x * w) * rinv) is applied in the compute phase with the weight staged in PERMUTED order.
-template <int R, int NLD, int NP, int TABMODE, bool NORM = false>
+template <int R, int NLD, int NP, int TABMODE, bool NORM = false, bool MC = false>
 struct QuantKernel {
   static constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
   static constexpr int SLOT = 2 * R;        // bytes per slot
@@ -269,6 +303,8 @@ struct QuantKernel {
     for (int j = 0; j < R; ++j) {
       // rows past the end re-read row0; they are zeroed when stored to shared memory
       const uint16_t* bj = (FULL || j < nvalid) ? b0 + j * rs : b0;
+      if (p.row_src != nullptr)  // grouped: the row is gathered through the routing table (uniform branch)
+        bj = xt + (int64_t)__ldg(p.row_src + ((FULL || j < nvalid) ? row0 + 32 * j : row0)) * K;
 #pragma unroll
       for (int i = 0; i < NLD; ++i)
         if (EXACT || i * T + t < K8) pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
@@ -416,7 +452,24 @@ struct QuantKernel {
     }
 
     // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row, 4 bytes apart)
-    if (meta & 128u) {
+    if constexpr (MC) {
+      // multicast stores are 32 bits wide at least: lanes 8q .. 8q+7 hold the four groups of ONE scale atom column
+      // (128 channels, same segment: segments are multiples of 128), the four bytes of a row are contiguous -- lane 8q
+      // collects them from lanes 8q+2, +4, +6 and writes one word per row
+      const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
+      uint8_t* d = up.sfp + sfoff;
+#pragma unroll
+      for (int k = 0; k < RW; ++k) {
+        const uint32_t v1 = __shfl_down_sync(0xffffffffu, sfb[k], 2), v2 = __shfl_down_sync(0xffffffffu, sfb[k], 4);
+        const uint32_t v3 = __shfl_down_sync(0xffffffffu, sfb[k], 6);
+        const uint32_t lo01 = __byte_perm(sfb[k], v1, 0x0040), lo23 = __byte_perm(v2, v3, 0x0040);  // row 2k : bytes 0
+        const uint32_t hi01 = __byte_perm(sfb[k], v1, 0x0062), hi23 = __byte_perm(v2, v3, 0x0062);  // row 2k+1: bytes 2
+        if ((meta & 64u) && (threadIdx.x & 7) == 0) {
+          stg_b32<true>(d + 8 * k, __byte_perm(lo01, lo23, 0x5410));
+          if (FULL || 2 * k + 1 < nvalid) stg_b32<true>(d + 8 * k + 4, __byte_perm(hi01, hi23, 0x5410));
+        }
+      }
+    } else if (meta & 128u) {
       const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
       uint8_t* d = up.sfp + sfoff;
 #pragma unroll
@@ -431,9 +484,9 @@ struct QuantKernel {
     const int64_t rstride = (int64_t)(32u * up.rbytes);
     const int nstore = active ? nvalid : 0;
     if (FULL && !active) {
-    } else if (fmt == 4) convert_store<4, R, FULL>(g, mult, dst, rstride, nstore);
-    else if (fmt == 6) convert_store<6, R, FULL>(g, mult, dst, rstride, nstore);
-    else convert_store<8, R, FULL>(g, mult, dst, rstride, nstore);
+    } else if (fmt == 4) convert_store<4, R, FULL, MC>(g, mult, dst, rstride, nstore);
+    else if (fmt == 6) convert_store<6, R, FULL, MC>(g, mult, dst, rstride, nstore);
+    else convert_store<8, R, FULL, MC>(g, mult, dst, rstride, nstore);
   }
 };
 
@@ -498,12 +551,13 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
   return next_row0;
 }
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT, bool NORM>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT, bool NORM, bool MC = false>
 __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
   static_assert(NBUF == 1 || (NBUF == 2 && TABMODE != 2), "absolute table addresses cannot follow a second xs buffer");
   static_assert(!NORM || NP == 1, "the fused RMSNorm keeps a thread's weights addressable by thread index");
-  using QK = QuantKernel<R, NLD, NP, TABMODE, NORM>;
+  static_assert(!MC || R == 2, "the multicast scale-byte path is written for two rows per item");
+  using QK = QuantKernel<R, NLD, NP, TABMODE, NORM, MC>;
   const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
   extern __shared__ __align__(128) uint8_t smem[];
   const int K = p.K;
@@ -532,8 +586,9 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   // ---- one-time per CTA: inverse permutation as swizzled slot positions.  Eight consecutive permuted positions
   // j = 8*j8 + e occupy 8*SLOT contiguous bytes of xs whose chunks share one swizzle mask, so position e is at
   // base ^ (e * SLOT).
+  auto build_tab = [&](const int16_t* idxp) {
   for (int j8 = t; j8 < K8; j8 += T) {
-    const uint4 iv = __ldg(reinterpret_cast<const uint4*>(p.idx) + j8);
+    const uint4 iv = __ldg(reinterpret_cast<const uint4*>(idxp) + j8);
     const uint32_t ivw[4] = {iv.x, iv.y, iv.z, iv.w};
     const uint32_t pc0 = (uint32_t)j8 * (QK::SLOT / 2);  // first 16-byte chunk of the eight slots
     const uint32_t base = ((pc0 ^ ((pc0 >> 3) & QK::SWM)) << 4) + (TABMODE == 2 ? xs_a : 0u);
@@ -556,6 +611,10 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
                    : "memory");
     }
   }
+  };
+  int cur_grp = 0;
+  if (p.grp_rowblk == nullptr) build_tab(p.idx);
+  else cur_grp = -1;  // grouped: the first item's group is only known after griddepcontrol.wait (the router wrote it)
   if constexpr (NORM) {
     for (int i = t; i < NBUF * R * 128; i += T) sts32(ss_a + 4u * (uint32_t)i, 0u);
   }
@@ -579,11 +638,41 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
     if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, row0, t, T, K8, pre);
     else QK::template prefetch<false, EXACT>(p, xt, row0, t, T, K8, pre);
   }
+  if constexpr (MC) {
+    // the gather buffers may be overwritten once EVERY rank has finished reading the previous gather (normally long ago)
+    if (t == 0) {
+      uint32_t issued, seen;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(issued) : "l"(p.ag_issued) : "memory");
+      const uint32_t need = issued * (uint32_t)p.ag_tp;
+      unsigned long long t0 = 0;
+      for (uint32_t it = 1;; ++it) {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ag_consumed) : "memory");
+        if ((int32_t)(seen - need) >= 0) break;
+        __nanosleep(64);
+        if ((it & 1023u) == 0) {  // bounded (10 s): a lost peer must not hang the GPU
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) break;
+        }
+      }
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+    }
+  }
   __syncthreads();
 
   // items are ordered by row: the first item past the last row ends this CTA's work (block-uniform)
   int n = 0;
   while (row0 < rows) {
+    if (p.grp_rowblk != nullptr) {
+      const int g = __ldg(p.grp_rowblk + (row0 >> 7));  // block-uniform
+      if (g != cur_grp) {
+        __syncthreads();  // (NORM: the previous item's compute still reads the permuted weights)
+        build_tab(p.idx + (int64_t)g * K);
+        cur_grp = g;
+        __syncthreads();
+      }
+    }
     const uint32_t xs_cur = xs_a + ((NBUF == 2 && (n & 1)) ? xs_bytes : 0u);
     const uint32_t ss_cur = ss_a + ((NBUF == 2 && (n & 1)) ? (uint32_t)(R * 512) : 0u);
     if (row0 + 32 * (R - 1) < rows)
@@ -592,16 +681,31 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
       row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit);
     ++n;
   }
+  if constexpr (MC) {
+    __syncthreads();                      // every thread's multicast stores are issued ...
+    if (t == 0) __threadfence_system();   // ... and performed at system scope before this CTA counts as finished
+  }
   // the last CTA to leave resets the schedule for the next launch that uses this slot
   if (t == 0) {
     const unsigned int done = atomicInc(p.sched + 1, gridDim.x - 1);  // wraps to 0 by itself
-    if (done == gridDim.x - 1) atomicExch(p.sched, 0u);
+    if (done == gridDim.x - 1) {
+      atomicExch(p.sched, 0u);
+      if constexpr (MC) {
+        // all CTAs' stores have landed everywhere: tell every rank that this rank's rows of the gather are complete
+        __threadfence_system();
+        uint32_t issued;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(issued) : "l"(p.ag_issued) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.ag_issued), "r"(issued + 1u) : "memory");
+        for (int d = 0; d < p.ag_tp; ++d)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(p.ag_arrived[d]) : "memory");
+      }
+    }
   }
 }
 
 __device__ unsigned int g_quant_sched[64][2];  // rotating schedule slots (zero-initialised, self-resetting)
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool NORM = false>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool NORM = false, bool MC = false>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
   // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
@@ -616,25 +720,34 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
     return MMX_ERR_INVALID;
   }
   const bool exact = (int64_t)NLD * T * 8 == p.K && (int64_t)NP * T * 16 == p.K;
-  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM>
-                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM>;
-  static size_t attr_set[kMaxDevices][2] = {};
-  const int dev = current_device_slot();
-  if (smem > attr_set[dev][exact]) {
-    MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[dev][exact] = smem;
-  }
-  static int occ_cached = 0;
-  static size_t occ_smem = 0;
-  static int occ_T = 0;
-  static bool occ_exact = false;
-  if (occ_cached == 0 || occ_smem != smem || occ_T != T || occ_exact != exact) {
-    occ_T = T;
-    occ_exact = exact;
+  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM, MC>
+                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM, MC>;
+  // per-device, per-variant launch facts (dynamic shared memory opt-in, occupancy), guarded: callers may be threads
+  struct Cache {
+    size_t attr_smem = 0;  // largest opt-in granted so far
+    size_t occ_smem = 0;
+    int occ_T = 0;
     int occ = 0;
-    MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
-    occ_cached = occ < 1 ? 1 : occ;
-    occ_smem = smem;
+  };
+  static Cache cache[kMaxDevices][2];
+  static std::mutex mu;
+  const int dev = current_device_slot();
+  int occ_cached;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    Cache& c = cache[dev][exact];
+    if (smem > c.attr_smem) {
+      MMX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      c.attr_smem = smem;
+    }
+    if (c.occ == 0 || c.occ_smem != smem || c.occ_T != T) {
+      int occ = 0;
+      MMX_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+      c.occ = occ < 1 ? 1 : occ;
+      c.occ_smem = smem;
+      c.occ_T = T;
+    }
+    occ_cached = c.occ;
   }
   const int64_t rblocks = (p.rows + 127) / 128;
   const int64_t items = rblocks * 32 * (4 / R);
@@ -642,7 +755,10 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   int64_t grid = (int64_t)sm_count() * occ_cached;  // every SM full; items beyond two rounds are claimed dynamically
   if (options().quant_ctas > 0) grid = options().quant_ctas;
   if (grid > items) grid = items;
-  if (grid < 1) return MMX_OK;
+  if (grid < 1) {
+    if (!MC) return MMX_OK;
+    grid = 1;  // no rows on this rank: one CTA still waits, then announces the (empty) shard
+  }
   static unsigned int* sched_base[kMaxDevices] = {};  // the symbol's address differs from device to device
   if (!sched_base[dev]) MMX_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&sched_base[dev]), g_quant_sched));
   static std::atomic<unsigned int> seq{0};
@@ -662,10 +778,10 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   return MMX_OK;
 }
 
-static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO,
-                            const int fmt[3], uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1,
-                            uint8_t* s2, void* stream, const void* norm_w = nullptr, float eps = 0.0f,
-                            bool norm = false) {
+int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO,
+                     const int fmt[3], uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1,
+                     uint8_t* s2, void* stream, const void* norm_w, float eps, bool norm, const QuantGather* ag,
+                     const int* grp_rowblk, const int* row_src) {
   if (rows < 0 || K <= 0 || KN < 0 || KS < 0 || KO < 0 || KN + KS + KO != K) {
     set_error("reorder_quantize: bad shape rows=%lld K=%d (KN,KS,KO)=(%d,%d,%d)", (long long)rows, K, KN, KS, KO);
     return MMX_ERR_INVALID;
@@ -707,8 +823,17 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
     set_error("rmsnorm_quantize_x: K=%d exceeds the supported 16384", K);
     return MMX_ERR_INVALID;
   }
-  if (rows == 0) return MMX_OK;
+  if (rows == 0 && ag == nullptr) return MMX_OK;  // (a gather takes part with zero rows too: its arrival is awaited)
   QuantParams p;
+  memset(&p, 0, sizeof(p));
+  if (ag != nullptr) {
+    p.ag_consumed = ag->consumed;
+    p.ag_issued = ag->issued;
+    p.ag_tp = ag->tp;
+    for (int d = 0; d < ag->tp && d < kMaxTp; ++d) p.ag_arrived[d] = ag->arrived[d];
+  }
+  p.grp_rowblk = grp_rowblk;
+  p.row_src = row_src;
   p.nw = static_cast<const uint16_t*>(norm_w);
   p.eps = eps;
   p.x = static_cast<const uint16_t*>(x);
@@ -732,6 +857,20 @@ static int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* i
   // minimum CTAs per SM (register bound), table encoding
   // (measured on B200, profiles/r01_quantize_sweep.log: all K <= 4096 variants are within 3 % of each other; the
   // double-buffered form wins by 2-3 % where one CTA owns the whole SM)
+  if (ag != nullptr) {  // sequence-parallel hand-over: multicast stores + arrival (one configuration per K range)
+    if (K > 16384) {
+      set_error("quantize_allgather: K=%d exceeds the supported 16384", K);
+      return MMX_ERR_INVALID;
+    }
+    if (norm) {
+      if (K <= 4096) return launch_quant<2, 256, 2, 1, 3, 0, 1, true, true>(p, st);
+      if (K <= 8192) return launch_quant<2, 512, 2, 1, 1, 0, 2, true, true>(p, st);
+      return launch_quant<2, 1024, 2, 1, 1, 0, 2, true, true>(p, st);
+    }
+    if (K <= 4096) return launch_quant<2, 256, 2, 1, 4, 0, 1, false, true>(p, st);
+    if (K <= 8192) return launch_quant<2, 512, 2, 1, 2, 0, 2, false, true>(p, st);
+    return launch_quant<2, 1024, 2, 1, 1, 0, 2, false, true>(p, st);
+  }
   if (norm) {
     if (K <= 4096) return launch_quant<2, 256, 2, 1, 3, 0, 1, true>(p, st);
     if (K <= 8192) return launch_quant<2, 512, 2, 1, 1, 0, 2, true>(p, st);
@@ -756,26 +895,42 @@ extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_x(con
                                       uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
                                       void* stream) {
   const int fmt[3] = {4, 6, 8};
-  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream);
+  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, nullptr, 0.0f, false, nullptr, nullptr);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_w(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO,
                                       uint8_t* wn, uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
                                       void* stream) {
   const int fmt[3] = {4, 6, 8};
-  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream);
+  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream, nullptr, 0.0f, false, nullptr, nullptr);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_w4(const void* w, int64_t N, int K, const int16_t* idx, int KN, int KS, int KO,
                                        uint8_t* wn, uint8_t* ws, uint8_t* wo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
                                        void* stream) {
   const int fmt[3] = {4, 4, 4};
-  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream);
+  return mmx::reorder_quantize(w, N, K, idx, KN, KS, KO, fmt, wn, ws, wo, sfn, sfs, sfo, stream, nullptr, 0.0f, false, nullptr, nullptr);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_rmsnorm_quantize_x(const void* x, const void* w, float eps, int64_t M, int K, const int16_t* idx,
                                       int KN, int KS, int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn,
                                       uint8_t* sfs, uint8_t* sfo, void* stream) {
   const int fmt[3] = {4, 6, 8};
-  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, w, eps, true);
+  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, w, eps, true, nullptr, nullptr);
+}
+
+// Grouped form (Mixtral experts, extension; the reference loops over experts in Python, model/qMixtralLayer.py:437-450):
+// rows sorted by group, each 128-row block owned by ONE group; idx = int16 [groups, K], grp_rowblk = int32 [ceil(M/128)]
+// in device memory (written on the stream -- no host synchronisation), the same (KN, KS, KO) for every group.
+// row_src (optional) = int32 [M]: sorted row r is row row_src[r] of x -- the gather of the routed tokens is fused.
+extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_x_grouped(
+    const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk, const int32_t* row_src, int KN, int KS,
+    int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream) {
+  if (!grp_rowblk) {
+    mmx::set_error("reorder_quantize_x_grouped: null group table");
+    return MMX_ERR_INVALID;
+  }
+  const int fmt[3] = {4, 6, 8};
+  return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, nullptr, 0.0f, false, nullptr,
+                               grp_rowblk, row_src);
 }

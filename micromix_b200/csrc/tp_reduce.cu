@@ -28,14 +28,22 @@
 // symmetric-memory allocator, which also provides the multicast mapping):
 //   [flags 256 KB][staging: 2 parities x tp slots x own_tiles_cap tiles of 256x256 bf16][C: 2 parities x M_cap x N_cap]
 // A staging tile is BOX-MAJOR: the 32 x 32 box (band b of 32 rows, column chunk sc) is the 2 KB at ((b * 8 + sc) * 2 KB).
-// Calls alternate the parity, which is all the protection the protocol needs: a rank can run at most one call ahead
-// of its peers (its reducer of call c cannot finish before every peer has delivered call c), so while a slow rank still
-// reads staging[c & 1] a fast rank writes staging[(c+1) & 1].  Counters are reset by their only reader.
+// Ordering.  (1) The reducer triggers its programmatic dependents only at its very END, so on one rank the kernels of call
+// c+1 never overlap the reducer of call c (an early trigger would let the reducer of call c+2 -- same parity -- run next to
+// it whenever the grids are small enough to be co-resident).  (2) A rank's reducer of call c cannot finish before every
+// peer's reducer CTAs have arrived on its `done` counter, i.e. before every peer has finished reading staging and has
+// reset its tile counters for call c; hence a rank is at most one call ahead of its peers.  (3) Calls alternate the parity
+// (staging, C, counters), so the caller's result stays valid until the second next call.  The host-side parity is baked
+// into a captured CUDA graph: a graph holding an ODD number of calls replays with the same parity on both sides of the
+// replay boundary.  That is still safe -- by (1) and (2) every reader of call c is done before any writer of call c+1
+// starts, and `done` is a MONOTONIC counter compared against a device-side base, so an early arrival can never be wiped
+// out by a late reset -- only the result's lifetime shrinks to "until the next call" across that boundary.
 // Every rank must issue the same sequence of calls (same shapes) on one stream -- the usual SPMD contract.
 // Every cross-rank wait is bounded (option tp_timeout_ms): a lost peer costs an error word, not the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -52,20 +60,40 @@ constexpr int64_t kOffConsumed = 2 * kFlagCap * 4;   // u32 [2][kFlagCap]
 constexpr int64_t kOffDone = 4 * kFlagCap * 4;       // u32 [2], 128 bytes apart
 constexpr int64_t kOffTicket = kOffDone + 256;       // u32 [2], 128 bytes apart
 constexpr int64_t kOffErr = kOffTicket + 256;        // u32: 1 = tile wait timed out, 2 = final wait timed out
+constexpr int64_t kOffDoneBase = kOffErr + 128;      // u32 [2], 128 bytes apart: value of `done` before the current call
+// sequence-parallel gather channel (all counters only ever count up)
+constexpr int64_t kOffAgArrived = kOffDoneBase + 256;            // u32 [kMaxTp], 128 bytes apart: gathers landed from rank s
+constexpr int64_t kOffAgConsumed = kOffAgArrived + 128 * kMaxTp; // u32: +1 per rank that finished reading a gather
+constexpr int64_t kOffAgIssued = kOffAgConsumed + 128;           // u32: gathers issued by this rank
+constexpr int64_t kOffAgTaken = kOffAgIssued + 128;              // u32: gathers consumed by this rank's GEMMs
+constexpr int64_t kOffAgTicket = kOffAgTaken + 128;              // u32: last-CTA ticket of the consuming GEMM
+static_assert(kOffAgTicket + 128 <= kFlagBytes, "flags region");
 
 struct TpLayout {
-  int64_t own_tiles_cap, slot_bytes, stage_off, out_off, out_bytes, total;
+  int64_t own_tiles_cap, slot_bytes, stage_off, out_off, out_bytes, ag_off, ag_bytes, total;
 };
 
-static TpLayout make_layout(int64_t M_cap, int64_t N_cap, int tp) {
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// bytes of one gathered activation [M, K] in the worst split (all FP8) + its three scale buffers
+static int64_t ag_region_bytes(int64_t M, int64_t K) {
+  if (M <= 0 || K <= 0) return 0;
+  const int64_t sf = align_up((M / 128 + 1) * 128 * K / 32, 1024);
+  return 3 * align_up(M * K, 1024) + 3 * sf;
+}
+
+static TpLayout make_layout(int64_t M_cap, int64_t N_cap, int tp, int64_t ag_M = 0, int64_t ag_K = 0) {
   TpLayout L;
-  const int64_t tiles = ((M_cap + 255) / 256) * ((N_cap + 255) / 256);
-  L.own_tiles_cap = (tiles + tp - 1) / tp;
+  const int64_t n_t = (N_cap + 255) / 256;
+  const int64_t tiles = ((M_cap + 255) / 256) * n_t;
+  L.own_tiles_cap = (tiles + tp - 1) / tp + n_t;  // + one row of tiles: the reduce-scatter raster rounds m-tiles up to tp
   L.slot_bytes = L.own_tiles_cap * kTileBytes;
   L.stage_off = kFlagBytes;
   L.out_off = L.stage_off + 2 * (int64_t)tp * L.slot_bytes;
   L.out_bytes = ((M_cap * N_cap * 2 + 1023) / 1024) * 1024;
-  L.total = L.out_off + 2 * L.out_bytes;
+  L.ag_off = L.out_off + 2 * L.out_bytes;
+  L.ag_bytes = ag_region_bytes(ag_M, ag_K);
+  L.total = L.ag_off + L.ag_bytes;
   return L;
 }
 
@@ -75,6 +103,7 @@ struct TpCtx {
   uint8_t* ws[kMaxTp];
   TpLayout L;
   CUtensorMap maps[2][kMaxTp];  // [parity][destination rank]
+  int64_t ag_M, ag_K;           // capacity of the gather channel (rows x channels), 0 = none
   uint8_t* mc;                  // NVSwitch multicast mapping of the whole workspace (all ranks), or null
   int pull;                     // reduce in the switch (multimem.ld_reduce) instead of pushing partials to owner slots
   uint64_t calls;
@@ -87,6 +116,7 @@ struct ReduceParams {
   uint32_t* consumed;       // local, this parity
   uint32_t* done[kMaxTp];   // this parity's "C is complete" counter on every rank (peer-mapped)
   uint32_t* ticket;         // local
+  uint32_t* done_base;      // local: `done` is never reset; this call completes at done_base + done_expect
   uint32_t* err;            // local
   __nv_bfloat16* c[kMaxTp];  // this parity's C on every rank (peer-mapped)
   __nv_bfloat16* mc_c;       // ... and its multicast address (one multimem.st reaches every rank), or null
@@ -94,6 +124,7 @@ struct ReduceParams {
   int rank, tile_rows, own_tiles, m_tiles, n_tiles, n_fastest;  // own_tiles = blocks of tp tiles (the last may be partial)
   int rot_s, num_tiles;
   int pull;                 // 1: partials live in every rank's own C, reduced in the switch (needs mc_c)
+  int shard, m_per;         // reduce-scatter: this rank keeps only the m-tiles [rank * m_per, (rank+1) * m_per)
   uint32_t tile_expect;     // tp * 4 * CG arrivals complete a tile
   uint32_t done_expect;     // reducer CTAs of all ranks
   unsigned long long timeout_ns;
@@ -117,7 +148,7 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 __device__ bool spin_until(const uint32_t* flag, uint32_t target, unsigned long long timeout_ns) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
-    if (ld_relaxed_sys(flag) >= target) {
+    if ((int32_t)(ld_relaxed_sys(flag) - target) >= 0) {  // wrap-safe: `done` counts up for the life of the workspace
       asm volatile("fence.acq_rel.sys;" ::: "memory");
       return true;
     }
@@ -145,97 +176,119 @@ __device__ __forceinline__ void acc_bf16x8(float (&a)[8], const uint4& v) {
 
 __device__ unsigned long long g_tp_times[8];  // timeline probe of reducer CTA 0: entry, first tile ready, last unit done, exit
 
-// Work unit = 64 rows of one owned tile (256 threads: 32 x 16-byte columns, 8 rows per pass).
+// Work unit = 64 rows of one owned tile (256 threads: 32 x 16-byte columns, 8 rows per thread, all 8 loads in flight at
+// once: the in-switch reduction is a ~few-us round trip and the kernel is bound by bytes in flight, not by issue).
 template <int TP>
 __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_constant__ ReduceParams p) {
-  // the next kernel in the stream may start its prologue; this kernel itself does NOT wait for the GEMM grid in front of
-  // it -- the per-tile counters are the dependency -- until the very end (griddepcontrol.wait below)
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // this kernel does NOT wait for the GEMM grid in front of it -- the per-tile counters are the dependency -- until the
+  // very end (griddepcontrol.wait below); its own dependents are released only there too (see "Ordering" in the header)
   const int tid = threadIdx.x;
+  __shared__ uint32_t s_bad;
+  uint32_t done_target = 0;
+  if (tid == 0) done_target = ld_relaxed_sys(p.done_base) + p.done_expect;  // before any CTA of this grid can bump it
   const int c16 = tid & 31, r0 = tid >> 5;
   const int upt = p.tile_rows >> 6;
   const int units = p.own_tiles * upt;
   if (blockIdx.x == 0 && tid == 0) g_tp_times[0] = global_ns();
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int own_idx = u / upt, sub = u - own_idx * upt;
-    if (own_idx * TP + ((p.rank - (own_idx * TP) / p.rot_s) % TP + TP) % TP >= p.num_tiles) continue;  // partial last block
-    if (tid == 0 && !(p.dbg & 4u) && !spin_until(p.tile_flags + own_idx, p.tile_expect, p.timeout_ns)) atomicOr(p.err, 1u);
+    int tile, m_blk, n_blk;
+    if (p.shard) {
+      // reduce-scatter raster (GemmParams::n_fastest == 2): my j-th tile is tile j * TP + rank
+      tile = own_idx * TP + p.rank;
+      m_blk = p.rank * p.m_per + own_idx / p.n_tiles;
+      n_blk = own_idx % p.n_tiles;
+      if (m_blk >= p.m_tiles) continue;
+    } else {
+      tile = own_idx * TP + ((p.rank - (own_idx * TP) / p.rot_s) % TP + TP) % TP;  // see RsParams::rot_s
+      if (tile >= p.num_tiles) continue;  // partial last block
+      m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
+      n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+    }
+    if (tid == 0) {
+      const bool ok = (p.dbg & 4u) || spin_until(p.tile_flags + own_idx, p.tile_expect, p.timeout_ns);
+      if (!ok) atomicOr(p.err, 1u);
+      s_bad = ok ? 0u : 1u;
+    }
     if (blockIdx.x == 0 && tid == 0 && u == 0) g_tp_times[1] = global_ns();
     __syncthreads();
-    const int tile = own_idx * TP + ((p.rank - (own_idx * TP) / p.rot_s) % TP + TP) % TP;  // see RsParams::rot_s
-    const int m_blk = p.n_fastest ? tile / p.n_tiles : tile % p.m_tiles;
-    const int n_blk = p.n_fastest ? tile % p.n_tiles : tile / p.m_tiles;
+    const bool bad = s_bad != 0;  // a peer never delivered: the unit's rows are POISONED (NaN), never silently wrong
     const int64_t grow0 = (int64_t)m_blk * p.tile_rows + sub * 64 + r0;
     const int64_t gcol = (int64_t)n_blk * 256 + c16 * 8;
     // box-major staging (see the RS epilogue in gemm.cu): box (band, sc) of a tile is 32 rows x 64 bytes, contiguous
     const int bands = p.tile_rows >> 5;
     const uint4* src = p.stage + ((((int64_t)own_idx * bands + sub * 2) * 8 + (c16 >> 2)) * 32 + r0) * 4 + (c16 & 3);
     auto row_off = [](int k) { return (int64_t)((k >> 2) * (8 * 32 * 4) + (k & 3) * (8 * 4)); };  // row r0 + 8k, in uint4
-    if (p.pull) {
-      // IN-SWITCH reduction: every rank's GEMM wrote its partial tile into ITS OWN C (same offsets everywhere); one
-      // multimem.ld_reduce makes the NVSwitch read the tp copies and return their sum (fp32 accumulation), one
-      // multimem.st writes the bf16 result back over all tp copies.  Per rank and direction the wire carries the
-      // output once instead of 2(tp-1)/tp times; every rank receives the same bits.
-      if (gcol < p.N && !(p.dbg & 2u)) {
-#pragma unroll 1
-        for (int i = 0; i < 8; i += 4) {
-          uint4 v[4];
+    // where a reduced row goes: all-reduce -> every rank's C (one multicast store, or TP peer stores); reduce-scatter ->
+    // this rank's own C only (its rows of C ARE its shard: nobody else reads them, and the in-switch load of an address
+    // has returned before the store to it is issued)
+    auto store_row = [&](int64_t off, const uint4& o) {
+      if (p.shard) {
+        *reinterpret_cast<uint4*>(p.c[p.rank] + off) = o;
+      } else if (p.mc_c != nullptr) {
+        if (!(p.dbg & 1u))
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc_c + off),
+                       "f"(__uint_as_float(o.x)), "f"(__uint_as_float(o.y)), "f"(__uint_as_float(o.z)),
+                       "f"(__uint_as_float(o.w))
+                       : "memory");
+      } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t grow = grow0 + 8 * (i + j);
-            if (grow < p.M)
-              asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w)
-                           : "l"(p.mc_c + grow * p.N + gcol)
-                           : "memory");
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t grow = grow0 + 8 * (i + j);
-            if (grow < p.M && !(p.dbg & 1u))
-              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc_c + grow * p.N + gcol),
-                           "f"(__uint_as_float(v[j].x)), "f"(__uint_as_float(v[j].y)), "f"(__uint_as_float(v[j].z)),
-                           "f"(__uint_as_float(v[j].w))
-                           : "memory");
-          }
-        }
+        for (int d = 0; d < TP; ++d)
+          if (!(p.dbg & 1u) || d == p.rank) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
       }
-    } else if (gcol < p.N && !(p.dbg & 2u)) {
+    };
+    if (gcol < p.N && !(p.dbg & 2u)) {
+      if (bad) {
+        const uint4 nan4 = make_uint4(0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u, 0x7fc07fc0u);
 #pragma unroll 1
-      for (int i = 0; i < 8; i += 2) {
-        uint4 v[2][TP];
+        for (int k = 0; k < 8; ++k)
+          if (grow0 + 8 * k < p.M) store_row((grow0 + 8 * k) * p.N + gcol, nan4);
+      } else if (p.pull) {
+        // IN-SWITCH reduction: every rank's GEMM wrote its partial tile into ITS OWN C (same offsets everywhere); one
+        // multimem.ld_reduce makes the NVSwitch read the tp copies and return their sum (fp32 accumulation).  All-reduce:
+        // one multimem.st writes the bf16 result back over all tp copies -- per rank and direction the wire carries the
+        // output once instead of 2(tp-1)/tp times; reduce-scatter: the result stays here.  Every rank gets the same bits.
+        uint4 v[8];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool live = grow0 + 8 * (i + j) < p.M;
-#pragma unroll
-          for (int s = 0; s < TP; ++s)
-            v[j][s] = live ? ld_cg_u4(src + (int64_t)s * p.slot_u4 + row_off(i + j)) : make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < 8; ++k) {
+          const int64_t grow = grow0 + 8 * k;
+          if (grow < p.M)
+            asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w)
+                         : "l"(p.mc_c + grow * p.N + gcol)
+                         : "memory");
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int64_t grow = grow0 + 8 * (i + j);
-          if (grow < p.M) {
-            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < 8; ++k) {
+          const int64_t grow = grow0 + 8 * k;
+          if (grow < p.M) store_row(grow * p.N + gcol, v[k]);
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 8; i += 2) {
+          uint4 v[2][TP];
 #pragma unroll
-            for (int s = 0; s < TP; ++s) acc_bf16x8(a, v[j][s]);  // rank order: identical bits on every rank
-            uint4 o;
-            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+          for (int j = 0; j < 2; ++j) {
+            const bool live = grow0 + 8 * (i + j) < p.M;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * e], a[2 * e + 1]);
-              ow[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            const int64_t off = grow * p.N + gcol;
-            if (p.mc_c != nullptr && !(p.dbg & 1u)) {
-              // the switch replicates the store to every rank's C (own included): 1/tp of the NVLink egress
-              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.mc_c + off),
-                           "f"(__uint_as_float(o.x)), "f"(__uint_as_float(o.y)), "f"(__uint_as_float(o.z)),
-                           "f"(__uint_as_float(o.w))
-                           : "memory");
-            } else {
+            for (int sl = 0; sl < TP; ++sl)
+              v[j][sl] = live ? ld_cg_u4(src + (int64_t)sl * p.slot_u4 + row_off(i + j)) : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
-              for (int d = 0; d < TP; ++d)
-                if (!(p.dbg & 1u) || d == p.rank) *reinterpret_cast<uint4*>(p.c[d] + off) = o;
+          for (int j = 0; j < 2; ++j) {
+            const int64_t grow = grow0 + 8 * (i + j);
+            if (grow < p.M) {
+              float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int sl = 0; sl < TP; ++sl) acc_bf16x8(a, v[j][sl]);  // rank order: identical bits on every rank
+              uint4 o;
+              uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(a[2 * e], a[2 * e + 1]);
+                ow[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              store_row(grow * p.N + gcol, o);
             }
           }
         }
@@ -254,23 +307,26 @@ __global__ void __launch_bounds__(256, 2) tile_allreduce_kernel(const __grid_con
   __syncthreads();
   if (blockIdx.x == 0 && tid == 0) g_tp_times[2] = global_ns();
   if (tid == 0) {
-    // everything this CTA wrote into the ranks' C buffers is visible before the arrival
+    // everything this CTA wrote into the ranks' C buffers (and its counter resets) is visible before the arrival
     // (ONE system-scope fence, then relaxed arrivals: a release per destination would be a fence per destination)
     __threadfence_system();
 #pragma unroll
     for (int d = 0; d < TP; ++d) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.done[d]) : "memory");
-    // ... and this rank's C is complete once the reducer CTAs of ALL ranks have arrived here
-    if (!spin_until(p.done[p.rank], p.done_expect, p.timeout_ns)) atomicOr(p.err, 2u);
+    // ... and this rank's C is complete -- and every peer is done READING this rank's partials -- once the reducer CTAs of
+    // ALL ranks have arrived here.  `done` only ever counts up; the target is relative to its value before this call.
+    if (!spin_until(p.done[p.rank], done_target, p.timeout_ns)) atomicOr(p.err, 2u);
     const uint32_t t = atomicAdd(p.ticket, 1u);
     if (blockIdx.x == 0) g_tp_times[3] = global_ns();
-    if (t == gridDim.x - 1) {  // every local CTA is past its spin: reset for the call after next
-      *p.done[p.rank] = 0;
+    if (t == gridDim.x - 1) {  // every local CTA is past its spin (and has read done_base): publish the next base
+      *p.done_base = done_target;
       *p.ticket = 0;
       __threadfence();
     }
   }
-  // completion of this grid implies completion of the GEMM grid in front of it
+  __syncthreads();
+  // completion of this grid implies completion of the GEMM grid in front of it; only now may the next kernel start
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 static int reducer_grid(int own_tiles, int tile_rows) {
@@ -349,14 +405,19 @@ MMX_API int mmx_peer_free(void* ptr) {
 }
 
 // ------------------------------------------------------------------------------------------------ context
-MMX_API int64_t mmx_tp_workspace_bytes(int64_t M_cap, int64_t N_cap, int tp) {
-  if (M_cap <= 0 || N_cap <= 0 || tp < 1 || tp > kMaxTp) return -1;
-  return make_layout(M_cap, N_cap, tp).total;
+MMX_API int64_t mmx_tp_workspace_bytes_ex(int64_t M_cap, int64_t N_cap, int tp, int64_t ag_M, int64_t ag_K) {
+  if (M_cap <= 0 || N_cap <= 0 || tp < 1 || tp > kMaxTp || ag_M < 0 || ag_K < 0) return -1;
+  return make_layout(M_cap, N_cap, tp, ag_M, ag_K).total;
 }
 
-MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, void** ctx) {
+MMX_API int64_t mmx_tp_workspace_bytes(int64_t M_cap, int64_t N_cap, int tp) {
+  return mmx_tp_workspace_bytes_ex(M_cap, N_cap, tp, 0, 0);
+}
+
+MMX_API int mmx_tp_ctx_create_ex(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, int64_t ag_M, int64_t ag_K,
+                                 void** ctx) {
   if (!ws || !ctx || !(tp == 1 || tp == 2 || tp == 4 || tp == 8) || rank < 0 || rank >= tp || M_cap <= 0 || N_cap <= 0 ||
-      (N_cap % 128)) {
+      (N_cap % 128) || ag_M < 0 || ag_K < 0 || (ag_K % 128)) {
     set_error("mmx_tp_ctx_create: bad arguments (tp must be 1, 2, 4 or 8; N_cap a multiple of 128)");
     return MMX_ERR_INVALID;
   }
@@ -370,7 +431,9 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
   c->rank = rank;
   c->M_cap = M_cap;
   c->N_cap = N_cap;
-  c->L = make_layout(M_cap, N_cap, tp);
+  c->ag_M = ag_M;
+  c->ag_K = ag_K;
+  c->L = make_layout(M_cap, N_cap, tp, ag_M, ag_K);
   if (c->L.own_tiles_cap > kFlagCap) {
     set_error("mmx_tp_ctx_create: %lld tiles per rank exceed the flag capacity %d", (long long)c->L.own_tiles_cap, kFlagCap);
     delete c;
@@ -395,6 +458,10 @@ MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, 
     }
   *ctx = c;
   return MMX_OK;
+}
+
+MMX_API int mmx_tp_ctx_create(void* const* ws, int tp, int rank, int64_t M_cap, int64_t N_cap, void** ctx) {
+  return mmx_tp_ctx_create_ex(ws, tp, rank, M_cap, N_cap, 0, 0, ctx);
 }
 
 MMX_API int mmx_tp_ctx_set_multicast(void* ctx, void* mc_ws, int in_switch_reduce) {
@@ -428,13 +495,14 @@ MMX_API int mmx_tp_status(void* ctx, uint32_t* out) {
   return MMX_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ the fused op
-MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
-                                 const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
-                                 const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo,
-                                 int64_t M, int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out,
-                                 void* stream) {
-  TpCtx* c = static_cast<TpCtx*>(ctx);
+// ------------------------------------------------------------------------------------------------ the fused ops
+// shard = 0: all-reduce (every rank ends with the whole C); shard = 1: reduce-scatter (rank r ends with the rows of its
+// m-tiles only).  *row0 / *rows (shard) = the global row range this rank owns.
+static int matmul_reduce_impl(TpCtx* c, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                              const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                              const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M,
+                              int64_t N, int KN, int KS, int KO, int w4, const void* bias, int shard, void** c_out,
+                              int64_t* row0, int64_t* rows, void* stream) {
   if (!c || !c_out) {
     set_error("mmx_matmul_allreduce: null context or output slot");
     return MMX_ERR_INVALID;
@@ -455,14 +523,15 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   rsl.rank = c->rank;
   rsl.own_tiles_cap = c->L.own_tiles_cap;
   rsl.pull = c->pull;
+  rsl.shard = shard;
   rsl.c_local = c->ws[c->rank] + c->L.out_off + (int64_t)par * c->L.out_bytes;
   int rc = matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, nullptr,
                        stream, &rsl);
   if (rc) return rc;
   const int tile_rows = 128 * rsl.cg;
-  const int num_tiles = rsl.m_tiles * rsl.n_tiles;
-  // every rank walks ceil(num_tiles / tp) blocks; in a partial last block the ranks without a tile skip it
-  auto own_tiles = [&](int) { return (num_tiles + tp - 1) / tp; };
+  const int num_tiles = shard ? tp * rsl.m_per * rsl.n_tiles : rsl.m_tiles * rsl.n_tiles;
+  // every rank walks ceil(num_tiles / tp) blocks; tiles that do not exist (partial last block, raster round-up) are skipped
+  const int own_tiles = (num_tiles + tp - 1) / tp;
   uint8_t* me = c->ws[c->rank];
   ReduceParams p;
   memset(&p, 0, sizeof(p));
@@ -471,30 +540,31 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   p.tile_flags = rsl.tile_flags[c->rank];
   p.consumed = reinterpret_cast<uint32_t*>(me + kOffConsumed) + (int64_t)par * kFlagCap;
   p.ticket = reinterpret_cast<uint32_t*>(me + kOffTicket + 128 * par);
+  p.done_base = reinterpret_cast<uint32_t*>(me + kOffDoneBase + 128 * par);
   p.err = reinterpret_cast<uint32_t*>(me + kOffErr);
-  uint32_t done_expect = 0;
+  const int grid = reducer_grid(own_tiles, tile_rows);
   for (int d = 0; d < tp; ++d) {
     p.done[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffDone + 128 * par);
     p.c[d] = reinterpret_cast<__nv_bfloat16*>(c->ws[d] + c->L.out_off + (int64_t)par * c->L.out_bytes);
     if (c->mc) p.mc_c = reinterpret_cast<__nv_bfloat16*>(c->mc + c->L.out_off + (int64_t)par * c->L.out_bytes);
-    done_expect += (uint32_t)reducer_grid(own_tiles(d), tile_rows);
   }
   p.M = M;
   p.N = N;
   p.rank = c->rank;
   p.tile_rows = tile_rows;
-  p.own_tiles = own_tiles(c->rank);
+  p.own_tiles = own_tiles;
   p.m_tiles = rsl.m_tiles;
   p.n_tiles = rsl.n_tiles;
   p.n_fastest = rsl.n_fastest;
   p.rot_s = rsl.rot_s;
   p.num_tiles = num_tiles;
   p.pull = c->pull;
+  p.shard = shard;
+  p.m_per = rsl.m_per;
   p.tile_expect = (uint32_t)(tp * 4 * rsl.cg);
-  p.done_expect = done_expect;
+  p.done_expect = (uint32_t)(tp * grid);  // every rank launches the same reducer grid (same shapes, same device type)
   p.timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
   p.dbg = (uint32_t)options().tp_debug;
-  const int grid = reducer_grid(p.own_tiles, tile_rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (tp) {
     case 1: rc = launch_reducer<1>(p, grid, st); break;
@@ -504,6 +574,138 @@ MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn
   }
   if (rc) return rc;
   c->calls++;
-  *c_out = p.c[c->rank];
+  if (shard) {
+    const int64_t r0 = (int64_t)c->rank * rsl.m_per * tile_rows;
+    const int64_t r1 = r0 + (int64_t)rsl.m_per * tile_rows;
+    const int64_t lo = r0 < M ? r0 : M, hi = r1 < M ? r1 : M;
+    if (row0) *row0 = lo;
+    if (rows) *rows = hi - lo;
+    *c_out = p.c[c->rank] + lo * N;
+  } else {
+    *c_out = p.c[c->rank];
+  }
   return MMX_OK;
+}
+
+MMX_API int mmx_matmul_allreduce(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                                 const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                                 const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo,
+                                 int64_t M, int64_t N, int KN, int KS, int KO, int w4, const void* bias, void** c_out,
+                                 void* stream) {
+  return matmul_reduce_impl(static_cast<TpCtx*>(ctx), an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN,
+                            KS, KO, w4, bias, 0, c_out, nullptr, nullptr, stream);
+}
+
+MMX_API int mmx_matmul_reduce_scatter(void* ctx, const uint8_t* an, const uint8_t* bn, const uint8_t* as,
+                                      const uint8_t* bs, const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan,
+                                      const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+                                      const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                                      const void* bias, void** c_out, int64_t* row0, int64_t* rows, void* stream) {
+  return matmul_reduce_impl(static_cast<TpCtx*>(ctx), an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN,
+                            KS, KO, w4, bias, 1, c_out, row0, rows, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ sequence-parallel hand-over
+// Column-parallel linears read a REPLICATED activation.  Instead of every rank re-quantizing all M rows (and, before that,
+// receiving them as 2 bytes per element), each rank quantizes only ITS rows (the rows its reduce-scatter produced) and the
+// quantizer's stores go to the NVSwitch multicast address of a gather buffer that exists at the same offset in every
+// rank's workspace: 0.53-0.66 bytes per element on the wire, written once, landing everywhere.  The consuming GEMM
+// (mmx_tp_matmul_gathered) waits per source rank for that rank's arrival counter -- m-tile by m-tile, so the GEMM starts
+// on the rows that are there -- and its last CTA tells every rank that the buffer may be overwritten.
+struct AgViews {
+  int64_t off[6];  // xn, xs, xo, sfn, sfs, sfo inside the gather region
+};
+static AgViews ag_views(int64_t M, int KN, int KS, int KO) {
+  AgViews v;
+  int64_t o = 0;
+  const int64_t code_bytes[3] = {M * KN / 2, M * KS * 3 / 4, M * (int64_t)KO};
+  const int ks[3] = {KN, KS, KO};
+  for (int i = 0; i < 3; ++i) {
+    v.off[i] = o;
+    o += align_up(code_bytes[i], 1024);
+  }
+  for (int i = 0; i < 3; ++i) {
+    v.off[3 + i] = o;
+    o += align_up((M / 128 + 1) * 128 * ks[i] / 32, 1024);
+  }
+  return v;
+}
+
+static int ag_check(TpCtx* c, int64_t M, int K, const char* who) {
+  if (!c) {
+    set_error("%s: null context", who);
+    return MMX_ERR_INVALID;
+  }
+  if (!c->mc || c->L.ag_bytes == 0) {
+    set_error("%s: the context has no gather channel (create it with mmx_tp_ctx_create_ex and a multicast mapping)", who);
+    return MMX_ERR_INVALID;
+  }
+  if (M <= 0 || K <= 0 || ag_region_bytes(M, K) > c->L.ag_bytes) {
+    set_error("%s: M=%lld K=%d exceed the gather channel (%lld x %lld)", who, (long long)M, K, (long long)c->ag_M,
+              (long long)c->ag_K);
+    return MMX_ERR_INVALID;
+  }
+  return MMX_OK;
+}
+
+MMX_API int64_t mmx_tp_shard_rows(int64_t M, int tp) {
+  if (M <= 0 || tp < 1) return 0;
+  const int64_t m_tiles = (M + 255) / 256;
+  return (m_tiles + tp - 1) / tp * 256;
+}
+
+MMX_API int mmx_tp_quantize_allgather(void* ctx, const void* x_shard, int64_t M, int K, const int16_t* idx, int KN, int KS,
+                                      int KO, const void* norm_w, float eps, void** views, void* stream) {
+  TpCtx* c = static_cast<TpCtx*>(ctx);
+  if (int rc = ag_check(c, M, K, "mmx_tp_quantize_allgather")) return rc;
+  const int64_t per = mmx_tp_shard_rows(M, c->tp);
+  const int64_t row0 = std::min<int64_t>(M, per * c->rank), row1 = std::min<int64_t>(M, per * (c->rank + 1));
+  const AgViews v = ag_views(M, KN, KS, KO);
+  const int ks[3] = {KN, KS, KO};
+  const int bits[3] = {4, 6, 8};
+  uint8_t* q[3];
+  uint8_t* sf[3];
+  uint8_t* mc_base = c->mc + c->L.ag_off;
+  for (int i = 0; i < 3; ++i) {
+    // this rank's rows start at row0 (a multiple of 256): whole packed rows and whole 128-row scale blocks
+    q[i] = ks[i] ? mc_base + v.off[i] + row0 * ((int64_t)ks[i] * bits[i] / 8) : nullptr;
+    sf[i] = ks[i] ? mc_base + v.off[3 + i] + (row0 / 128) * (int64_t)(ks[i] / 128) * 512 : nullptr;
+  }
+  uint8_t* me = c->ws[c->rank];
+  QuantGather ag;
+  memset(&ag, 0, sizeof(ag));
+  ag.consumed = reinterpret_cast<const uint32_t*>(me + kOffAgConsumed);
+  ag.issued = reinterpret_cast<uint32_t*>(me + kOffAgIssued);
+  ag.tp = c->tp;
+  for (int d = 0; d < c->tp; ++d)
+    ag.arrived[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffAgArrived + 128 * c->rank);
+  const int fmt[3] = {4, 6, 8};
+  if (int rc = reorder_quantize(x_shard, row1 - row0, K, idx, KN, KS, KO, fmt, q[0], q[1], q[2], sf[0], sf[1], sf[2], stream,
+                                norm_w, eps, norm_w != nullptr, &ag))
+    return rc;
+  if (views) {
+    uint8_t* local = me + c->L.ag_off;
+    for (int i = 0; i < 6; ++i) views[i] = local + v.off[i];
+  }
+  return MMX_OK;
+}
+
+MMX_API int mmx_tp_matmul_gathered(void* ctx, const uint8_t* bn, const uint8_t* bs, const uint8_t* bo, const uint8_t* sfbn,
+                                   const uint8_t* sfbs, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO,
+                                   int w4, const void* bias, void* c_out, void* stream) {
+  TpCtx* c = static_cast<TpCtx*>(ctx);
+  if (int rc = ag_check(c, M, KN + KS + KO, "mmx_tp_matmul_gathered")) return rc;
+  const AgViews v = ag_views(M, KN, KS, KO);
+  uint8_t* me = c->ws[c->rank];
+  uint8_t* local = me + c->L.ag_off;
+  MatmulExtra ex;
+  ex.ag_arrived = reinterpret_cast<const uint32_t*>(me + kOffAgArrived);
+  ex.ag_taken = reinterpret_cast<uint32_t*>(me + kOffAgTaken);
+  ex.ag_rows = (int)mmx_tp_shard_rows(M, c->tp);
+  ex.ag_ticket = reinterpret_cast<uint32_t*>(me + kOffAgTicket);
+  ex.ag_tp = c->tp;
+  for (int d = 0; d < c->tp; ++d) ex.ag_consumed[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffAgConsumed);
+  return matmul_impl(KN ? local + v.off[0] : nullptr, bn, KS ? local + v.off[1] : nullptr, bs, KO ? local + v.off[2] : nullptr,
+                     bo, KN ? local + v.off[3] : nullptr, sfbn, KS ? local + v.off[4] : nullptr, sfbs,
+                     KO ? local + v.off[5] : nullptr, sfbo, M, N, KN, KS, KO, w4, bias, c_out, stream, nullptr, &ex);
 }

@@ -23,7 +23,8 @@ import torch
 from . import _lib
 
 __all__ = ["matmul", "reorder_quantize_x", "reorder_quantize_w", "reorder_quantize_w4", "rmsnorm_quantize_x",
-           "activate_quantize_x", "downproj_quantize_w", "downproj_quantize_w4", "test_function", "launch_count"]
+           "activate_quantize_x", "downproj_quantize_w", "downproj_quantize_w4", "test_function", "launch_count",
+           "reorder_quantize_x_grouped", "matmul_grouped", "moe_combine"]
 
 
 def _stream() -> int:
@@ -244,6 +245,87 @@ def downproj_quantize_w4(W, KN, KS, KO):
     """Quantize already-ordered weight rows to MXFP4 in all three segments (bindings.cpp:362-387)."""
     return _rowwise("mmx_downproj_quantize_w4", (W,), ("W",), KN, KS, KO,
                     lambda kn, ks, ko: (kn // 2, ks // 2, ko // 2))
+
+
+# ---------------------------------------------------------------------------------------------- grouped forms (Mixtral)
+def reorder_quantize_x_grouped(X, reorder_index, group_of_rowblock, KN, KS, KO, row_src=None, rows=None):
+    """Extension (the reference loops over experts in Python, qMixtralLayer.py:437-450): ONE quantize launch over the
+    expert-sorted, per-expert-padded token matrix.  reorder_index int16 [groups, K]; group_of_rowblock int32 [rows/128]
+    (device); row_src int32 [rows] (device, optional): sorted row r is X[row_src[r]] -- the gather is fused; `rows` = rows
+    of the sorted matrix (defaults to X.size(0)).  -> the six tensors of reorder_quantize_x for the sorted matrix."""
+    lib = _lib.load()
+    _check_cuda("X", X, torch.bfloat16, 2)
+    _check_cuda("reorder_index", reorder_index, torch.int16, 2)
+    _check_cuda("group_of_rowblock", group_of_rowblock, torch.int32, 1)
+    K = X.size(1)
+    M = int(rows) if rows is not None else X.size(0)
+    KN, KS, KO = _check_split(K, KN, KS, KO)
+    if reorder_index.size(1) != K:
+        raise ValueError(f"reorder_index must be [groups, {K}]")
+    if M % 128 or group_of_rowblock.numel() < M // 128:
+        raise ValueError("the sorted matrix must be padded to whole 128-row blocks, one group id per block")
+    if row_src is not None:
+        _check_cuda("row_src", row_src, torch.int32, 1)
+        if row_src.numel() < M:
+            raise ValueError(f"row_src must have {M} entries")
+    elif X.size(0) != M:
+        raise ValueError("without row_src, X must be the sorted matrix itself")
+    opts = dict(dtype=torch.uint8, device=X.device)
+    with torch.cuda.device(X.device):
+        q = [torch.empty((M, w), **opts) for w in (KN // 2, KS // 4 * 3, KO)]
+        sf = [torch.empty((int(lib.mmx_sf_bytes_act(M, k)),), **opts) for k in (KN, KS, KO)]
+        rc = 0
+        if M > 0:
+            rc = lib.mmx_reorder_quantize_x_grouped(_ptr(X), M, K, _ptr(reorder_index), _ptr(group_of_rowblock), _ptr(row_src),
+                                                    KN, KS, KO, _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]),
+                                                    _ptr(sf[2]), _stream())
+    _lib.check(rc, "mmx_reorder_quantize_x_grouped")
+    return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
+
+
+def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None):
+    """Extension: ONE persistent mixed GEMM over all experts.  A = the six tensors of the sorted, padded activation
+    ([M, *]); W = six tensors with the experts' MXFP4 weights stacked on N ([groups * N, *]); group_of_mtile int32
+    [M / tile_rows] (device): expert of each m-tile, -1 = padding tile (skipped) -> bf16 [M, N]."""
+    lib = _lib.load()
+    for t in list(A) + list(W):
+        _check_cuda("operand", t, torch.uint8)
+    _check_cuda("group_of_mtile", group_of_mtile, torch.int32, 1)
+    M = A[0].size(0)
+    KN, KS, KO = A[0].size(1) * 2, A[1].size(1) * 4 // 3, A[2].size(1)
+    if W[0].size(0) % groups:
+        raise ValueError("the stacked weights must hold `groups` equal blocks of rows")
+    N = W[0].size(0) // groups
+    if tile_rows not in (128, 256) or M % tile_rows or group_of_mtile.numel() < M // tile_rows:
+        raise ValueError("M must be padded to whole m-tiles (128 | 256 rows), one group id per m-tile")
+    with torch.cuda.device(A[0].device):
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=A[0].device)
+        rc = 0
+        if M > 0:
+            rc = lib.mmx_matmul_grouped(_ptr(A[0]), _ptr(W[0]), _ptr(A[1]), _ptr(W[1]), _ptr(A[2]), _ptr(W[2]), _ptr(A[3]),
+                                        _ptr(W[3]), _ptr(A[4]), _ptr(W[4]), _ptr(A[5]), _ptr(W[5]), M, N, KN, KS, KO, 1,
+                                        int(groups), int(tile_rows), _ptr(group_of_mtile), _ptr(out), _stream())
+    _lib.check(rc, "mmx_matmul_grouped")
+    return out
+
+
+def moe_combine(Y, row, expert, weight, out=None):
+    """out[t] = sum over token t's slots, ascending expert id, of bf16(Y[row[t,s]] * weight[t,s]) with a bf16 rounding
+    after every add (the reference's index_add_ loop, qMixtralLayer.py:446-450); row < 0 = expert not on this rank."""
+    lib = _lib.load()
+    _check_cuda("Y", Y, torch.bfloat16, 2)
+    _check_cuda("row", row, torch.int32, 2)
+    _check_cuda("expert", expert, torch.int32, 2)
+    _check_cuda("weight", weight, torch.bfloat16, 2)
+    T, k = row.shape
+    H = Y.size(1)
+    with torch.cuda.device(Y.device):
+        if out is None:
+            out = torch.empty((T, H), dtype=torch.bfloat16, device=Y.device)
+        rc = lib.mmx_moe_combine(_ptr(Y), _ptr(row), _ptr(expert), _ptr(weight), T, k, H, _ptr(out), _stream()) if T else 0
+    _lib.check(rc, "mmx_moe_combine")
+    return out
 
 
 def test_function():

@@ -32,8 +32,10 @@ import torch.nn as nn
 
 
 # --------------------------------------------------------------------------------------------------- shard planning
-def _round128(n: float, lo: int, hi: int) -> int:
-    return int(min(max(int(round(n / 128.0)) * 128, lo), hi))
+def _ceil128(n: int, hi: int) -> int:
+    """n rounded UP to a multiple of 128 (clipped to hi): like the reference's calibration (reorder_indices.py:109-110),
+    a shard never stores a channel in a LOWER precision than the global split gives it."""
+    return int(min(-(-int(n) // 128) * 128, hi))
 
 
 def column_shard_range(N: int, tp: int, rank: int) -> Tuple[int, int]:
@@ -49,7 +51,9 @@ def row_shard_plan(reorder_index: torch.Tensor, p6_num: int, p8_num: int, tp: in
 
     The global permutation lists channels in ascending importance: [0,p4) FP4, [p4,p4+p6) FP6, the last p8 FP8
     (reorder_indices.py:64-69).  Filtering it to the rank's slice keeps that order; the local FP6/FP8 counts are the
-    number of globally-FP6/FP8 channels that fell into the slice, rounded to multiples of 128.
+    number of globally-FP6/FP8 channels that fell into the slice, rounded UP to multiples of 128 (the channels the
+    rounding promotes into FP8 come from the top of the FP6 population and are not counted twice): no globally-FP8
+    channel is ever stored as FP6 / FP4 and no globally-FP6 channel as FP4.
     Returns (k0, k1, local_index[int16, K/tp], p4, p6, p8).
     """
     idx = reorder_index.to(torch.int64).cpu()
@@ -64,8 +68,8 @@ def row_shard_plan(reorder_index: torch.Tensor, p6_num: int, p8_num: int, tp: in
     p4_global = K - p6_num - p8_num
     n8 = int((pos >= p4_global + p6_num).sum())
     n6 = int(((pos >= p4_global) & (pos < p4_global + p6_num)).sum())
-    p8 = _round128(n8, 0, per) if p8_num else 0
-    p6 = _round128(n6, 0, per - p8) if p6_num else 0
+    p8 = _ceil128(n8, per) if p8_num else 0
+    p6 = _ceil128(max(n6 - (p8 - n8), 0), per - p8) if p6_num else 0
     p4 = per - p6 - p8
     return k0, k1, local.contiguous(), p4, p6, p8
 
@@ -81,8 +85,9 @@ def all_reduce_sum(t: torch.Tensor, group=None, async_op: bool = False):
 class _DeviceBytes:
     """Zero-copy torch view of raw device memory owned by libmicromix_b200 (CUDA array interface)."""
 
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 2,), "typestr": "<i2", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, nbytes: int, typestr: str = "<i2"):
+        item = int(typestr[-1])
+        self.__cuda_array_interface__ = {"shape": (nbytes // item,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class PeerWorkspace:
@@ -94,11 +99,14 @@ class PeerWorkspace:
     loads / stores / reductions over NVLink.
     """
 
-    def __init__(self, M_cap: int, N_cap: int, group=None, device=None, _sim=None, mode: Optional[str] = None):
+    def __init__(self, M_cap: int, N_cap: int, group=None, device=None, _sim=None, mode: Optional[str] = None,
+                 gather: Optional[Tuple[int, int]] = None):
         """mode: "push" (partials pushed to owner slots over peer mappings, rank-ordered fp32 sum),
         "switch" (partials reduced inside the NVSwitch through a multicast mapping), or None = "auto": the environment
         variable MMX_TP_MODE if set, else "switch" for tp >= 4 when the box offers multicast memory, "push" otherwise
-        (at tp = 2 the switch path loops every result back to its sender and moves more bytes than the push path)."""
+        (at tp = 2 the switch path loops every result back to its sender and moves more bytes than the push path).
+        gather = (M, K): also reserve the sequence-parallel gather channel for activations up to [M, K]
+        (quantize_allgather / matmul_gathered); it needs the multicast mapping whatever the reduction mode."""
         import ctypes
         import os
         mode = mode or os.environ.get("MMX_TP_MODE", "auto")
@@ -110,27 +118,32 @@ class PeerWorkspace:
         self._ctypes = ctypes
         self.group = group
         self.M_cap, self.N_cap = int(M_cap), int(N_cap)
+        self.gather = (int(gather[0]), int(gather[1])) if gather else (0, 0)
         self.peers, self.own = [], None
+        self._calls = 0
         if _sim is not None:  # (tp, rank, [workspace pointers]) -- several "ranks" inside one process (tests)
             self.tp, self.rank, ptrs = _sim
             self.device = torch.device("cuda", torch.cuda.current_device())
-            self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
+            self.nbytes = int(lib.mmx_tp_workspace_bytes_ex(self.M_cap, self.N_cap, self.tp, *self.gather))
         else:
             if not (dist.is_available() and dist.is_initialized()):
                 raise RuntimeError("PeerWorkspace needs an initialised torch.distributed process group")
             self.tp, self.rank = dist.get_world_size(group), dist.get_rank(group)
             self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-            self.nbytes = int(lib.mmx_tp_workspace_bytes(self.M_cap, self.N_cap, self.tp))
+            self.nbytes = int(lib.mmx_tp_workspace_bytes_ex(self.M_cap, self.N_cap, self.tp, *self.gather))
             if self.nbytes <= 0:
                 raise ValueError(f"tensor-parallel degree {self.tp} is not supported by the fused path (1, 2, 4, 8)")
             explicit = mode != "auto"
             if mode == "auto":
                 mode = "switch" if self.tp >= 4 else "push"
-            ptrs = self._map_symmetric(group) if mode in ("switch", "push_mc") else None
+            want_mc = mode in ("switch", "push_mc") or self.gather[0] > 0
+            ptrs = self._map_symmetric(group) if want_mc else None
             if ptrs is None:
-                if explicit and mode in ("switch", "push_mc"):  # asked for by name: do not silently change the data path
-                    raise RuntimeError(f"PeerWorkspace mode {mode!r} needs NVSwitch multicast memory (torch symmetric "
-                                       "memory with a multicast mapping), which this box / torch build does not offer")
+                if (explicit and mode in ("switch", "push_mc")) or self.gather[0] > 0:
+                    # asked for by name: do not silently change the data path
+                    raise RuntimeError(f"PeerWorkspace mode {mode!r} / the gather channel need NVSwitch multicast memory "
+                                       "(torch symmetric memory with a multicast mapping), which this box / torch build "
+                                       "does not offer")
                 mode = "push"
                 with torch.cuda.device(self.device):
                     own = ctypes.c_void_p()
@@ -151,8 +164,8 @@ class PeerWorkspace:
         arr = (ctypes.c_void_p * self.tp)(*ptrs)
         ctx = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(lib.mmx_tp_ctx_create(arr, self.tp, self.rank, self.M_cap, self.N_cap, ctypes.byref(ctx)),
-                       "mmx_tp_ctx_create")
+            _lib.check(lib.mmx_tp_ctx_create_ex(arr, self.tp, self.rank, self.M_cap, self.N_cap, self.gather[0],
+                                                self.gather[1], ctypes.byref(ctx)), "mmx_tp_ctx_create_ex")
         self.ctx = ctx
         self.mode = mode if _sim is None else "push"
         if self.multicast_ptr:
@@ -168,6 +181,7 @@ class PeerWorkspace:
         mappings as the cudaIpc path PLUS an NVSwitch multicast address of the whole workspace, which lets the reducer
         write a result tile to every rank with ONE multimem.st instead of tp peer stores.  Returns the per-rank
         pointers, or None when this box / torch build has no multicast (the cudaIpc path is used then)."""
+        ptrs, buf, h, mc = None, None, None, 0
         try:
             import torch.distributed._symmetric_memory as symm
             pg = group if group is not None else dist.group.WORLD
@@ -176,31 +190,44 @@ class PeerWorkspace:
             mc = int(getattr(h, "multicast_ptr", 0) or 0)
             ptrs = [int(x) for x in h.buffer_ptrs]
             if not mc or len(ptrs) != self.tp or ptrs[self.rank] != buf.data_ptr():
-                return None
-            buf.zero_()
-            torch.cuda.synchronize(self.device)
-            self._symm_buf, self._symm_handle, self.multicast_ptr = buf, h, mc
-            return ptrs
+                ptrs = None
         except Exception:  # noqa: BLE001 -- no symmetric memory here: fall back to cudaIpc peer mappings
+            ptrs = None
+        # the ranks must AGREE on the outcome: a rank that fell back alone would run different collectives / data paths
+        ok = [None] * self.tp
+        dist.all_gather_object(ok, ptrs is not None, group=group)
+        if not all(ok):
+            del buf, h  # drop the symmetric allocation instead of leaking it next to the cudaIpc workspace
             return None
+        buf.zero_()
+        torch.cuda.synchronize(self.device)
+        self._symm_buf, self._symm_handle, self.multicast_ptr = buf, h, mc
+        return ptrs
 
     @classmethod
-    def simulate(cls, tp: int, M_cap: int, N_cap: int):
+    def simulate(cls, tp: int, M_cap: int, N_cap: int, gather=None):
         """`tp` contexts inside ONE process on the current device (each "rank" on its own stream): the same kernels
-        and protocol with local pointers instead of cudaIpc mappings.  For the single-GPU parity tests."""
+        and protocol with local pointers instead of cudaIpc mappings.  For the single-GPU parity tests.
+        gather (tp == 1 only): the gather channel with the workspace's own address standing in for the multicast mapping
+        (multimem.st to an ordinary address is an ordinary store) -- exercises the gather kernels and counters."""
         import ctypes
         from . import _lib
         lib = _lib.load()
-        nbytes = int(lib.mmx_tp_workspace_bytes(M_cap, N_cap, tp))
+        if gather and tp != 1:
+            raise ValueError("the simulated gather channel needs tp == 1 (no multicast mapping inside one process)")
+        nbytes = int(lib.mmx_tp_workspace_bytes_ex(M_cap, N_cap, tp, *(gather or (0, 0))))
         ptrs = []
         for _ in range(tp):
             p = ctypes.c_void_p()
             h = ctypes.create_string_buffer(64)
             _lib.check(lib.mmx_peer_alloc(nbytes, ctypes.byref(p), h), "mmx_peer_alloc")
             ptrs.append(p.value)
-        out = [cls(M_cap, N_cap, _sim=(tp, r, ptrs)) for r in range(tp)]
+        out = [cls(M_cap, N_cap, _sim=(tp, r, ptrs), gather=gather) for r in range(tp)]
         for r, w in enumerate(out):
             w.own = ptrs[r]
+            if gather:
+                w.multicast_ptr = ptrs[r]
+                _lib.check(lib.mmx_tp_ctx_set_multicast(w.ctx, ptrs[r], 0), "mmx_tp_ctx_set_multicast")
         return out
 
     def matmul_allreduce(self, A, W, bias=None):
@@ -218,6 +245,7 @@ class PeerWorkspace:
                                                ctypes.byref(c), torch.cuda.current_stream().cuda_stream)
         from . import _lib
         _lib.check(rc, "mmx_matmul_allreduce")
+        self._tick()
         view = self._views.get(c.value)
         if view is None:
             nbytes = self.nbytes - (c.value - self._base)
@@ -225,6 +253,103 @@ class PeerWorkspace:
             view = torch.as_tensor(_DeviceBytes(c.value, nbytes), device=self.device).view(torch.bfloat16)
             self._views[c.value] = view
         return view[: M * N].view(M, N)
+
+    # ---- sequence-parallel forms (include/micromix_b200.h: mmx_matmul_reduce_scatter, mmx_tp_quantize_allgather, ...)
+    def shard_rows(self, M: int) -> int:
+        """Rows of an [M, *] activation each rank owns: whole 256-row GEMM tiles, ceil(ceil(M/256)/tp)*256."""
+        return int(self.lib.mmx_tp_shard_rows(int(M), self.tp))
+
+    def shard_range(self, M: int) -> Tuple[int, int]:
+        per = self.shard_rows(M)
+        return min(M, per * self.rank), min(M, per * (self.rank + 1))
+
+    def _view(self, ptr: int, nbytes: int, dtype=torch.uint8):
+        key = (ptr, nbytes, dtype)
+        v = self._views.get(key)
+        if v is None:
+            v = torch.as_tensor(_DeviceBytes(ptr, nbytes, "|u1"), device=self.device)
+            if dtype != torch.uint8:
+                v = v.view(dtype)
+            self._views[key] = v
+        return v
+
+    def matmul_reduce_scatter(self, A, W, bias=None):
+        """Like matmul_allreduce, but this rank keeps only its rows: -> (bf16 [rows, N] view, row0)."""
+        ctypes = self._ctypes
+        M, N = A[0].size(0), W[0].size(0)
+        KN, KS, KO = A[0].size(1) * 2, A[1].size(1) * 4 // 3, A[2].size(1)
+        p = lambda t: t.data_ptr() if t is not None and t.numel() > 0 else None
+        c, r0, rows = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int64()
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_matmul_reduce_scatter(self.ctx, p(A[0]), p(W[0]), p(A[1]), p(W[1]), p(A[2]), p(W[2]), p(A[3]),
+                                                    p(W[3]), p(A[4]), p(W[4]), p(A[5]), p(W[5]), M, N, KN, KS, KO, 1, p(bias),
+                                                    ctypes.byref(c), ctypes.byref(r0), ctypes.byref(rows),
+                                                    torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_matmul_reduce_scatter")
+        self._tick()
+        n = int(rows.value)
+        if n == 0:
+            return torch.empty((0, N), dtype=torch.bfloat16, device=self.device), int(r0.value)
+        return self._view(c.value, n * N * 2, torch.bfloat16).view(n, N), int(r0.value)
+
+    def quantize_allgather(self, x_shard, M, reorder_index, KN, KS, KO, norm=None):
+        """Quantize THIS rank's rows (x_shard bf16 [shard rows, K]; norm = (weight, eps) fuses RMSNorm) and multicast
+        the packed codes + scales into every rank's gather channel -> the six tensors of the gathered [M, K] activation
+        (views into the workspace, valid until the next gather; consume them with matmul_gathered)."""
+        ctypes = self._ctypes
+        lo, hi = self.shard_range(M)
+        K = KN + KS + KO
+        if x_shard.dim() != 2 or x_shard.shape != (hi - lo, K) or x_shard.dtype != torch.bfloat16 or not x_shard.is_contiguous():
+            raise ValueError(f"x_shard must be contiguous bf16 [{hi - lo}, {K}] (this rank's rows {lo}:{hi} of M={M}), "
+                             f"got {tuple(x_shard.shape)} {x_shard.dtype}")
+        views = (ctypes.c_void_p * 6)()
+        nw = norm[0].data_ptr() if norm is not None else None
+        eps = float(norm[1]) if norm is not None else 0.0
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_tp_quantize_allgather(self.ctx, x_shard.data_ptr() if x_shard.numel() else reorder_index.data_ptr(),
+                                                    M, K, reorder_index.data_ptr(), KN, KS, KO, nw, eps, views,
+                                                    torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_tp_quantize_allgather")
+        widths = (KN // 2, KS // 4 * 3, KO)
+        out = []
+        for i in range(3):
+            out.append(self._view(views[i], M * widths[i]).view(M, widths[i]) if widths[i] else
+                       torch.empty((M, 0), dtype=torch.uint8, device=self.device))
+        for i, k in enumerate((KN, KS, KO)):
+            n = int(self.lib.mmx_sf_bytes_act(M, k))
+            out.append(self._view(views[3 + i], n) if n else torch.empty((0,), dtype=torch.uint8, device=self.device))
+        return tuple(out)
+
+    def matmul_gathered(self, M, W, KN, KS, KO, bias=None, out=None):
+        """The column-parallel GEMM on the gathered activation of the preceding quantize_allgather (exactly one per gather):
+        waits per source rank for that rank's rows, then tells every rank the channel is free again."""
+        N = W[0].size(0)
+        p = lambda t: t.data_ptr() if t is not None and t.numel() > 0 else None
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_tp_matmul_gathered(self.ctx, p(W[0]), p(W[1]), p(W[2]), p(W[3]), p(W[4]), p(W[5]), M, N, KN, KS,
+                                                 KO, 1, p(bias), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_tp_matmul_gathered")
+        return out
+
+    def _tick(self, every: int = 256):
+        """A lost / slow peer costs a timeout and POISONED (NaN) rows, never silently wrong activations; the error word is
+        read at a cheap cadence (never while a CUDA graph is being captured) and raises.  After an error the workspace
+        must be rebuilt: its counters are no longer consistent across the ranks."""
+        self._calls += 1
+        if self._calls % every == 0 and not torch.cuda.is_current_stream_capturing():
+            self.check()
+
+    def check(self):
+        st = self.status()
+        if st:
+            raise RuntimeError(f"fused tensor-parallel reduction: a cross-rank wait timed out (status {st:#x}: bit 0 = a "
+                               "tile never arrived, bit 1 = a peer's reducer never finished); the affected rows were "
+                               "written as NaN.  Rebuild the PeerWorkspace on every rank.")
 
     def status(self) -> int:
         w = self._ctypes.c_uint32(0)
@@ -333,6 +458,18 @@ class RowParallelQLinear(nn.Module):
             if w is not None:
                 w.wait()
         return y.reshape(bsz, q_len, -1)
+
+
+def forward_row_shard(layer: "RowParallelQLinear", x):
+    """Sequence-parallel form of RowParallelQLinear.forward: x_local [b, s, K/tp] -> (bf16 [rows, N], row0), the rows of
+    the summed output this rank owns (PeerWorkspace.shard_range) -- GEMM fused with a REDUCE-SCATTER."""
+    from . import mixedgemm
+    if layer.workspace is None:
+        raise RuntimeError("the sequence-parallel path needs a PeerWorkspace")
+    lin = layer.linear
+    x2 = x.reshape(-1, x.shape[-1]).contiguous()
+    a = mixedgemm.reorder_quantize_x(x2, lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num)
+    return layer.workspace.matmul_reduce_scatter(a, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), lin.bias)
 
 
 def init_tensor_parallel(backend: Optional[str] = None):

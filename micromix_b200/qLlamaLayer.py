@@ -14,5 +14,6 @@ from ._qdecoder import QGatedMLP as QLlamaMLP  # noqa: F401  (qLlamaLayer.py:324
 
 class QLlamaDecoderLayer(QDecoderLayer):
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
-                 workspace=None):
-        super().__init__(originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused, workspace)
+                 workspace=None, sequence_parallel=False):
+        super().__init__(originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused, workspace,
+                         sequence_parallel)

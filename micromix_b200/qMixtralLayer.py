@@ -45,19 +45,139 @@ def group_tokens_by_expert(sel: torch.Tensor, num_experts: int):
     return order, tok_sorted, counts
 
 
+def route_tables(sel: torch.Tensor, local_slot: torch.Tensor, n_local: int, tile: int):
+    """Device-side routing tables of the grouped path -- pure tensor code, NO host synchronisation.
+
+    sel int64 [T, k] expert ids; local_slot int64 [E]: position of expert e among this rank's experts, or n_local for an
+    expert that lives elsewhere.  The (token, slot) pairs of local experts are sorted by expert (stable: tokens ascending
+    inside an expert, the order torch.where gives the reference's loop) and each expert's rows are padded to whole m-tiles.
+    Returns, for the static upper bound Mp = roundup(T*k + n_local*(tile-1), tile) of padded rows:
+      row_src  int32 [Mp]      token whose activation row sits at padded row r (padding rows: token 0)
+      pair_row int32 [T, k]    padded row holding the pair's expert output, -1 = expert not on this rank
+      grp_rowblk int32 [Mp/128], grp_mtile int32 [Mp/tile]   expert slot per 128-row block / m-tile (-1 = unused m-tile)
+    """
+    T, k = sel.shape
+    dev = sel.device
+    flat = sel.reshape(-1)
+    key = local_slot[flat]                                    # [T*k], n_local = "not mine"
+    order = torch.argsort(key, stable=True)
+    ks = key[order]
+    counts = torch.bincount(key, minlength=n_local + 1)[:n_local]
+    padded = (counts + tile - 1) // tile * tile
+    ends_p = torch.cumsum(padded, 0)
+    starts_p = ends_p - padded
+    starts_u = torch.cumsum(counts, 0) - counts
+    Mp = (T * k + n_local * (tile - 1) + tile - 1) // tile * tile
+    pos = torch.arange(T * k, device=dev)
+    valid = ks < n_local
+    ksc = ks.clamp(max=n_local - 1)
+    dst = torch.where(valid, starts_p[ksc] + pos - starts_u[ksc], torch.full_like(pos, Mp))  # Mp = trash slot
+    row_src = torch.zeros(Mp + 1, dtype=torch.int32, device=dev)
+    row_src[dst] = torch.div(order, k, rounding_mode="floor").to(torch.int32)
+    pair_row = torch.full((T * k + 1,), -1, dtype=torch.int32, device=dev)
+    pair_row[torch.where(valid, order, torch.full_like(order, T * k))] = dst.to(torch.int32)
+    blk = torch.arange(Mp // 128, device=dev) * 128
+    grp_rowblk = torch.searchsorted(ends_p, blk, right=True).clamp(max=n_local - 1).to(torch.int32)
+    mt = torch.arange(Mp // tile, device=dev) * tile
+    g = torch.searchsorted(ends_p, mt, right=True)
+    grp_mtile = torch.where(g < n_local, g, torch.full_like(g, -1)).to(torch.int32)
+    return row_src[:Mp], pair_row[:T * k].view(T, k), grp_rowblk, grp_mtile, Mp
+
+
 class QMixtralSparseMoeBlock(nn.Module):
-    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False):
+    """qMixtralLayer.py:393-452.  `grouped=True` (default whenever this rank's experts share one (p4, p6, p8) per input):
+    the experts run as ONE grouped quantize + ONE grouped GEMM per projection over the expert-sorted token matrix, with the
+    gather of the routed tokens fused into the quantizer's loads and the weighted scatter-add done by one combine kernel;
+    no device->host synchronisation anywhere.  `grouped=False` is the reference's op sequence: a Python loop over experts."""
+
+    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False, grouped=None):
         super().__init__()
         self.num_experts = getattr(originalSparseMoeBlock, "num_experts", len(originalSparseMoeBlock.experts))
         self.top_k = originalSparseMoeBlock.top_k
         self.gate = originalSparseMoeBlock.gate
         self.ep_group = ep_group
         self.ep, self.rank = tp_info(ep_group)
+        self.fused = bool(fused)
+        self.local = [j for j in range(self.num_experts) if j % self.ep == self.rank]
+        key = lambda j, n: _KEY.format(i, 'block_sparse_moe', 'experts', j, n, 'input')
+        same = lambda n: all(int(p8_nums[key(j, n)]) == int(p8_nums[key(self.local[0], n)]) and
+                             int(p6_nums[key(j, n)]) == int(p6_nums[key(self.local[0], n)]) for j in self.local)
+        shared13 = all(torch.equal(reorder_index[key(j, 'w1')].cpu(), reorder_index[key(j, 'w3')].cpu()) and
+                       int(p8_nums[key(j, 'w1')]) == int(p8_nums[key(j, 'w3')]) and
+                       int(p6_nums[key(j, 'w1')]) == int(p6_nums[key(j, 'w3')]) for j in self.local)
+        can_group = bool(self.local) and shared13 and same('w1') and same('w2')
+        self.grouped = can_group if grouped is None else bool(grouped)
+        if self.grouped and not can_group:
+            raise ValueError("grouped=True needs w1/w3 to share their calibration and all local experts to share one split")
         self.experts = nn.ModuleDict()
-        for j in range(self.num_experts):
-            if j % self.ep == self.rank:
+        if not self.grouped:
+            for j in self.local:
                 self.experts[str(j)] = QMixtralBlockSparseTop2MLP(originalSparseMoeBlock.experts[j], p8_nums, p6_nums,
                                                                   reorder_index, i, j, fused=fused)
+            return
+        # ---- grouped: the experts' MXFP4 weights stacked on N, one permutation per expert
+        from . import mixedgemm
+        j0 = self.local[0]
+        e0 = originalSparseMoeBlock.experts[j0]
+        self.hidden, self.inter = e0.w1.in_features, e0.w1.out_features
+        self.s13 = (self.hidden - int(p6_nums[key(j0, 'w1')]) - int(p8_nums[key(j0, 'w1')]), int(p6_nums[key(j0, 'w1')]),
+                    int(p8_nums[key(j0, 'w1')]))
+        self.s2 = (self.inter - int(p6_nums[key(j0, 'w2')]) - int(p8_nums[key(j0, 'w2')]), int(p6_nums[key(j0, 'w2')]),
+                   int(p8_nums[key(j0, 'w2')]))
+        W13, W2, idx13, idx2 = [], [], [], []
+        for j in self.local:
+            e = originalSparseMoeBlock.experts[j]
+            i13 = reorder_index[key(j, 'w1')].to(torch.int16).cuda().contiguous()
+            i2 = reorder_index[key(j, 'w2')].to(torch.int16).cuda().contiguous()
+            w1 = e.w1.weight.data.to(device='cuda', dtype=torch.bfloat16)
+            w3 = e.w3.weight.data.to(device='cuda', dtype=torch.bfloat16)
+            w2 = e.w2.weight.data.to(device='cuda', dtype=torch.bfloat16)
+            if self.fused:
+                # w1 / w3 rows in w2's channel order: SiLU(w1 x) * w3 x is born permuted and quantized in place
+                perm = i2.to(torch.int64)
+                w1, w3 = w1[perm], w3[perm]
+                W2.append(mixedgemm.downproj_quantize_w4(w2[:, perm].contiguous(), *self.s2))
+            else:
+                W2.append(mixedgemm.reorder_quantize_w4(w2.contiguous(), i2, *self.s2))
+            W13.append(mixedgemm.reorder_quantize_w4(torch.cat([w1, w3], 0).contiguous(), i13, *self.s13))
+            idx13.append(i13)
+            idx2.append(i2)
+            del w1, w2, w3
+        n2 = self.hidden  # rows of w2
+        # (scale buffers of the row-wise quantizer are sized like activations: keep the N * K/32 bytes the GEMM reads)
+        cut = lambda t, rows, k: t[: rows * k // 32]
+        for name, Ws, rows, split in (("W13", W13, 2 * self.inter, self.s13), ("W2", W2, n2, self.s2)):
+            for c in range(3):
+                self.register_buffer(f"{name}_q{c}", torch.cat([w[c] for w in Ws], 0).contiguous(), persistent=False)
+                self.register_buffer(f"{name}_s{c}", torch.cat([cut(w[3 + c], rows, split[c]) for w in Ws], 0).contiguous(),
+                                     persistent=False)
+        self.register_buffer("idx13", torch.stack(idx13).contiguous(), persistent=False)
+        self.register_buffer("idx2", torch.stack(idx2).contiguous(), persistent=False)
+        slot = torch.full((self.num_experts,), len(self.local), dtype=torch.int64)
+        for s_, j in enumerate(self.local):
+            slot[j] = s_
+        self.register_buffer("local_slot", slot.cuda(), persistent=False)
+
+    def _w(self, name):
+        return tuple(getattr(self, f"{name}_q{c}") for c in range(3)) + tuple(getattr(self, f"{name}_s{c}") for c in range(3))
+
+    @torch.no_grad()
+    def _forward_grouped(self, x, w, sel):
+        from . import mixedgemm
+        T = x.shape[0]
+        n_local = len(self.local)
+        tile = 256 if T * self.top_k >= 256 * self.num_experts else 128
+        row_src, pair_row, grp_rowblk, grp_mtile, Mp = route_tables(sel, self.local_slot, n_local, tile)
+        a = mixedgemm.reorder_quantize_x_grouped(x, self.idx13, grp_rowblk, *self.s13, row_src=row_src, rows=Mp)
+        h = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile)          # [Mp, 2 * inter]
+        I = self.inter
+        if self.fused:
+            a2 = mixedgemm.activate_quantize_x(h[:, :I], h[:, I:], *self.s2)
+        else:
+            act = F.silu(h[:, :I]) * h[:, I:]
+            a2 = mixedgemm.reorder_quantize_x_grouped(act, self.idx2, grp_rowblk, *self.s2)
+        y = mixedgemm.matmul_grouped(a2, self._w("W2"), grp_mtile, n_local, tile)          # [Mp, hidden]
+        return mixedgemm.moe_combine(y, pair_row, sel.to(torch.int32), w.contiguous())
 
     @torch.no_grad()
     def forward(self, hidden_states):
@@ -67,6 +187,11 @@ class QMixtralSparseMoeBlock(nn.Module):
         w = F.softmax(router_logits, dim=1, dtype=torch.float)
         w, sel = torch.topk(w, self.top_k, dim=-1)
         w = (w / w.sum(dim=-1, keepdim=True)).to(x.dtype)
+        if self.grouped:
+            out = self._forward_grouped(x.contiguous(), w, sel)
+            if self.ep > 1:
+                dist.all_reduce(out, group=self.ep_group)
+            return out.view(b, s, h), router_logits
         out = torch.zeros_like(x)
         # group the (token, slot) pairs by expert ONCE: a stable sort keeps tokens ascending inside an expert (the order
         # torch.where gives the reference's loop, qMixtralLayer.py:437-450) and one host read of the counts replaces a

@@ -52,6 +52,31 @@ def test_row_shard_plan_properties():
         row_shard_plan(H.make_index(4096), 1024, 512, 64, 0)
 
 
+def test_row_shard_plan_never_demotes():
+    """the rank-local counts are rounded UP -- no globally-FP8 channel may land in a local FP6 / FP4 segment and
+    no globally-FP6 channel in the local FP4 segment, at any tp (the stock 5:2:1 split at K=4096, tp=8 has ~64 FP8
+    channels per rank: nearest-multiple rounding gave p8 = 0 there)."""
+    from micromix_b200.parallel_utils import row_shard_plan
+    for K, (p4, p6, p8) in ((4096, (2560, 1024, 512)), (14336, (8960, 3584, 1792)), (5120, (3200, 1280, 640)),
+                            (4096, (3968, 0, 128)), (4096, (3840, 128, 128))):
+        for tp in (2, 4, 8):
+            for seed in (0, 1):
+                idx = H.make_index(K, seed=seed)
+                glob = idx.to(torch.int64)
+                prec = torch.empty(K, dtype=torch.int64)  # bits each ORIGINAL channel gets in the global split
+                prec[glob[:p4]] = 4
+                prec[glob[p4:p4 + p6]] = 6
+                prec[glob[p4 + p6:]] = 8
+                for r in range(tp):
+                    k0, k1, lidx, q4, q6, q8 = row_shard_plan(idx, p6, p8, tp, r)
+                    li = lidx.to(torch.int64) + k0
+                    local_bits = torch.cat([torch.full((q4,), 4), torch.full((q6,), 6), torch.full((q8,), 8)])
+                    assert bool((local_bits >= prec[li]).all()), (K, tp, r, q4, q6, q8)
+                    # ... and the promotion stays below one 128-group per format
+                    n8, n6 = int((prec[li] == 8).sum()), int((prec[li] == 6).sum())
+                    assert q8 - n8 < 128 and q6 + q8 - (n6 + n8) < 128
+
+
 def _worker(rank, world, port, K, N, M, split, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

@@ -129,3 +129,116 @@ def test_fused_allreduce_multiprocess(cuda, mode):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert f'"mode": "{mode}"' in r.stdout and '"bit_exact_all_ranks": true' in r.stdout
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+@pytest.mark.parametrize("tp,M,N,K", [(2, 300, 512, 1024), (2, 1024, 1024, 1024), (4, 1000, 1152, 2048), (8, 2100, 768, 4096),
+                                      (2, 128, 256, 512)])
+def test_fused_reduce_scatter_matches_rows_of_the_sum(cuda, mmx_lib, tp, M, N, K):
+    """mmx_matmul_reduce_scatter (push data path, simulated ranks): rank r must hold exactly the rows
+    [r * shard, (r+1) * shard) of bf16(sum in fp32, rank order) of the partials -- the same bits the all-reduce gives."""
+    from micromix_b200.parallel_utils import PeerWorkspace
+    mmx_lib.mmx_set_option(b"tp_reduce_ctas", 8)
+    mmx_lib.mmx_set_option(b"tp_timeout_ms", 4000)
+    try:
+        shards = _shards(tp, M, N, K, seed=tp + 40)
+        want = _expected(shards)
+        works = PeerWorkspace.simulate(tp, M, N)
+        streams = [torch.cuda.Stream() for _ in range(tp)]
+        torch.cuda.synchronize()
+        per = works[0].shard_rows(M)
+        assert per % 256 == 0 and per * tp >= M
+        for call in range(3):
+            ys = []
+            for r in range(tp):
+                with torch.cuda.stream(streams[r]):
+                    ys.append(works[r].matmul_reduce_scatter(*shards[r]))
+            torch.cuda.synchronize()
+            seen = 0
+            for r in range(tp):
+                y, row0 = ys[r]
+                assert works[r].status() == 0, f"rank {r}: cross-rank wait timed out (call {call})"
+                lo, hi = min(M, per * r), min(M, per * (r + 1))
+                assert row0 == lo and y.shape == (hi - lo, N)
+                assert torch.equal(y, want[lo:hi]), f"rank {r} call {call}: shard differs from the rows of the sum"
+                seen += hi - lo
+            assert seen == M
+        for w in works:
+            w.close()
+    finally:
+        mmx_lib.mmx_set_option(b"tp_reduce_ctas", 0)
+        mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)
+
+
+def test_fused_allreduce_back_to_back_small(cuda, mmx_lib):
+    """many decode-sized fused calls back to back with NOTHING between them (the grids of several calls fit
+    on the GPU at once), odd call counts, all-reduce and reduce-scatter interleaved: the reducer releases its dependents
+    only at its end and `done` is a monotonic counter, so no call can see another call's counters."""
+    from micromix_b200.parallel_utils import PeerWorkspace
+    mmx_lib.mmx_set_option(b"tp_reduce_ctas", 4)
+    mmx_lib.mmx_set_option(b"tp_timeout_ms", 4000)
+    try:
+        tp = 2
+        sa = _shards(tp, 16, 256, 512, seed=31)
+        sb = _shards(tp, 96, 512, 512, seed=32)
+        wa, wb = _expected(sa), _expected(sb)
+        works = PeerWorkspace.simulate(tp, 128, 512)
+        streams = [torch.cuda.Stream() for _ in range(tp)]
+        torch.cuda.synchronize()
+        plan = [("a", 0), ("a", 0), ("b", 1), ("a", 0), ("b", 0), ("b", 1), ("a", 1)] * 3  # (shape, reduce-scatter?)
+        outs = [[] for _ in range(tp)]
+        for r in range(tp):
+            with torch.cuda.stream(streams[r]):
+                for which, rs in plan:
+                    sh = sa if which == "a" else sb
+                    if rs:
+                        y, row0 = works[r].matmul_reduce_scatter(*sh[r])
+                        outs[r].append((which, rs, y.clone(), row0))
+                    else:
+                        outs[r].append((which, rs, works[r].matmul_allreduce(*sh[r]).clone(), 0))
+        torch.cuda.synchronize()
+        for r in range(tp):
+            assert works[r].status() == 0
+            for i, (which, rs, y, row0) in enumerate(outs[r]):
+                want = wa if which == "a" else wb
+                ref = want[row0:row0 + y.shape[0]] if rs else want
+                assert torch.equal(y, ref), f"rank {r} call {i} ({which}, rs={rs})"
+        for w in works:
+            w.close()
+    finally:
+        mmx_lib.mmx_set_option(b"tp_reduce_ctas", 0)
+        mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)
+
+
+@pytest.mark.parametrize("M,K,norm", [(512, 1024, False), (300, 2048, False), (1024, 4096, True), (256, 5120, True)])
+def test_gather_channel_single_rank(cuda, mmx_lib, M, K, norm):
+    """The sequence-parallel hand-over at tp = 1 (the workspace's own address stands in for the multicast mapping): the
+    multicast-store quantizer must write exactly the bytes of mmx_reorder_quantize_x / mmx_rmsnorm_quantize_x into the gather
+    channel, and the gathered GEMM must equal mmx_matmul on them -- three rounds, so the channel's counters are re-used."""
+    from micromix_b200 import mixedgemm
+    from micromix_b200.parallel_utils import PeerWorkspace
+    N = 512
+    split = (K // 2, K // 4, K // 4)
+    idx = H.make_index(K, seed=5).to(cuda)
+    w = H.make_weights(N, K).to(cuda)
+    W = mixedgemm.reorder_quantize_w4(w, idx, *split)
+    nw = (1.0 + 0.1 * torch.randn(K, device=cuda)).to(torch.bfloat16)
+    ws = PeerWorkspace.simulate(1, M, N, gather=(M, K))[0]
+    try:
+        for rnd in range(3):
+            x = H.make_activations(M, K, idx.cpu(), seed=100 + rnd).to(cuda)
+            if norm:
+                ref = mixedgemm.rmsnorm_quantize_x(x, nw, 1e-5, idx, *split)
+            else:
+                ref = mixedgemm.reorder_quantize_x(x, idx, *split)
+            got = ws.quantize_allgather(x, M, idx, *split, norm=(nw, 1e-5) if norm else None)
+            y = ws.matmul_gathered(M, W, *split)
+            torch.cuda.synchronize()
+            for i in range(3):
+                assert torch.equal(got[i], ref[i]), f"codes of segment {i} (round {rnd})"
+                m = torch.from_numpy(H.O.sf_valid_mask(M, split[i], ref[3 + i].numel())).to(cuda)
+                assert torch.equal(got[3 + i][: ref[3 + i].numel()][m], ref[3 + i][m]), f"scales of segment {i} (round {rnd})"
+            want = mixedgemm.matmul(ref[0], W[0], ref[1], W[1], ref[2], W[2], ref[3], W[3], ref[4], W[4], ref[5], W[5])
+            assert torch.equal(y, want), f"gathered GEMM differs (round {rnd})"
+    finally:
+        ws.close()
