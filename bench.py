@@ -179,6 +179,9 @@ def workload_config(args, world):
             "tokens": args.tokens, "split_4096": list(split_for(4096)), "split_14336": list(split_for(14336)),
             "parallelism": f"tp{world}" if world > 1 else "single",
             "tp_reduce": (args.tp_reduce if world > 1 and args.impl == "ours" else None),
+            "reference_arm_sample": (f"{args.cpu_tokens} of {args.tokens} tokens per step, {args.steps_ref} timed steps "
+                                     "(a bounded CPU sample: same_steps is false by design)"
+                                     if args.impl == "reference" else None),
             "tp_chunks": (args.tp_chunks if world > 1 and args.impl == "ours" else None),
             "l2": "inputs+weights+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
@@ -229,6 +232,8 @@ class HotLinear:
         self.out = torch.empty((M, self.N), dtype=torch.bfloat16, device=dev)
         self.flops = 2.0 * M * self.N * self.K
         self.qbytes = 2.0 * M * self.K + M * (p4 / 2 + p6 * 3 / 4 + p8) + M * self.K / 32
+        # GEMM: packed A + scales, MXFP4 B + scales, bf16 C -- each touched once
+        self.gbytes = M * (p4 / 2 + p6 * 3 / 4 + p8) + M * self.K / 32 + self.N * self.K / 2 + self.N * self.K / 32 + 2.0 * M * self.N
         p = lambda t: t.data_ptr() if t.numel() else None
         self._qargs = (p(self.x), M, self.K, p(self.idx), p4, p6, p8, p(self.A[0]), p(self.A[1]), p(self.A[2]),
                        p(self.SFA[0]), p(self.SFA[1]), p(self.SFA[2]))
@@ -236,22 +241,65 @@ class HotLinear:
         self._margs = (p(self.A[0]), p(W[0]), p(self.A[1]), p(W[1]), p(self.A[2]), p(W[2]), p(self.SFA[0]), p(W[3]),
                        p(self.SFA[1]), p(W[4]), p(self.SFA[2]), p(W[5]), M, self.N, p4, p6, p8, 1, None, p(self.out))
 
+    def enable_sp(self, ws):
+        """Sequence-parallel step (tp_mode "sp"): a column-parallel linear quantizes only THIS rank's rows of X and
+        multicasts the packed codes into every rank's gather channel (its GEMM waits per source rank); a row-parallel
+        linear ends in a reduce-scatter (this rank keeps its rows of the sum)."""
+        self.sp_ws = ws
+        p4, p6, p8 = self.split
+        if self.mode == "col":
+            lo, hi = ws.shard_range(self.M)
+            self.x_shard = self.x[lo:hi].contiguous()
+            self._views = (ctypes.c_void_p * 6)()
+            pq = lambda t: t.data_ptr() if t.numel() else self.idx.data_ptr()
+            self._gargs = (ws.ctx, pq(self.x_shard), self.M, self.K, self.idx.data_ptr(), p4, p6, p8, None, 0.0, self._views)
+            p = lambda t: t.data_ptr() if t.numel() else None
+            W = self.W
+            self._mgargs = (ws.ctx, p(W[0]), p(W[1]), p(W[2]), p(W[3]), p(W[4]), p(W[5]), self.M, self.N, p4, p6, p8, 1,
+                            None, self.out.data_ptr())
+        else:
+            self._row0, self._rows = ctypes.c_int64(), ctypes.c_int64()
+
     def run(self, stream, events=None):
         """quantize + GEMM of this rank's shard (fused mode: + the reduction, inside the GEMM launch pair)."""
+        lib = self.lib
         if events is not None:
             events[0].record()
-        rc = self.lib.mmx_reorder_quantize_x(*self._qargs, stream)
-        if events is not None:
-            events[1].record()
-        if self.ws is not None:
-            # fused: GEMM epilogue pushes partial tiles to their owner rank over NVLink, co-resident reducer kernel
-            rc |= self.lib.mmx_matmul_allreduce(self.ws.ctx, *self._margs[:-1], ctypes.byref(self._c_out), stream)
+        sp = getattr(self, "sp_ws", None)
+        if sp is not None and self.mode == "col":
+            rc = lib.mmx_tp_quantize_allgather(*self._gargs, stream)
+            if events is not None:
+                events[1].record()
+            rc |= lib.mmx_tp_matmul_gathered(*self._mgargs, stream)
         else:
-            rc |= self.lib.mmx_matmul(*self._margs, stream)
+            rc = lib.mmx_reorder_quantize_x(*self._qargs, stream)
+            if events is not None:
+                events[1].record()
+            if sp is not None:
+                rc |= lib.mmx_matmul_reduce_scatter(sp.ctx, *self._margs[:-1], ctypes.byref(self._c_out),
+                                                    ctypes.byref(self._row0), ctypes.byref(self._rows), stream)
+            elif self.ws is not None:
+                # fused: GEMM epilogue pushes partial tiles to their owner rank over NVLink, co-resident reducer kernel
+                rc |= lib.mmx_matmul_allreduce(self.ws.ctx, *self._margs[:-1], ctypes.byref(self._c_out), stream)
+            else:
+                rc |= lib.mmx_matmul(*self._margs, stream)
         if events is not None:
             events[2].record()
         if rc:
-            raise RuntimeError(self.lib.mmx_last_error().decode())
+            raise RuntimeError(lib.mmx_last_error().decode())
+
+    def result(self):
+        """The linear's output as this rank holds it after run(): (tensor, row0) -- row-parallel fused outputs live in
+        the peer workspace (all rows, or this rank's rows under sequence parallelism)."""
+        import torch
+        from micromix_b200.parallel_utils import _DeviceBytes
+        sp = getattr(self, "sp_ws", None)
+        if self.mode == "row" and (sp is not None or self.ws is not None):
+            rows = int(self._rows.value) if sp is not None else self.M
+            row0 = int(self._row0.value) if sp is not None else 0
+            t = torch.as_tensor(_DeviceBytes(self._c_out.value, rows * self.N * 2, "|u1"), device=self.out.device)
+            return t.view(torch.bfloat16).view(rows, self.N), row0
+        return self.out, 0
 
     def reduce_async(self):
         """Row-parallel partial sum over the ranks: NCCL all-reduce on NCCL's own stream (returns the Work to wait on
@@ -282,19 +330,35 @@ def run_ours(args, rank, world, local_rank):
         C = 1
     Mc = M // C
     ws, ws_note = None, None
+    tp_mode = "none"
     if world > 1 and args.tp_reduce == "fused":
         from micromix_b200.parallel_utils import PeerWorkspace
+        n_row = max(N for _, N, _, mode in LINEARS if mode == "row")
+        k_col = max(K for _, _, K, mode in LINEARS if mode == "col")
+        want_sp = args.tp_mode in ("auto", "sp") and C == 1
         try:
-            ws = PeerWorkspace(Mc, max(N for _, N, _, mode in LINEARS if mode == "row"), device=dev)
-        except Exception as e:  # noqa: BLE001 -- no peer mapping on this box: every rank must agree on the fallback
-            ws_note = f"peer workspace unavailable ({e!r})"[:200]
+            # sequence parallel needs the NVSwitch multicast mapping (gather channel); the constructor is collective and
+            # raises on EVERY rank when any rank cannot map it
+            ws = PeerWorkspace(Mc, n_row, device=dev, gather=(Mc, k_col) if want_sp else None)
+            tp_mode = "sp" if want_sp else "ar"
+        except Exception as e:  # noqa: BLE001
+            ws_note = f"sequence-parallel workspace unavailable ({e!r})"[:200]
+            if args.tp_mode == "sp":
+                raise
+            try:
+                ws = PeerWorkspace(Mc, n_row, device=dev)
+                tp_mode = "ar"
+            except Exception as e2:  # noqa: BLE001 -- no peer mapping on this box: every rank must agree on the fallback
+                ws_note = f"peer workspace unavailable ({e2!r})"[:200]
         ok = torch.tensor([1 if ws is not None else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if not int(ok.item()):
             if ws is not None:
                 ws.close()
-            ws, args.tp_reduce = None, "nccl"
+            ws, args.tp_reduce, tp_mode = None, "nccl", "ar"
             ws_note = ws_note or "peer workspace unavailable on another rank"
+    elif world > 1:
+        tp_mode = "ar"
     if world > 1 and args.gemm_ctas > 0:
         lib.mmx_set_option(b"gemm_ctas", args.gemm_ctas)  # leave SMs to the concurrent NCCL kernel
     chunks = []
@@ -303,7 +367,11 @@ def run_ours(args, rank, world, local_rank):
                                  share=(chunks[0][i] if c else None), chunk=c)
                        for i, (n, N, K, mode) in enumerate(LINEARS)])
     lins = chunks[0]
+    if tp_mode == "sp":
+        for l in lins:
+            l.enable_sp(ws)
     total_flops = M * flops_per_token()  # whole job, all ranks together
+    mx_peak = measure_mx_peak(lib)
 
     def barrier():
         if world > 1:
@@ -336,6 +404,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         issue_step()
     barrier()
+    tp_parity = check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev) if world > 1 else None
     # N > 1: the step is replayed from a CUDA graph (8C kernels + 2C NCCL all-reduces per replay) -- at tp=8 the
     # kernels are 10-70 us each and eager launches from 8 Python processes would bound the step
     graph, graph_note = None, None
@@ -408,19 +477,48 @@ def run_ours(args, rank, world, local_rank):
     g_pure_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells if li in pure)
     pure_flops = C * sum(lins[li].flops for li in pure)
     gemm_tflops = pure_flops * n_ev / g_pure_ms / 1e9
-    # split-weighted tensor peak: FP4xFP4 at 4x, the FP6/FP8 segments at 2x the MEASURED dense bf16 rate
-    p_bf16 = peaks["bf16_tflops"]
-    tmin = sum(2.0 * M * lins[li].N * (lins[li].split[0] / (4 * p_bf16) + (lins[li].split[1] + lins[li].split[2]) / (2 * p_bf16))
-               for li in pure)  # C chunks of M/C
+    # split-weighted tensor peak from the MEASURED MX issue rates of this GPU (mmx_debug_mma_peak): the FP4 segment runs as
+    # kind::mxf4, the FP6 / FP8 segments as kind::mxf8f6f4.  The GEMMs are timed inside a long step -> sustained figures.
+    sus = tuple(mx_peak[f"{n}_sustained_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
+    bur = tuple(mx_peak[f"{n}_burst_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
+
+    def tmin_of(l, a):
+        return 2.0 * l.M * l.N * (l.split[0] / a[0] + l.split[1] / a[1] + l.split[2] / a[2])
+
+    tmin = C * sum(tmin_of(lins[li], sus) for li in pure)
     peak_eff = pure_flops / tmin  # TFLOP/s
+    peak_burst = pure_flops / (C * sum(tmin_of(lins[li], bur) for li in pure))
+    p_bf16 = peaks["bf16_tflops"]
+    peak_proxy = pure_flops / (C * sum(tmin_of(lins[li], (4 * p_bf16, 2 * p_bf16, 2 * p_bf16)) for li in pure))
+    for li in pure:
+        l = lins[li]
+        per_lin[l.name]["gemm_roofline_frac"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, sus))
+        per_lin[l.name]["gemm_roofline_frac_vs_burst_peak"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, bur))
+    for l in lins:
+        per_lin[l.name]["quant_roofline_frac"] = per_lin[l.name]["quant_gbs"] / peaks["hbm_gbs"]
     quant_gbs = C * sum(l.qbytes for l in lins) * n_ev / q_ms / 1e6
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-    if os.path.exists(prof):
+    # DRAM bytes per launch from the ncu --set full capture of this same command (profiles/, tools/ncu_traffic.py), next to
+    # the algorithmic bytes of each launch; N = 1 only (the capture is a one-GPU run)
+    traffic = traffic_q = None
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if world == 1 and os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            for l in lins:
+                g = tj.get("gemm", {}).get(l.name)
+                if g:
+                    per_lin[l.name]["gemm_dram_bytes"] = g["dram_bytes"]
+                    per_lin[l.name]["gemm_algorithmic_bytes"] = l.gbytes
+                qd = tj.get("quantize", {}).get(l.name)
+                if qd:
+                    per_lin[l.name]["quant_dram_bytes"] = qd["dram_bytes"]
+                    per_lin[l.name]["quant_algorithmic_bytes"] = l.qbytes
+            if all("gemm_dram_bytes" in per_lin[l.name] for l in lins):
+                traffic = sum(per_lin[l.name]["gemm_dram_bytes"] for l in lins)
+            if all("quant_dram_bytes" in per_lin[l.name] for l in lins):
+                traffic_q = sum(per_lin[l.name]["quant_dram_bytes"] for l in lins)
         except Exception:
-            traffic = None
+            traffic = traffic_q = None
 
     # ---- e2e: the plugin call a user makes (QLinearLayer.forward) with HOST buffers, copies inside the timed region
     e2e = None if args.no_e2e else measure_e2e(args, rank, world, dev, chunks, total_flops)
@@ -439,18 +537,56 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks,
             "roofline": {"kernel": "mixed_gemm_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_eff,
                          "unit": "TFLOP/s", "frac": gemm_tflops / peak_eff, "traffic": traffic,
+                         "traffic_note": "DRAM bytes of the step's GEMM launches (sum; per launch under per_linear) from the "
+                                         "ncu capture in profiles/r02_traffic.json" if traffic else None,
+                         "algorithmic_bytes": sum(l.gbytes for l in lins) if traffic else None,
                          "launches_counted": [lins[li].name for li in pure],
-                         "peak_note": f"split-weighted: 4x (kind::mxf4) and 2x (kind::mxf8f6f4) the {peaks['source']} "
-                                      f"dense bf16 burst peak {p_bf16} TFLOP/s"},
+                         "frac_vs_burst_peak": gemm_tflops / peak_burst, "frac_vs_bf16_proxy": gemm_tflops / peak_proxy,
+                         "mx_peak_measured": mx_peak,
+                         "peak_note": "split-weighted over the linears' (p4, p6, p8) from the MEASURED sustained issue rates "
+                                      "of kind::mxf4 / kind::mxf8f6f4 (E3M2, E4M3) on this GPU (mmx_debug_mma_peak: 0.45 s of "
+                                      "back-to-back MMAs on smem-resident operands, power-capped clocks; the same probe as a "
+                                      f"0.5 ms burst gives {peak_burst:.0f}); the round-1 proxy (4x / 2x the "
+                                      f"{peaks['source']} cuBLAS bf16 burst {p_bf16}) would give {peak_proxy:.0f} TFLOP/s"},
             "roofline_quantize": {"kernel": "reorder_quantize_kernel", "bound": "hbm", "achieved": quant_gbs,
                                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": quant_gbs / peaks["hbm_gbs"],
-                                  "traffic": None, "peak_note": f"{peaks['source']} copy bandwidth"},
+                                  "traffic": traffic_q,
+                                  "algorithmic_bytes": sum(l.qbytes for l in lins) if traffic_q else None,
+                                  "peak_note": f"{peaks['source']} copy bandwidth"},
             "share": {"gemm": g_ms / ms_total if world == 1 else None, "quantize": q_ms / ms_total if world == 1 else None},
             "per_linear": per_lin}
     if tp_status is not None:
         line["tp_fused_status"] = tp_status
+    if tp_parity is not None:
+        line["tp_parity"] = tp_parity
     if world > 1:
-        line["tp"] = {"reduce": args.tp_reduce, "fused_mode": ws_mode, "fallback_note": ws_note,
+        # what the row-parallel collectives put on NVLink, per rank and call, against the measured peer-copy rate
+        wire = {}
+        for l in lins:
+            if l.mode != "row":
+                continue
+            full = l.M * l.N * 2.0
+            if tp_mode == "sp":
+                egress = full * (world - 1) / world  # partial rows pulled by / pushed to their owners
+                note = "reduce-scatter: (tp-1)/tp of the bf16 partial leaves each rank, 1/tp of the sum comes back"
+            elif ws is not None and ws.mode == "switch":
+                egress = full * (world - 1) / world + full / world
+                note = "in-switch all-reduce: partials out + own result tiles multicast"
+            else:
+                egress = 2.0 * full * (world - 1) / world
+                note = "all-reduce: partials to owners + results to every rank"
+            us = per_lin[l.name]["gemm_us"]
+            wire[l.name] = {"egress_bytes_per_rank": egress, "gemm_plus_collective_us": us,
+                            "egress_gbs_over_that_interval": egress / us / 1e3, "note": note}
+        line["tp_wire"] = {"per_linear": wire, "peer_copy_peak_gbs": 770.0,
+                           "peak_note": "measured peer copy per direction on this pool (B200_PROFILING.md); round 1 "
+                                        "measured 744 GB/s (profiles/r01_nvlink_p2p_bw.log)"}
+    if world > 1:
+        line["tp"] = {"reduce": args.tp_reduce, "mode": tp_mode, "fused_mode": ws_mode, "fallback_note": ws_note,
+                      "mode_note": {"sp": "sequence parallel: row-parallel GEMMs end in a reduce-scatter, column-parallel "
+                                          "GEMMs start from an NVSwitch-multicast all-gather of the packed MX codes that each "
+                                          "rank quantized for ITS rows", "ar": "row-parallel GEMM -> all-reduce, every rank "
+                                          "quantizes the replicated activation"}.get(tp_mode),
                       "chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
                       "gemm_ctas": args.gemm_ctas or None,
                       "per_kernel_times": "eager evented pass after the timed region" if graph is not None
@@ -459,6 +595,91 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline(args)
     if rank == 0:
         emit(line)
+
+
+def measure_mx_peak(lib):
+    """The MEASURED dense MX tensor-pipe peak of this GPU (mmx_debug_mma_peak: every SM issues back-to-back block-scaled
+    tcgen05 MMAs on shared-memory-resident operands): burst = a ~0.5 ms kernel, sustained = a ~5 ms kernel under the power
+    cap.  kind::mxf4 carries the FP4 segment, kind::mxf8f6f4 the FP6 and FP8 segments (same rate for both)."""
+    out = {}
+    for name, kind in (("mxf4", 0), ("mxf6", 1), ("mxf8", 2)):
+        # burst: best of 3 kernels of ~0.5 ms; sustained: 40 back-to-back kernels of ~11 ms (~0.45 s, power-capped clocks)
+        for tag, stages, reps in (("burst", 2000, 3), ("sustained", 40000, -40)):
+            t, ms = ctypes.c_double(), ctypes.c_double()
+            rc = lib.mmx_debug_mma_peak(kind, stages, 0, reps, ctypes.byref(t), ctypes.byref(ms))
+            if rc:
+                raise RuntimeError(lib.mmx_last_error().decode())
+            out[f"{name}_{tag}_tflops"] = t.value
+    return out
+
+
+def _bf16_ulps(a, b):
+    """Largest distance in bf16 rounding steps between two bf16 tensors (ordered-integer view of the bit patterns)."""
+    import torch
+    ka, kb = a.contiguous().view(torch.int16).to(torch.int32), b.contiguous().view(torch.int16).to(torch.int32)
+    ka = torch.where(ka < 0, -32768 - ka, ka)
+    kb = torch.where(kb < 0, -32768 - kb, kb)
+    return int((ka - kb).abs().max().item()) if ka.numel() else 0
+
+
+def check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev):
+    """Real-rank parity of every tensor-parallel linear, BEFORE the timed region (the driver's scaling run must
+    carry it).  Column-parallel: the product path (sequence parallel: rows quantized by their owner rank, packed codes
+    multicast, gathered GEMM) must equal mmx_reorder_quantize_x + mmx_matmul on the full activation of THIS rank bit for
+    bit.  Row-parallel: the fused GEMM -> all-reduce / reduce-scatter must equal bf16(sum over ranks, fp32, rank order) of
+    the ranks' mmx_matmul partials -- exactly on the push data path, within one bf16 rounding step on the in-switch path
+    (the NVSwitch fixes the summation order) -- and is also compared with mmx_matmul + ncclAllReduce."""
+    import torch
+    import torch.distributed as dist
+    from micromix_b200 import mixedgemm
+    stream = torch.cuda.current_stream().cuda_stream
+    exact_expected = ws is None or ws.mode == "push"
+    out = {"mode": tp_mode, "data_path": (ws.mode if ws is not None else "nccl"), "linears": {}}
+    ok_all = True
+    for l in lins:
+        l.run(stream)
+        torch.cuda.synchronize()
+        got, row0 = l.result()
+        got = got.clone()
+        a = mixedgemm.reorder_quantize_x(l.x, l.idx, *l.split)
+        W = l.W
+        part = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5])
+        if l.mode == "col":
+            ulps = _bf16_ulps(got, part)
+            ok = ulps == 0
+            rec = {"kind": "column-parallel", "rows": got.shape[0], "max_bf16_steps_vs_local_quantize+matmul": ulps}
+        else:
+            parts = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(parts, part)
+            acc = parts[0].float()
+            for q in parts[1:]:
+                acc += q.float()
+            ref = acc.to(torch.bfloat16)
+            del parts, acc
+            nccl = part.clone()
+            dist.all_reduce(nccl)
+            rows = got.shape[0]
+            ulps = _bf16_ulps(got, ref[row0:row0 + rows])
+            ulps_nccl = _bf16_ulps(got, nccl[row0:row0 + rows])
+            ok = ulps == 0 if exact_expected else ulps <= 1
+            rec = {"kind": "row-parallel", "rows": [row0, row0 + rows], "max_bf16_steps_vs_fp32_rank_order_sum": ulps,
+                   "max_bf16_steps_vs_matmul+ncclAllReduce": ulps_nccl, "bound": 0 if exact_expected else 1}
+            if tp_mode != "sp":  # all-reduce: every rank must hold the same bits
+                h = got.view(torch.int16).to(torch.int64).sum().reshape(1)
+                hs = [torch.empty_like(h) for _ in range(world)]
+                dist.all_gather(hs, h)
+                rec["identical_on_all_ranks"] = all(int(x.item()) == int(h.item()) for x in hs)
+                ok = ok and rec["identical_on_all_ranks"]
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        worst = torch.tensor([ulps], device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        rec["ok_on_all_ranks"] = bool(int(flag.item()))
+        rec["worst_rank_bf16_steps"] = int(worst.item())
+        ok_all = ok_all and rec["ok_on_all_ranks"]
+        out["linears"][l.name] = rec
+    out["ok"] = ok_all
+    return out
 
 
 def measure_e2e(args, rank, world, dev, chunks, total_flops):
@@ -478,10 +699,20 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
         q.register_buffer("reorder_index", l.idx, persistent=False)
         q.BN, q.BS, q.BO, q.SFBN, q.SFBS, q.SFBO = l.W
         layers.append(q)
-        xin.append(l.x.cpu().pin_memory())
-        # a row-parallel result is replicated on every rank after the reduction: each rank returns its 1/N of the rows
-        # (the host holds the whole result once); a column-parallel shard is returned whole
-        r0, r1 = (l.M * rank // world, l.M * (rank + 1) // world) if (world > 1 and l.mode == "row") else (0, l.M)
+        sp = getattr(l, "sp_ws", None)
+        if sp is not None and l.mode == "col":
+            # sequence parallel: a rank uploads only ITS rows of the replicated activation (the packed codes of the other
+            # rows arrive over NVLink) -- every activation byte crosses PCIe once per box, not once per rank
+            lo, hi = sp.shard_range(l.M)
+            xin.append(l.x[lo:hi].cpu().pin_memory())
+        else:
+            xin.append(l.x.cpu().pin_memory())
+        # a row-parallel result: each rank returns its 1/N of the rows (sequence parallel: exactly the rows it owns; all-
+        # reduce: the result is replicated and the host needs it once); a column-parallel shard is returned whole
+        if sp is not None and l.mode == "row":
+            r0, r1 = sp.shard_range(l.M)
+        else:
+            r0, r1 = (l.M * rank // world, l.M * (rank + 1) // world) if (world > 1 and l.mode == "row") else (0, l.M)
         yrows.append((r0, r1))
         yout.append(torch.empty((r1 - r0, l.N), dtype=torch.bfloat16).pin_memory())
     h2d = sum(x.numel() * 2 for x in xin)
@@ -499,7 +730,15 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
                 e_in.record(s_in)
             s_run.wait_event(e_in)
             with torch.cuda.stream(s_run):
-                if l.ws is not None:
+                sp = getattr(l, "sp_ws", None)
+                if sp is not None and l.mode == "col":
+                    sp.quantize_allgather(xd, l.M, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
+                    yd = sp.matmul_gathered(l.M, l.W, q.p4_num, q.p6_num, q.p8_num)
+                elif sp is not None:
+                    a = mixedgemm.reorder_quantize_x(xd, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
+                    yd, _ = sp.matmul_reduce_scatter(a, l.W)
+                    r0, r1 = 0, yd.shape[0]  # already this rank's rows
+                elif l.ws is not None:
                     a = mixedgemm.reorder_quantize_x(xd, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
                     yd = l.ws.matmul_allreduce(a, l.W)
                 else:
@@ -510,7 +749,7 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
                 e_run.record(s_run)
             s_out.wait_event(e_run)
             with torch.cuda.stream(s_out):
-                y.copy_(yd.view(l.M, -1)[r0:r1], non_blocking=True)
+                y.copy_(yd.reshape(-1, l.N)[r0:r1], non_blocking=True)
             keep.append((xd, yd))  # alive until the step's synchronize: no cross-stream reuse by the allocator
         torch.cuda.synchronize()
 
@@ -553,6 +792,9 @@ def main():
     ap.add_argument("--gemm-ctas", type=int, default=0, help="N>1: cap the persistent GEMM grid (SMs left to NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
+    ap.add_argument("--tp-mode", default="auto", choices=["auto", "sp", "ar"],
+                    help="N>1, fused reduction: sp = sequence parallel (reduce-scatter + all-gather of packed codes through "
+                         "NVSwitch multicast; the default when the box offers multicast memory), ar = all-reduce")
     ap.add_argument("--tp-reduce", default="fused", choices=["nccl", "fused"],
                     help="row-parallel reduction at N>1: our GEMM->all-reduce over NVLink peer / NVSwitch multicast memory "
                          "(default; falls back to NCCL, and says so, if the peer workspace cannot be mapped), or mmx_matmul "

@@ -252,7 +252,8 @@ int mmx_matmul_grouped(const uint8_t* an, const uint8_t* bn, const uint8_t* as, 
 
 /* Tensor-pipe peak probe (measurement tool behind bench.py's roofline denominator): every SM issues `stages` x 4
  * back-to-back block-scaled MMAs (M=128, N=256) on shared-memory-resident operands; kind 0 = kind::mxf4 (K=64),
- * 1 = kind::mxf8f6f4 E3M2 x E2M1, 2 = kind::mxf8f6f4 E4M3 x E2M1 (K=32).  Best of `reps`; synchronises the device. */
+ * 1 = kind::mxf8f6f4 E3M2 x E2M1, 2 = kind::mxf8f6f4 E4M3 x E2M1 (K=32).  reps > 0: best of `reps` launches (burst);
+ * reps < 0: -reps launches back to back timed as one interval (sustained, under the power cap).  Synchronises the device. */
 int mmx_debug_mma_peak(int kind, int stages, int sf_copies, int reps, double* tflops, double* ms);
 
 /* Number of kernels launched by this library since load (bench.py's gpu_launches counter). */

@@ -1570,7 +1570,7 @@ __global__ void __launch_bounds__(128, 1) mma_peak_kernel(int kind, int stages, 
 extern "C" __attribute__((visibility("default"))) int mmx_debug_mma_peak(int kind, int stages, int sf_copies, int reps,
                                                                       double* tflops, double* ms_out) {
   using namespace mmx;
-  if (kind < 0 || kind > 2 || stages <= 0 || reps <= 0 || !tflops) {
+  if (kind < 0 || kind > 2 || stages <= 0 || reps == 0 || !tflops) {
     set_error("mmx_debug_mma_peak: bad arguments");
     return MMX_ERR_INVALID;
   }
@@ -1587,6 +1587,23 @@ extern "C" __attribute__((visibility("default"))) int mmx_debug_mma_peak(int kin
   const int grid = sm_count();
   mma_peak_kernel<<<grid, 128, smem>>>(kind, 64, sf_copies, idesc);  // warm-up
   float best = 1e30f;
+  if (reps < 0) {
+    // SUSTAINED: -reps launches back to back, timed as ONE interval (pick stages x launches >= ~0.5 s so that the power
+    // management has settled: a single 10 ms kernel still runs at the boost clock)
+    cudaEventRecord(e0);
+    for (int r = 0; r < -reps; ++r) mma_peak_kernel<<<grid, 128, smem>>>(kind, stages, sf_copies, idesc);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) return cuda_fail(e, "mma_peak_kernel");
+    const double k_per = kind == 0 ? 64.0 : 32.0;
+    *tflops = 2.0 * BM * BN * k_per * 4.0 * stages * grid * (double)(-reps) / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return MMX_OK;
+  }
   for (int r = 0; r < reps; ++r) {
     cudaEventRecord(e0);
     mma_peak_kernel<<<grid, 128, smem>>>(kind, stages, sf_copies, idesc);

@@ -194,18 +194,29 @@ __device__ __forceinline__ void convert_store(const uint32_t (&g)[16][R / 2], co
                                               int64_t row_stride, int nstore) {
 #pragma unroll
   for (int k = 0; k < R / 2; ++k) {
-    uint32_t h[16];
-    const __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&mult[k]);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&g[c][k]), m2);
-      h[c] = *reinterpret_cast<const uint32_t*>(&v);
-    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
+      // x * 2^-e straight into fp32: ONE mixed-precision FMA per element (FHFMA.BF16 with a half selector on both packed
+      // operands) replaces the bf16x2 multiply + the unpack of its halves.  The product of a bf16 and a power of two is
+      // exact in fp32; the addend is -0.0 so that a -0.0 input keeps its sign bit (reorder.cu gives -0 a sign-bit code).
       float f[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(half ? (h[c] & 0xffff0000u) : (h[c] << 16));
+      for (int c = 0; c < 16; ++c) {
+        if (half == 0)
+          asm("{.reg .b16 xl, xh, ml, mh;\n"
+              "mov.b32 {xl, xh}, %1;\n"
+              "mov.b32 {ml, mh}, %2;\n"
+              "fma.rn.f32.bf16 %0, xl, ml, 0f80000000;}"
+              : "=f"(f[c])
+              : "r"(g[c][k]), "r"(mult[k]));
+        else
+          asm("{.reg .b16 xl, xh, ml, mh;\n"
+              "mov.b32 {xl, xh}, %1;\n"
+              "mov.b32 {ml, mh}, %2;\n"
+              "fma.rn.f32.bf16 %0, xh, mh, 0f80000000;}"
+              : "=f"(f[c])
+              : "r"(g[c][k]), "r"(mult[k]));
+      }
       if (FULL || 2 * k + half < nstore) convert_store_row<FMT, MC>(f, dst);
       dst += row_stride;
     }

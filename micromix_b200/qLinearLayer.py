@@ -12,6 +12,9 @@ import torch.nn as nn
 
 from . import mixedgemm
 
+PACKED_NAMES = ("BN", "BS", "BO", "SFBN", "SFBS", "SFBO")  # the reference's attribute names, qLinearLayer.py:50-56
+PACKED_FORMAT = "micromix_b200.packed_linear.v1"
+
 
 def find_qlinear_layers(module, name=''):
     """qLinearLayer.py:8-17 (the reference tests a non-existent `enable_quant` attribute; every layer counts here)."""
@@ -48,11 +51,62 @@ class QLinearLayer(nn.Module):
             raise ValueError(f"p4/p6/p8 = {self.p4_num}/{self.p6_num}/{self.p8_num} must be non-negative multiples "
                              f"of 128 summing to in_features={self.in_features}")
 
-        self.register_buffer('reorder_index', reorder_index.to(torch.int16).cuda().contiguous(), persistent=False)
+        self.register_buffer('reorder_index', reorder_index.to(torch.int16).cuda().contiguous())
         w = originalLayer.weight.data.to(device='cuda', dtype=torch.bfloat16).contiguous()
-        (self.BN, self.BS, self.BO, self.SFBN, self.SFBS, self.SFBO) = mixedgemm.reorder_quantize_w4(
-            w, self.reorder_index, self.p4_num, self.p6_num, self.p8_num)
+        packed = mixedgemm.reorder_quantize_w4(w, self.reorder_index, self.p4_num, self.p6_num, self.p8_num)
         del w
+        # the six packed-weight tensors are BUFFERS: they follow .to() / .cuda() and appear in state_dict(), so a model
+        # of QLinearLayers can be saved once and reloaded without re-quantizing (the reference re-quantizes every weight at
+        # every start, model/qLinearLayer.py:50, and saves nothing: SURVEY.md section 5.4)
+        for name, t in zip(PACKED_NAMES, packed):
+            self.register_buffer(name, t)
+
+    # ---- packed-weight checkpoint: six uint8 tensors + index + split
+    def packed_state(self):
+        st = {"format": PACKED_FORMAT, "in_features": self.in_features, "out_features": self.out_features,
+              "p4_num": self.p4_num, "p6_num": self.p6_num, "p8_num": self.p8_num,
+              "reorder_index": self.reorder_index.detach().cpu(),
+              "bias": None if self.bias is None else self.bias.detach().cpu()}
+        for name in PACKED_NAMES:
+            st[name] = getattr(self, name).detach().cpu()
+        return st
+
+    def save_packed(self, path):
+        torch.save(self.packed_state(), path)
+
+    @classmethod
+    def from_packed(cls, state, device="cuda"):
+        """Rebuild a layer from packed_state() (or the path of a save_packed() file) WITHOUT touching the bf16 weight:
+        start-up cost is one host->device copy of ~0.53 bytes per weight."""
+        if not isinstance(state, dict):
+            state = torch.load(state, map_location="cpu", weights_only=True)
+        if state.get("format") != PACKED_FORMAT:
+            raise ValueError(f"not a {PACKED_FORMAT} checkpoint: format={state.get('format')!r}")
+        K, N = int(state["in_features"]), int(state["out_features"])
+        p4, p6, p8 = int(state["p4_num"]), int(state["p6_num"]), int(state["p8_num"])
+        if p4 + p6 + p8 != K or min(p4, p6, p8) < 0 or p4 % 128 or p6 % 128 or p8 % 128:
+            raise ValueError(f"inconsistent split {p4}/{p6}/{p8} for in_features={K}")
+        shapes = {"BN": (N, p4 // 2), "BS": (N, p6 // 2), "BO": (N, p8 // 2)}
+        for name, k in (("SFBN", p4), ("SFBS", p6), ("SFBO", p8)):
+            shapes[name] = (-(-N // 128) * 128 * k // 32,)
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.in_features, self.out_features = K, N
+        self.p4_num, self.p6_num, self.p8_num = p4, p6, p8
+        if state.get("bias") is not None:
+            self.register_buffer("bias", state["bias"].to(device=device, dtype=torch.bfloat16).contiguous())
+        else:
+            self.bias = None
+        idx = state["reorder_index"]
+        if idx.dtype != torch.int16 or idx.numel() != K:
+            raise ValueError("reorder_index must be int16 [in_features]")
+        self.register_buffer("reorder_index", idx.to(device).contiguous())
+        for name in PACKED_NAMES:
+            t = state[name]
+            if t.dtype != torch.uint8 or tuple(t.shape) != shapes[name]:
+                raise ValueError(f"{name}: expected uint8 {shapes[name]}, got {t.dtype} {tuple(t.shape)}")
+            self.register_buffer(name, t.to(device).contiguous())
+        return self
 
     @torch.no_grad()
     def forward(self, x):

@@ -217,3 +217,64 @@ def test_splitk_decode_shapes(cuda, mmx_lib, sk, M, N, split):
     mx1, _ = H.rel_err(H.bits(c), H.bits(c1))
     mxb, _ = H.rel_err(H.bits(cb), H.bits(c1b))
     assert mx1 <= TOL_MAX and mxb <= TOL_MAX, (mx1, mxb)
+
+
+# ---------------------------------------------------------------------------------------------- bench-size oracle checks
+def _edge_rows(M, n_extra=4, seed=0):
+    """>= 8 rows including every kind of tile edge: first / last row of the first and last 128- and 256-row tiles."""
+    base = {0, 127, 128, 255, 256, M - 257, M - 256, M - 129, M - 128, M - 1, M // 2}
+    g = torch.Generator().manual_seed(seed)
+    base |= set(torch.randint(0, M, (n_extra,), generator=g).tolist())
+    return sorted(r for r in base if 0 <= r < M)
+
+
+def _big_case(cuda, M, N, K, split, seed):
+    """Full-size GEMM on the GPU, sampled rows against the CPU oracle (the rows' codes are re-quantized on their own:
+    quantization is per row, so they are the same bytes)."""
+    from micromix_b200 import mixedgemm
+    idx = H.make_index(K, seed=seed).to(cuda)
+    g = torch.Generator(device="cuda").manual_seed(100 + seed)
+    gain = 1.0 + 31.0 * (torch.arange(K, device=cuda, dtype=torch.float32) / K) ** 8
+    x = torch.randn(M, K, generator=g, device=cuda)
+    xg = torch.empty_like(x)
+    xg[:, idx.long()] = x * gain
+    x = xg.to(torch.bfloat16)
+    del xg
+    w = (torch.randn(N, K, generator=g, device=cuda) * 0.02).to(torch.bfloat16)
+    a = mixedgemm.reorder_quantize_x(x, idx, *split)
+    b = mixedgemm.reorder_quantize_w4(w, idx, *split)
+    c = _mm(a, b)
+    rows = torch.tensor(_edge_rows(M, seed=seed), device=cuda)
+    a_s = mixedgemm.reorder_quantize_x(x[rows].contiguous(), idx, *split)
+    for i in range(3):  # the sampled rows' codes are exactly the rows of the full quantization
+        assert torch.equal(a_s[i], a[i][rows])
+    ref = _oracle(a_s, b)
+    mx, mean = H.rel_err(H.bits(c[rows]), ref)
+    assert mx <= TOL_MAX and mean <= TOL_MEAN, (M, N, K, mx, mean)
+    return c
+
+
+LLAMA_LINEARS = [("qkv", 6144, 4096), ("o", 4096, 4096), ("gate_up", 28672, 4096), ("down", 4096, 14336)]
+
+
+@pytest.mark.parametrize("M", [8192, 16384])
+@pytest.mark.parametrize("name,N,K", LLAMA_LINEARS)
+def test_llama_linears_at_bench_sizes_vs_oracle(cuda, M, name, N, K):
+    """all four Llama-3-8B linears at the benchmarked M = 8192 and the prefill M = 16384, >= 8 sampled rows
+    including tile edges, against the fake-quant oracle within the north_star tolerance."""
+    _big_case(cuda, M, N, K, H.SPLITS[K], seed=M // 8192 + N % 7)
+
+
+def _shard_split(K_local):
+    p8 = max(128, (K_local // 8 + 127) // 128 * 128)
+    p6 = max(128, (K_local // 4 + 127) // 128 * 128)
+    return K_local - p6 - p8, p6, p8
+
+
+@pytest.mark.parametrize("N,K", [(4096, 512), (4096, 1792), (768, 4096), (3584, 4096),   # Llama-3-8B at tp = 8
+                                 (5120, 3456), (5120, 6912), (5120, 13824), (5120, 640),  # Qwen2.5-32B down / o at tp 8/4/2
+                                 (6912, 5120), (896, 5120)])                              # ... gate_up / qkv at tp = 8
+def test_tp_shard_shapes_vs_oracle(cuda, N, K):
+    """The per-rank GEMM shapes of the tensor-parallel runs (K_local 512 / 1792, N 768 / 3584, the Qwen K = 27648 shards)
+    at M = 8192 against the oracle: short-K and narrow-N tiles take other code paths than the square prefill shapes."""
+    _big_case(cuda, 8192, N, K, _shard_split(K), seed=K % 11 + N % 5)

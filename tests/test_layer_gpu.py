@@ -55,3 +55,31 @@ def test_qlinear_rejects_bad_split(cuda):
     lin = nn.Linear(512, 256, bias=False).to(torch.bfloat16)
     with pytest.raises(ValueError):
         QLinearLayer(lin, 100, 128, H.make_index(512))
+
+
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_qlinear_packed_checkpoint_round_trip(cuda, tmp_path, use_bias):
+    """the six packed-weight tensors are buffers (state_dict / .to()) and save_packed() /
+    from_packed() rebuild the layer without re-quantizing -- same bytes, same forward bits."""
+    from micromix_b200.qLinearLayer import PACKED_NAMES, QLinearLayer
+    K, N = 1024, 512
+    idx = H.make_index(K, seed=23)
+    lin = nn.Linear(K, N, bias=use_bias).to(torch.bfloat16)
+    lin.weight.data = H.make_weights(N, K)
+    if use_bias:
+        lin.bias.data = (torch.randn(N) * 0.1).to(torch.bfloat16)
+    q = QLinearLayer(lin, 256, 256, idx)
+    sd = q.state_dict()
+    for name in PACKED_NAMES + ("reorder_index",):
+        assert name in sd, f"{name} must be a persistent buffer"
+    path = tmp_path / "lin.pt"
+    q.save_packed(path)
+    q2 = QLinearLayer.from_packed(str(path))
+    for name in PACKED_NAMES:
+        assert torch.equal(getattr(q, name), getattr(q2, name))
+    x = H.make_activations(200, K, idx).reshape(1, 200, K).to(cuda)
+    assert torch.equal(q(x), q2(x))
+    bad = q.packed_state()
+    bad["BN"] = bad["BN"][:, :-1]
+    with pytest.raises(ValueError):
+        QLinearLayer.from_packed(bad)

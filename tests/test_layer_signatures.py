@@ -76,3 +76,16 @@ def test_moe_token_grouping_matches_the_reference_loop():
             assert torch.equal(tok_sorted[off:off + n], tok)
             assert torch.equal(w.reshape(-1)[order][off:off + n], w[tok, slot])
             off += n
+
+
+def test_packed_checkpoint_validation_cpu():
+    """from_packed() validates format / shapes before anything touches the GPU."""
+    import pytest
+    import torch
+    from micromix_b200.qLinearLayer import PACKED_FORMAT, QLinearLayer
+    with pytest.raises(ValueError):
+        QLinearLayer.from_packed({"format": "something else"})
+    st = {"format": PACKED_FORMAT, "in_features": 512, "out_features": 256, "p4_num": 256, "p6_num": 128, "p8_num": 100,
+          "reorder_index": torch.arange(512, dtype=torch.int16), "bias": None}
+    with pytest.raises(ValueError):
+        QLinearLayer.from_packed(st)

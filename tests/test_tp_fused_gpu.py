@@ -242,3 +242,20 @@ def test_gather_channel_single_rank(cuda, mmx_lib, M, K, norm):
             assert torch.equal(y, want), f"gathered GEMM differs (round {rnd})"
     finally:
         ws.close()
+
+
+def test_tp_layers_multiprocess(cuda):
+    """Real ranks: a tensor-parallel decoder layer (NCCL, fused all-reduce, sequence parallel) and an expert-parallel
+    Mixtral block against the 1-GPU layer -- tools/tp_layer_check.py under torchrun on two GPUs (skipped on a one-GPU box;
+    the builder's multi-GPU logs are under profiles/)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29671", os.path.join(root, "tools", "tp_layer_check.py"), "--tokens", "512"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"ok": true' in r.stdout

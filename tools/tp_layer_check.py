@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Real-rank correctness of the tensor- / expert-parallel LAYERS (run under torchrun on N >= 2 GPUs of one box).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 \
+      tools/tp_layer_check.py [--model llama|qwen] [--tokens 1024]
+
+Every rank builds the same random-init decoder layer (same seed) and runs it
+  (1) unsharded (tp_group=None)                      -- the 1-GPU result,
+  (2) tensor parallel, mmx_matmul + NCCL all-reduce,
+  (3) tensor parallel, fused GEMM -> all-reduce (PeerWorkspace),
+  (4) tensor parallel, sequence parallel (reduce-scatter + multicast all-gather of packed codes), when the box has multicast.
+(2), (3) and (4) run the SAME shards (same rank-local permutations and splits), so they must agree within the rounding of a
+bf16 sum over ranks; against (1) the K-sharded linears quantize other 32-channel groups, so the bound is the quantization
+noise of the path itself (stated below).  Also: the Mixtral MoE block expert-parallel vs one GPU.
+Prints one JSON line on rank 0 and exits non-zero on any rank that fails.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from micromix_b200 import model_shapes as S  # noqa: E402
+from micromix_b200.parallel_utils import PeerWorkspace, init_tensor_parallel  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    rms = b.pow(2).mean().sqrt() + 1e-30
+    d = (a - b).abs() / torch.maximum(b.abs(), rms)
+    return float(d.max()), float(d.mean())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="llama", choices=["llama", "qwen"])
+    ap.add_argument("--tokens", type=int, default=1024)
+    ap.add_argument("--full-size", action="store_true", help="the real layer shapes instead of the scaled-down ones")
+    args = ap.parse_args()
+    rank, world, dev = init_tensor_parallel("nccl")
+    from micromix_b200 import _lib
+    _lib.load().mmx_set_option(b"tp_timeout_ms", 5000)
+    group = dist.group.WORLD
+    if args.model == "llama":
+        from micromix_b200.qLlamaLayer import QLlamaDecoderLayer as Layer
+        cfg = dict(S.LLAMA3_8B)
+    else:
+        from micromix_b200.qQwenLayer import QQwen2DecoderLayer as Layer
+        cfg = dict(S.QWEN25_32B)
+    if not args.full_size:  # scaled down, still shardable 8 ways in multiples of 128
+        cfg.update(hidden_size=2048, intermediate_size=4096, num_attention_heads=16, num_key_value_heads=8, head_dim=128)
+    b, s = max(1, args.tokens // 256), 256
+    M = b * s
+    layer = S.make_layer(cfg, dev, seed=0)
+    idx, p6, p8 = S.make_calibration(cfg, 0)
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(b, s, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    pos = S.rope_tables(cfg, b, s, dev)
+    res, fails = {}, []
+
+    single = Layer(layer, False, p8, p6, idx, 0)
+    y1 = single(x0, position_embeddings=pos)[0]
+    del single
+
+    nccl = Layer(layer, False, p8, p6, idx, 0, tp_group=group)
+    y2 = nccl(x0, position_embeddings=pos)[0]
+    del nccl
+
+    ws = PeerWorkspace(M, cfg["hidden_size"], group=group, device=dev)
+    fused = Layer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws)
+    y3 = fused(x0, position_embeddings=pos)[0].clone()
+    y3b = fused(x0, position_embeddings=pos)[0].clone()  # twice: both parities of the workspace
+    res["fused_mode"] = ws.mode
+    res["fused_status"] = ws.status()
+    del fused
+    ws.close()
+
+    y4 = None
+    try:
+        ws2 = PeerWorkspace(M, cfg["hidden_size"], group=group, device=dev, gather=(M, cfg["hidden_size"]))
+    except Exception as e:  # noqa: BLE001
+        ws2 = None
+        res["sp_note"] = f"sequence parallel unavailable: {e!r}"[:160]
+    if ws2 is not None:
+        sp = Layer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws2, sequence_parallel=True)
+        lo, hi = ws2.shard_range(M)
+        xs = x0.reshape(M, -1)[lo:hi].unsqueeze(0).contiguous()
+        for _ in range(2):
+            ys = sp(xs, position_embeddings=pos)[0].reshape(hi - lo, -1)
+        per = ws2.shard_rows(M)
+        buf = torch.zeros(per, ys.shape[1], dtype=ys.dtype, device=dev)
+        buf[: hi - lo] = ys
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        y4 = torch.cat(parts, 0)[:M].reshape(b, s, -1)
+        res["sp_mode"] = ws2.mode
+        res["sp_status"] = ws2.status()
+        del sp
+        ws2.close()
+
+    def check(name, a, ref, mx_tol, mean_tol):
+        mx, mean = rel(a, ref)
+        res[name] = {"max_rel": mx, "mean_rel": mean, "tol": [mx_tol, mean_tol]}
+        if not (mx <= mx_tol and mean <= mean_tol and bool(torch.isfinite(a.float()).all())):
+            fails.append(name)
+
+    # same shards, different reduction paths: a bf16 rounding step of the summed output (and its propagation through the
+    # MLP's quantizers: a flipped 4-bit code moves one product term by up to half a quantization step)
+    check("fused_vs_nccl", y3, y2, 6e-2, 2e-3)
+    check("fused_repeat", y3b, y3, 0.0, 0.0)
+    if y4 is not None:
+        check("sp_vs_nccl", y4, y2, 6e-2, 2e-3)
+    # against the unsharded layer: other quantization groups in o_proj / down_proj -> quantization-noise level agreement
+    check("tp_vs_single", y2, y1, 2.5e-1, 2e-2)
+
+    # ---- Mixtral MoE block, expert parallel vs one GPU
+    from micromix_b200.qMixtralLayer import QMixtralSparseMoeBlock
+    mcfg = dict(S.MIXTRAL_8X7B, hidden_size=1024, intermediate_size=2048, num_attention_heads=8, num_key_value_heads=2)
+    ml = S.make_layer(mcfg, dev, seed=3, moe=True)
+    midx, mp6, mp8 = S.make_calibration(mcfg, 0, moe=True)
+    xm = torch.randn(1, 1000, mcfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    for fz in (False, True):
+        one = QMixtralSparseMoeBlock(ml.block_sparse_moe, mp8, mp6, midx, 0, fused=fz)
+        ep = QMixtralSparseMoeBlock(ml.block_sparse_moe, mp8, mp6, midx, 0, ep_group=group, fused=fz)
+        ya, yb = one(xm)[0], ep(xm)[0]
+        check(f"moe_ep_vs_single_fused{int(fz)}", yb, ya, 2e-2, 2e-3)
+        del one, ep
+
+    ok = torch.tensor([0 if fails else 1], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    res.update({"check": "tp_layer_check", "model": args.model, "tokens": M, "world": world, "ok": bool(int(ok.item())),
+                "failed_on_rank0": fails})
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(ok.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
