@@ -183,6 +183,7 @@ def workload_config(args, world):
                                      "(a bounded CPU sample: same_steps is false by design)"
                                      if args.impl == "reference" else None),
             "tp_chunks": (args.tp_chunks if world > 1 and args.impl == "ours" else None),
+            "options": (args.set_option or None),
             "l2": "inputs+weights+outputs per step (>1 GB) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -318,6 +319,10 @@ def run_ours(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device: micromix_b200 has no CPU path (use --impl reference for "
                            "the host-core baseline)")
     lib = _lib.load()
+    for kv in args.set_option:
+        k, v = kv.split("=")
+        if lib.mmx_set_option(k.encode(), int(v)):
+            raise ValueError(lib.mmx_last_error().decode())
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     M = args.tokens
@@ -367,232 +372,265 @@ def run_ours(args, rank, world, local_rank):
                                  share=(chunks[0][i] if c else None), chunk=c)
                        for i, (n, N, K, mode) in enumerate(LINEARS)])
     lins = chunks[0]
-    if tp_mode == "sp":
-        for l in lins:
-            l.enable_sp(ws)
     total_flops = M * flops_per_token()  # whole job, all ranks together
     mx_peak = measure_mx_peak(lib)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def run_mode(tp_mode):
+        """Everything that is timed, for one tensor-parallel mode: warm-up, real-rank parity, the K timed steps, the evented
+        per-kernel pass, the end-to-end leg.  Returns the JSON line of that mode."""
+        for l in lins:
+            if tp_mode == "sp":
+                l.enable_sp(ws)
+            else:
+                l.sp_ws = None
 
-    def issue_step(ev=None):
-        """One pass of the hot path over the batch.  ev[c][li] = three events around quantize / GEMM."""
-        stream = torch.cuda.current_stream().cuda_stream
-        if world == 1:
-            for li, l in enumerate(lins):
-                l.run(stream, ev[0][li] if ev is not None else None)
-            return
-        pend = [None] * C
-        for half in ((0, 1), (2, 3)):  # attention linears, MLP linears
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def issue_step(ev=None):
+            """One pass of the hot path over the batch.  ev[c][li] = three events around quantize / GEMM."""
+            stream = torch.cuda.current_stream().cuda_stream
+            if world == 1:
+                for li, l in enumerate(lins):
+                    l.run(stream, ev[0][li] if ev is not None else None)
+                return
+            pend = [None] * C
+            for half in ((0, 1), (2, 3)):  # attention linears, MLP linears
+                for c in range(C):
+                    if pend[c] is not None:
+                        pend[c].wait()  # this chunk's previous all-reduce: overlapped the other chunks' kernels
+                        pend[c] = None
+                    for li in half:
+                        chunks[c][li].run(stream, ev[c][li] if ev is not None else None)
+                    pend[c] = chunks[c][half[1]].reduce_async()
             for c in range(C):
                 if pend[c] is not None:
-                    pend[c].wait()  # this chunk's previous all-reduce: overlapped the other chunks' kernels
-                    pend[c] = None
-                for li in half:
-                    chunks[c][li].run(stream, ev[c][li] if ev is not None else None)
-                pend[c] = chunks[c][half[1]].reduce_async()
-        for c in range(C):
-            if pend[c] is not None:
-                pend[c].wait()
+                    pend[c].wait()
 
-    def new_events():
-        return [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in LINEARS] for _ in range(C)]
+        def new_events():
+            return [[[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in LINEARS] for _ in range(C)]
 
-    for _ in range(max(args.warmup, 3)):
-        issue_step()
-    barrier()
-    tp_parity = check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev) if world > 1 else None
-    # N > 1: the step is replayed from a CUDA graph (8C kernels + 2C NCCL all-reduces per replay) -- at tp=8 the
-    # kernels are 10-70 us each and eager launches from 8 Python processes would bound the step
-    graph, graph_note = None, None
-    if world > 1 and not args.no_graph:
-        try:
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                issue_step()
-            torch.cuda.current_stream().wait_stream(side)
-            barrier()
-            graph = torch.cuda.CUDAGraph()
-            l0 = mixedgemm.launch_count()
-            with torch.cuda.graph(graph, stream=side):
-                issue_step()
-            launches_per_step = mixedgemm.launch_count() - l0
-            barrier()
-            for _ in range(3):
-                graph.replay()
-            barrier()
-        except Exception as e:  # noqa: BLE001 -- report, then time the eager step instead
-            graph, graph_note = None, f"capture failed: {e!r}"[:200]
-            torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    n_ev = args.steps if graph is None else max(3, min(args.steps, 10))
-    ev = [new_events() for _ in range(n_ev)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = mixedgemm.launch_count()
-    barrier()
-    sampler.active.set()
-    t_start.record()
-    if graph is not None:
-        for s in range(args.steps):
-            graph.replay()
-    else:
-        for s in range(args.steps):
-            issue_step(ev[s])
-    t_end.record()
-    barrier()
-    if graph is None:
-        sampler.active.clear()  # (graph mode: keep sampling through the evented pass of the same step below)
-    launches = (mixedgemm.launch_count() - launches0) if graph is None else launches_per_step * args.steps
-    ms_total = t_start.elapsed_time(t_end)
-    ms_step = ms_total / args.steps
-    if world > 1:
-        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
-    if graph is not None:
-        # per-kernel device times cannot be taken inside a graph replay: an eager, evented pass of the same step
-        for s in range(n_ev):
-            issue_step(ev[s])
+        for _ in range(max(args.warmup, 3)):
+            issue_step()
         barrier()
-        sampler.active.clear()
-    # per-kernel device time from the events (N = 1: inside the timed region itself)
-    cells = [(s, c, li) for s in range(n_ev) for c in range(C) for li in range(len(LINEARS))]
-    q_ms = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s, c, li in cells)
-    g_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells)
-    per_lin = {}
-    for li, l in enumerate(lins):
-        gq = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
-        gg = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
-        per_lin[l.name] = {"M": l.M, "N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
-                           "gemm_includes_allreduce": l.ws is not None,
-                           "quant_gbs": l.qbytes / gq / 1e6, "gemm_tflops": l.flops / gg / 1e9}
-    # the GEMM roofline counts launches that are GEMMs only: in fused mode a row-parallel "GEMM" interval is
-    # GEMM + all-reduce (reported per linear, not against the tensor peak)
-    pure = [li for li, l in enumerate(lins) if l.ws is None]
-    g_pure_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells if li in pure)
-    pure_flops = C * sum(lins[li].flops for li in pure)
-    gemm_tflops = pure_flops * n_ev / g_pure_ms / 1e9
-    # split-weighted tensor peak from the MEASURED MX issue rates of this GPU (mmx_debug_mma_peak): the FP4 segment runs as
-    # kind::mxf4, the FP6 / FP8 segments as kind::mxf8f6f4.  The GEMMs are timed inside a long step -> sustained figures.
-    sus = tuple(mx_peak[f"{n}_sustained_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
-    bur = tuple(mx_peak[f"{n}_burst_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
+        tp_parity = check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev) if world > 1 else None
+        # N > 1: the step is replayed from a CUDA graph (8C kernels + 2C NCCL all-reduces per replay) -- at tp=8 the
+        # kernels are 10-70 us each and eager launches from 8 Python processes would bound the step
+        graph, graph_note = None, None
+        if world > 1 and not args.no_graph:
+            try:
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    issue_step()
+                torch.cuda.current_stream().wait_stream(side)
+                barrier()
+                graph = torch.cuda.CUDAGraph()
+                l0 = mixedgemm.launch_count()
+                with torch.cuda.graph(graph, stream=side):
+                    issue_step()
+                launches_per_step = mixedgemm.launch_count() - l0
+                barrier()
+                for _ in range(3):
+                    graph.replay()
+                barrier()
+            except Exception as e:  # noqa: BLE001 -- report, then time the eager step instead
+                graph, graph_note = None, f"capture failed: {e!r}"[:200]
+                torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n_ev = args.steps if graph is None else max(3, min(args.steps, 10))
+        ev = [new_events() for _ in range(n_ev)]
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = mixedgemm.launch_count()
+        barrier()
+        sampler.active.set()
+        t_start.record()
+        if graph is not None:
+            for s in range(args.steps):
+                graph.replay()
+        else:
+            for s in range(args.steps):
+                issue_step(ev[s])
+        t_end.record()
+        barrier()
+        if graph is None:
+            sampler.active.clear()  # (graph mode: keep sampling through the evented pass of the same step below)
+        launches = (mixedgemm.launch_count() - launches0) if graph is None else launches_per_step * args.steps
+        ms_total = t_start.elapsed_time(t_end)
+        ms_step = ms_total / args.steps
+        if world > 1:
+            t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_step = float(t.item())
+        if graph is not None:
+            # per-kernel device times cannot be taken inside a graph replay: an eager, evented pass of the same step
+            for s in range(n_ev):
+                issue_step(ev[s])
+            barrier()
+            sampler.active.clear()
+        # per-kernel device time from the events (N = 1: inside the timed region itself)
+        cells = [(s, c, li) for s in range(n_ev) for c in range(C) for li in range(len(LINEARS))]
+        q_ms = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s, c, li in cells)
+        g_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells)
+        per_lin = {}
+        for li, l in enumerate(lins):
+            gq = sum(ev[s][c][li][0].elapsed_time(ev[s][c][li][1]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
+            gg = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s in range(n_ev) for c in range(C)) / (n_ev * C)
+            per_lin[l.name] = {"M": l.M, "N": l.N, "K": l.K, "quant_us": gq * 1e3, "gemm_us": gg * 1e3,
+                               "gemm_includes_allreduce": l.ws is not None,
+                               "quant_gbs": l.qbytes / gq / 1e6, "gemm_tflops": l.flops / gg / 1e9}
+        # the GEMM roofline counts launches that are GEMMs only: in fused mode a row-parallel "GEMM" interval is
+        # GEMM + all-reduce (reported per linear, not against the tensor peak)
+        pure = [li for li, l in enumerate(lins) if l.ws is None]
+        g_pure_ms = sum(ev[s][c][li][1].elapsed_time(ev[s][c][li][2]) for s, c, li in cells if li in pure)
+        pure_flops = C * sum(lins[li].flops for li in pure)
+        gemm_tflops = pure_flops * n_ev / g_pure_ms / 1e9
+        # split-weighted tensor peak from the MEASURED MX issue rates of this GPU (mmx_debug_mma_peak): the FP4 segment runs as
+        # kind::mxf4, the FP6 / FP8 segments as kind::mxf8f6f4.  The GEMMs are timed inside a long step -> sustained figures.
+        sus = tuple(mx_peak[f"{n}_sustained_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
+        bur = tuple(mx_peak[f"{n}_burst_tflops"] for n in ("mxf4", "mxf6", "mxf8"))
 
-    def tmin_of(l, a):
-        return 2.0 * l.M * l.N * (l.split[0] / a[0] + l.split[1] / a[1] + l.split[2] / a[2])
+        def tmin_of(l, a):
+            return 2.0 * l.M * l.N * (l.split[0] / a[0] + l.split[1] / a[1] + l.split[2] / a[2])
 
-    tmin = C * sum(tmin_of(lins[li], sus) for li in pure)
-    peak_eff = pure_flops / tmin  # TFLOP/s
-    peak_burst = pure_flops / (C * sum(tmin_of(lins[li], bur) for li in pure))
-    p_bf16 = peaks["bf16_tflops"]
-    peak_proxy = pure_flops / (C * sum(tmin_of(lins[li], (4 * p_bf16, 2 * p_bf16, 2 * p_bf16)) for li in pure))
-    for li in pure:
-        l = lins[li]
-        per_lin[l.name]["gemm_roofline_frac"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, sus))
-        per_lin[l.name]["gemm_roofline_frac_vs_burst_peak"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, bur))
-    for l in lins:
-        per_lin[l.name]["quant_roofline_frac"] = per_lin[l.name]["quant_gbs"] / peaks["hbm_gbs"]
-    quant_gbs = C * sum(l.qbytes for l in lins) * n_ev / q_ms / 1e6
-    # DRAM bytes per launch from the ncu --set full capture of this same command (profiles/, tools/ncu_traffic.py), next to
-    # the algorithmic bytes of each launch; N = 1 only (the capture is a one-GPU run)
-    traffic = traffic_q = None
-    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if world == 1 and os.path.exists(prof):
-        try:
-            tj = json.load(open(prof))
-            for l in lins:
-                g = tj.get("gemm", {}).get(l.name)
-                if g:
-                    per_lin[l.name]["gemm_dram_bytes"] = g["dram_bytes"]
-                    per_lin[l.name]["gemm_algorithmic_bytes"] = l.gbytes
-                qd = tj.get("quantize", {}).get(l.name)
-                if qd:
-                    per_lin[l.name]["quant_dram_bytes"] = qd["dram_bytes"]
-                    per_lin[l.name]["quant_algorithmic_bytes"] = l.qbytes
-            if all("gemm_dram_bytes" in per_lin[l.name] for l in lins):
-                traffic = sum(per_lin[l.name]["gemm_dram_bytes"] for l in lins)
-            if all("quant_dram_bytes" in per_lin[l.name] for l in lins):
-                traffic_q = sum(per_lin[l.name]["quant_dram_bytes"] for l in lins)
-        except Exception:
-            traffic = traffic_q = None
-
-    # ---- e2e: the plugin call a user makes (QLinearLayer.forward) with HOST buffers, copies inside the timed region
-    e2e = None if args.no_e2e else measure_e2e(args, rank, world, dev, chunks, total_flops)
-
-    clocks = sampler.summary()
-    sampler.stop_flag.set()
-    tp_status, ws_mode = None, None
-    if ws is not None:
-        ws_mode = ws.mode
-        tp_status = ws.status()  # 0 = no reducer wait ever timed out
-        ws.close()
-    line = {"metric": METRIC, "value": total_flops / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/mxfp6/mxfp8 x mxfp4 -> fp32 acc -> bf16",
-            "data": "synthetic", "tokens_per_s": M / ms_step * 1e3, "config": workload_config(args, world),
-            "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks,
-            "roofline": {"kernel": "mixed_gemm_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_eff,
-                         "unit": "TFLOP/s", "frac": gemm_tflops / peak_eff, "traffic": traffic,
-                         "traffic_note": "DRAM bytes of the step's GEMM launches (sum; per launch under per_linear) from the "
-                                         "ncu capture in profiles/r02_traffic.json" if traffic else None,
-                         "algorithmic_bytes": sum(l.gbytes for l in lins) if traffic else None,
-                         "launches_counted": [lins[li].name for li in pure],
-                         "frac_vs_burst_peak": gemm_tflops / peak_burst, "frac_vs_bf16_proxy": gemm_tflops / peak_proxy,
-                         "mx_peak_measured": mx_peak,
-                         "peak_note": "split-weighted over the linears' (p4, p6, p8) from the MEASURED sustained issue rates "
-                                      "of kind::mxf4 / kind::mxf8f6f4 (E3M2, E4M3) on this GPU (mmx_debug_mma_peak: 0.45 s of "
-                                      "back-to-back MMAs on smem-resident operands, power-capped clocks; the same probe as a "
-                                      f"0.5 ms burst gives {peak_burst:.0f}); the round-1 proxy (4x / 2x the "
-                                      f"{peaks['source']} cuBLAS bf16 burst {p_bf16}) would give {peak_proxy:.0f} TFLOP/s"},
-            "roofline_quantize": {"kernel": "reorder_quantize_kernel", "bound": "hbm", "achieved": quant_gbs,
-                                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": quant_gbs / peaks["hbm_gbs"],
-                                  "traffic": traffic_q,
-                                  "algorithmic_bytes": sum(l.qbytes for l in lins) if traffic_q else None,
-                                  "peak_note": f"{peaks['source']} copy bandwidth"},
-            "share": {"gemm": g_ms / ms_total if world == 1 else None, "quantize": q_ms / ms_total if world == 1 else None},
-            "per_linear": per_lin}
-    if tp_status is not None:
-        line["tp_fused_status"] = tp_status
-    if tp_parity is not None:
-        line["tp_parity"] = tp_parity
-    if world > 1:
-        # what the row-parallel collectives put on NVLink, per rank and call, against the measured peer-copy rate
-        wire = {}
+        tmin = C * sum(tmin_of(lins[li], sus) for li in pure)
+        peak_eff = pure_flops / tmin  # TFLOP/s
+        peak_burst = pure_flops / (C * sum(tmin_of(lins[li], bur) for li in pure))
+        p_bf16 = peaks["bf16_tflops"]
+        peak_proxy = pure_flops / (C * sum(tmin_of(lins[li], (4 * p_bf16, 2 * p_bf16, 2 * p_bf16)) for li in pure))
+        for li in pure:
+            l = lins[li]
+            per_lin[l.name]["gemm_roofline_frac"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, sus))
+            per_lin[l.name]["gemm_roofline_frac_vs_burst_peak"] = per_lin[l.name]["gemm_tflops"] / (l.flops / tmin_of(l, bur))
         for l in lins:
-            if l.mode != "row":
-                continue
-            full = l.M * l.N * 2.0
-            if tp_mode == "sp":
-                egress = full * (world - 1) / world  # partial rows pulled by / pushed to their owners
-                note = "reduce-scatter: (tp-1)/tp of the bf16 partial leaves each rank, 1/tp of the sum comes back"
-            elif ws is not None and ws.mode == "switch":
-                egress = full * (world - 1) / world + full / world
-                note = "in-switch all-reduce: partials out + own result tiles multicast"
-            else:
-                egress = 2.0 * full * (world - 1) / world
-                note = "all-reduce: partials to owners + results to every rank"
-            us = per_lin[l.name]["gemm_us"]
-            wire[l.name] = {"egress_bytes_per_rank": egress, "gemm_plus_collective_us": us,
-                            "egress_gbs_over_that_interval": egress / us / 1e3, "note": note}
-        line["tp_wire"] = {"per_linear": wire, "peer_copy_peak_gbs": 770.0,
-                           "peak_note": "measured peer copy per direction on this pool (B200_PROFILING.md); round 1 "
-                                        "measured 744 GB/s (profiles/r01_nvlink_p2p_bw.log)"}
-    if world > 1:
-        line["tp"] = {"reduce": args.tp_reduce, "mode": tp_mode, "fused_mode": ws_mode, "fallback_note": ws_note,
-                      "mode_note": {"sp": "sequence parallel: row-parallel GEMMs end in a reduce-scatter, column-parallel "
-                                          "GEMMs start from an NVSwitch-multicast all-gather of the packed MX codes that each "
-                                          "rank quantized for ITS rows", "ar": "row-parallel GEMM -> all-reduce, every rank "
-                                          "quantizes the replicated activation"}.get(tp_mode),
-                      "chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
-                      "gemm_ctas": args.gemm_ctas or None,
-                      "per_kernel_times": "eager evented pass after the timed region" if graph is not None
-                      else "events inside the timed region"}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args)
+            per_lin[l.name]["quant_roofline_frac"] = per_lin[l.name]["quant_gbs"] / peaks["hbm_gbs"]
+        quant_gbs = C * sum(l.qbytes for l in lins) * n_ev / q_ms / 1e6
+        # DRAM bytes per launch from the ncu --set full capture of this same command (profiles/, tools/ncu_traffic.py), next to
+        # the algorithmic bytes of each launch; N = 1 only (the capture is a one-GPU run)
+        traffic = traffic_q = None
+        prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        if world == 1 and os.path.exists(prof):
+            try:
+                tj = json.load(open(prof))
+                for l in lins:
+                    g = tj.get("gemm", {}).get(l.name)
+                    if g:
+                        per_lin[l.name]["gemm_dram_bytes"] = g["dram_bytes"]
+                        per_lin[l.name]["gemm_algorithmic_bytes"] = l.gbytes
+                    qd = tj.get("quantize", {}).get(l.name)
+                    if qd:
+                        per_lin[l.name]["quant_dram_bytes"] = qd["dram_bytes"]
+                        per_lin[l.name]["quant_algorithmic_bytes"] = l.qbytes
+                if all("gemm_dram_bytes" in per_lin[l.name] for l in lins):
+                    traffic = sum(per_lin[l.name]["gemm_dram_bytes"] for l in lins)
+                if all("quant_dram_bytes" in per_lin[l.name] for l in lins):
+                    traffic_q = sum(per_lin[l.name]["quant_dram_bytes"] for l in lins)
+            except Exception:
+                traffic = traffic_q = None
+
+        # ---- e2e: the plugin call a user makes (QLinearLayer.forward) with HOST buffers, copies inside the timed region
+        e2e = None if args.no_e2e else measure_e2e(args, rank, world, dev, chunks, total_flops)
+
+        clocks = sampler.summary()
+        sampler.stop_flag.set()
+        tp_status, ws_mode = None, None
+        if ws is not None:
+            ws_mode = ws.mode
+            tp_status = ws.status()  # 0 = no reducer wait ever timed out
+        line = {"metric": METRIC, "value": total_flops / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/mxfp6/mxfp8 x mxfp4 -> fp32 acc -> bf16",
+                "data": "synthetic", "tokens_per_s": M / ms_step * 1e3, "config": workload_config(args, world),
+                "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks,
+                "roofline": {"kernel": "mixed_gemm_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_eff,
+                             "unit": "TFLOP/s", "frac": gemm_tflops / peak_eff, "traffic": traffic,
+                             "traffic_note": "DRAM bytes of the step's GEMM launches (sum; per launch under per_linear) from the "
+                                             "ncu capture in profiles/r02_traffic.json" if traffic else None,
+                             "algorithmic_bytes": sum(l.gbytes for l in lins) if traffic else None,
+                             "launches_counted": [lins[li].name for li in pure],
+                             "frac_vs_burst_peak": gemm_tflops / peak_burst, "frac_vs_bf16_proxy": gemm_tflops / peak_proxy,
+                             "mx_peak_measured": mx_peak,
+                             "peak_note": "split-weighted over the linears' (p4, p6, p8) from the MEASURED sustained issue rates "
+                                          "of kind::mxf4 / kind::mxf8f6f4 (E3M2, E4M3) on this GPU (mmx_debug_mma_peak: 0.45 s of "
+                                          "back-to-back MMAs on smem-resident operands, power-capped clocks; the same probe as a "
+                                          f"0.5 ms burst gives {peak_burst:.0f}); the round-1 proxy (4x / 2x the "
+                                          f"{peaks['source']} cuBLAS bf16 burst {p_bf16}) would give {peak_proxy:.0f} TFLOP/s"},
+                "roofline_quantize": {"kernel": "reorder_quantize_kernel", "bound": "hbm", "achieved": quant_gbs,
+                                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": quant_gbs / peaks["hbm_gbs"],
+                                      "traffic": traffic_q,
+                                      "algorithmic_bytes": sum(l.qbytes for l in lins) if traffic_q else None,
+                                      "peak_note": f"{peaks['source']} copy bandwidth"},
+                "share": {"gemm": g_ms / ms_total if world == 1 else None, "quantize": q_ms / ms_total if world == 1 else None},
+                "per_linear": per_lin}
+        if tp_status is not None:
+            line["tp_fused_status"] = tp_status
+        if tp_parity is not None:
+            line["tp_parity"] = tp_parity
+        if world > 1:
+            # what the row-parallel collectives put on NVLink, per rank and call, against the measured peer-copy rate
+            wire = {}
+            for l in lins:
+                if l.mode != "row":
+                    continue
+                full = l.M * l.N * 2.0
+                if tp_mode == "sp":
+                    egress = full * (world - 1) / world  # partial rows pulled by / pushed to their owners
+                    note = "reduce-scatter: (tp-1)/tp of the bf16 partial leaves each rank, 1/tp of the sum comes back"
+                elif ws is not None and ws.mode == "switch":
+                    egress = full * (world - 1) / world + full / world
+                    note = "in-switch all-reduce: partials out + own result tiles multicast"
+                else:
+                    egress = 2.0 * full * (world - 1) / world
+                    note = "all-reduce: partials to owners + results to every rank"
+                us = per_lin[l.name]["gemm_us"]
+                wire[l.name] = {"egress_bytes_per_rank": egress, "gemm_plus_collective_us": us,
+                                "egress_gbs_over_that_interval": egress / us / 1e3, "note": note}
+            line["tp_wire"] = {"per_linear": wire, "peer_copy_peak_gbs": 770.0,
+                               "peak_note": "measured peer copy per direction on this pool (B200_PROFILING.md); round 1 "
+                                            "measured 744 GB/s (profiles/r01_nvlink_p2p_bw.log)"}
+        if world > 1:
+            line["tp"] = {"reduce": args.tp_reduce, "mode": tp_mode, "fused_mode": ws_mode, "fallback_note": ws_note,
+                          "mode_note": {"sp": "sequence parallel: row-parallel GEMMs end in a reduce-scatter, column-parallel "
+                                              "GEMMs start from an NVSwitch-multicast all-gather of the packed MX codes that each "
+                                              "rank quantized for ITS rows", "ar": "row-parallel GEMM -> all-reduce, every rank "
+                                              "quantizes the replicated activation"}.get(tp_mode),
+                          "chunks": C, "cuda_graph": graph is not None, "graph_note": graph_note,
+                          "gemm_ctas": args.gemm_ctas or None,
+                          "per_kernel_times": "eager evented pass after the timed region" if graph is not None
+                          else "events inside the timed region"}
+        if world == 1 and not args.no_prefill:
+            try:
+                line["prefill"] = measure_prefill(args, dev)
+                line["prefill_tokens_per_s"] = line["prefill"]["tokens_per_s"]
+            except Exception as e:  # noqa: BLE001 -- the headline line must survive a failure of the secondary leg
+                line["prefill"] = {"error": repr(e)[:300]}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        return line
+
+    # N > 1 with the fused reduction: the row-parallel design has two forms here -- GEMM -> all-reduce ("ar") and the
+    # sequence-parallel GEMM -> reduce-scatter + all-gather of packed codes ("sp").  `--tp-mode auto` measures BOTH (each its
+    # own K timed steps) and reports the faster one as the line, the other under "tp_modes_measured".
+    modes = [tp_mode]
+    if world > 1 and ws is not None and tp_mode == "sp" and args.tp_mode == "auto":
+        modes = ["ar", "sp"]
+    lines = {m: run_mode(m) for m in modes}
+    best = min(lines, key=lambda m: lines[m]["ms_per_step"])
+    line = lines[best]
+    if len(lines) > 1:
+        line["tp_modes_measured"] = {m: {"ms_per_step": l["ms_per_step"], "value": l["value"],
+                                         "e2e_value": (l.get("e2e") or {}).get("value"),
+                                         "e2e_ms_per_step": (l.get("e2e") or {}).get("ms_per_step"),
+                                         "tp_parity_ok": (l.get("tp_parity") or {}).get("ok"),
+                                         "per_linear_us": {k: [round(v["quant_us"], 1), round(v["gemm_us"], 1)]
+                                                           for k, v in l["per_linear"].items()}}
+                                     for m, l in lines.items()}
+        line["tp_mode_choice"] = f"{best}: the faster of the modes measured in this run (each timed over its own {args.steps} steps)"
+    if ws is not None:
+        ws.close()
     if rank == 0:
         emit(line)
 
@@ -633,7 +671,7 @@ def check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev):
     import torch.distributed as dist
     from micromix_b200 import mixedgemm
     stream = torch.cuda.current_stream().cuda_stream
-    exact_expected = ws is None or ws.mode == "push"
+    exact_expected = ws is not None and ws.mode == "push"  # (ncclAllReduce sums in its own order: within one step)
     out = {"mode": tp_mode, "data_path": (ws.mode if ws is not None else "nccl"), "linears": {}}
     ok_all = True
     for l in lins:
@@ -641,6 +679,8 @@ def check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev):
         torch.cuda.synchronize()
         got, row0 = l.result()
         got = got.clone()
+        if ws is None and l.mode == "row":
+            dist.all_reduce(got)  # --tp-reduce nccl: the step's reduction is the separate ncclAllReduce
         a = mixedgemm.reorder_quantize_x(l.x, l.idx, *l.split)
         W = l.W
         part = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5])
@@ -721,16 +761,25 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
     # three streams: H2D copies, the layers, D2H copies -- a step is bound by the slower PCIe direction, not their sum
     s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
+    # Steps are PIPELINED: the host enqueues step s+1 while step s is still copying / computing, and synchronises once at
+    # the end of the timed region (every step's H2D and D2H copies are inside it).  Tensors that cross streams are handed to
+    # the allocator with record_stream; a result that lives in the peer workspace (fused all-reduce / reduce-scatter) is
+    # overwritten by the same linear's next call, so that call waits for the previous step's D2H of it.
+    prev_out = {}
+
     def step():
-        keep = []
-        for q, x, y, l, (r0, r1) in zip(layers, xin, yout, lins, yrows):
+        for i, (q, x, y, l, (r0, r1)) in enumerate(zip(layers, xin, yout, lins, yrows)):
             with torch.cuda.stream(s_in):
                 xd = x.to(dev, non_blocking=True)
                 e_in = torch.cuda.Event()
                 e_in.record(s_in)
+            xd.record_stream(s_run)
             s_run.wait_event(e_in)
             with torch.cuda.stream(s_run):
                 sp = getattr(l, "sp_ws", None)
+                in_ws = l.mode == "row" and (sp is not None or l.ws is not None)
+                if in_ws and i in prev_out:
+                    s_run.wait_event(prev_out[i])
                 if sp is not None and l.mode == "col":
                     sp.quantize_allgather(xd, l.M, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
                     yd = sp.matmul_gathered(l.M, l.W, q.p4_num, q.p6_num, q.p8_num)
@@ -747,20 +796,25 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
                         dist.all_reduce(yd)
                 e_run = torch.cuda.Event()
                 e_run.record(s_run)
+            if not in_ws:
+                yd.record_stream(s_out)
             s_out.wait_event(e_run)
             with torch.cuda.stream(s_out):
                 y.copy_(yd.reshape(-1, l.N)[r0:r1], non_blocking=True)
-            keep.append((xd, yd))  # alive until the step's synchronize: no cross-stream reuse by the allocator
-        torch.cuda.synchronize()
+                e_out = torch.cuda.Event()
+                e_out.record(s_out)
+            prev_out[i] = e_out
 
     for _ in range(2):
         step()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     n = max(3, min(args.steps, 8))
     t0 = time.perf_counter()
     for _ in range(n):
         step()
+    torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -768,8 +822,77 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
         dt = float(t.item())
     return {"value": total_flops / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "tokens_per_s": M / dt,
-            "api": "QLinearLayer.forward on pinned host tensors; per linear: H2D copy, quantize, GEMM (+ all-reduce), D2H "
-                   "copy, on three streams (copy-in / layers / copy-out); bytes are per rank"}
+            "steps_timed": n,
+            "api": "QLinearLayer.forward on pinned host tensors; per linear: H2D copy, quantize, GEMM (+ reduction), D2H "
+                   "copy, on three streams (copy-in / layers / copy-out), steps pipelined, one synchronize at the end of the "
+                   "timed region; bytes are per rank.  Sequence-parallel mode: a rank uploads only ITS rows of a replicated "
+                   "activation and returns only its rows of a row-parallel result (every byte crosses PCIe once per box)"}
+
+
+def measure_prefill(args, dev):
+    """BASELINE config 3 -- the metric's "prefill tokens/s" half: ALL 32 Llama-3-8B decoder layers (random-init weights,
+    synthetic reorder_index, 5-bit split), batch 8 x seq 2048 = 16384 tokens (/root/reference/prof_micromix.sh:1), through
+    QLlamaDecoderLayer(fused=True) -- RMSNorm inside the quantizer, SiLU*up inside down_proj's quantizer -- replayed from
+    ONE CUDA graph.  Attention is torch SDPA, RoPE / residual adds are torch ops: only the linears are the hot path."""
+    import torch
+    from micromix_b200 import mixedgemm
+    from micromix_b200 import model_shapes as S
+    from micromix_b200.qLlamaLayer import QLlamaDecoderLayer
+    cfg = S.LLAMA3_8B
+    n_layers, b, s = cfg["num_hidden_layers"], args.prefill_batch, args.prefill_seq
+    layers = []
+    for i in range(n_layers):
+        layer = S.make_layer(cfg, dev, seed=i)
+        idx, p6, p8 = S.make_calibration(cfg, i)
+        layers.append(QLlamaDecoderLayer(layer, False, p8, p6, idx, i, fused=True))
+        del layer
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(b, s, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    pos = S.rope_tables(cfg, b, s, dev)
+
+    @torch.no_grad()
+    def fwd():
+        x = x0
+        for l in layers:
+            x = l(x, position_embeddings=pos)[0]
+        return x
+
+    for _ in range(2):
+        y = fwd()
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(y.float()).all())
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    l0 = mixedgemm.launch_count()
+    with torch.cuda.graph(graph, stream=side):
+        y = fwd()
+    launches = mixedgemm.launch_count() - l0
+    torch.cuda.synchronize()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    n = args.prefill_iters
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    tokens = b * s
+    lin_flops = tokens * flops_per_token() * n_layers
+    out = {"config": f"Llama-3-8B full prefill: {n_layers} decoder layers, batch {b} x seq {s} = {tokens} tokens, "
+                     "random-init weights, synthetic reorder_index, 5.0-bit split", "layers_run": n_layers,
+           "ms_per_prefill": ms, "tokens_per_s": tokens / ms * 1e3, "linear_tflops": lin_flops / ms / 1e9,
+           "iters": n, "cuda_graph": True, "mmx_launches_per_prefill": int(launches), "output_finite": finite,
+           "fused_norm_act": True,
+           "note": "decoder layers only (no embedding / lm_head, as in the reference's layer-wise eval); attention = torch "
+                   "SDPA, RoPE / residual adds = torch ops; one CUDA-graph replay per prefill"}
+    del graph, layers, y
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_baseline(args):
@@ -792,6 +915,12 @@ def main():
     ap.add_argument("--gemm-ctas", type=int, default=0, help="N>1: cap the persistent GEMM grid (SMs left to NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the 32-layer Llama-3-8B prefill leg (N = 1)")
+    ap.add_argument("--prefill-batch", type=int, default=8)
+    ap.add_argument("--prefill-seq", type=int, default=2048)
+    ap.add_argument("--prefill-iters", type=int, default=5)
+    ap.add_argument("--set-option", action="append", default=[], metavar="KEY=VALUE",
+                    help="mmx_set_option(KEY, VALUE) before the run (tuning sweeps)")
     ap.add_argument("--tp-mode", default="auto", choices=["auto", "sp", "ar"],
                     help="N>1, fused reduction: sp = sequence parallel (reduce-scatter + all-gather of packed codes through "
                          "NVSwitch multicast; the default when the box offers multicast memory), ar = all-reduce")

@@ -84,6 +84,7 @@ struct MatmulExtra {
   uint32_t* ag_ticket = nullptr;
   uint32_t* ag_consumed[kMaxTp] = {};
   int ag_tp = 0;
+  uint32_t* ag_err = nullptr;  // local error word (mmx_tp_status): bit 3 = a source rank's rows never arrived
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
@@ -94,6 +95,7 @@ struct QuantGather {
   const uint32_t* consumed;  // local: bumped once per rank when that rank is done reading the previous gather
   uint32_t* issued;          // local: gathers this rank has issued so far
   uint32_t* arrived[kMaxTp]; // rank d's (peer-mapped) count of gathers whose rows from THIS rank have landed there
+  uint32_t* err;             // local error word (mmx_tp_status): bit 2 = the wait for the consumers timed out
   int tp;
 };
 // quantize.cu: the reorder+quantize launcher behind mmx_reorder_quantize_* (fmt = bits per segment; norm_w: fused RMSNorm)

@@ -101,7 +101,8 @@ struct GemmParams {
   const int* grp_mblk;
   int grp_n;             // B rows per group
   // GATHERED A (sequence-parallel hand-over, tp_reduce.cu): the A rows of source rank s = row / ag_rows are valid once
-  // ag_arrived[s] has reached ag_taken[0] + 1 (the peers' quantizers multicast them and then bump the counter)
+  // ag_arrived[32 * s] (one counter per 128-byte line) has reached ag_taken[0] + 1 (the peers' quantizers multicast them
+  // and then bump the counter)
   const uint32_t* ag_arrived;
   uint32_t* ag_taken;
   int ag_rows;
@@ -110,6 +111,8 @@ struct GemmParams {
   uint32_t* ag_ticket;
   uint32_t* ag_consumed[kMaxTp];
   int ag_tp;
+  uint32_t* ag_err;
+  unsigned long long ag_timeout_ns;
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
@@ -543,17 +546,20 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
             uint32_t v;
             unsigned long long t0 = 0;
             for (uint32_t it = 1;; ++it) {
-              asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + src) : "memory");
+              asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
               if ((int32_t)(v - ag_target) >= 0) break;
               __nanosleep(64);
               if ((it & 1023u) == 0) {  // bounded: a lost peer costs wrong rows (flagged), never a hung GPU
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > 10000000000ull) { atomicOr(&p.dbg[3], 1u << src); break; }
+                else if (now - t0 > p.ag_timeout_ns) {
+                  atomicOr(p.ag_err, 8u);
+                  break;
+                }
               }
             }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
             asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA loads below read what the peers wrote
             ag_ok_mask |= 1u << src;
           }
@@ -850,6 +856,9 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           ++nstore;
         }
       };
+      // Software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is packed, staged and handed to TMA
+      // (a chunk is latency-, not bandwidth-bound: ld -> wait -> 16 cvt -> 4 st.shared -> fence -> TMA issue).
+      uint32_t ra[32], rb[32];
       {
         uint32_t rs[kShared][32];
 #pragma unroll
@@ -860,15 +869,20 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         if (lane == 0) {
           if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
         }
+        tmem_ld32(tbase + (uint32_t)(chunk_col(kShared) * 32), ra);  // first private chunk: under the shared chunks' emit
 #pragma unroll
         for (int i = 0; i < kShared; ++i) emit(rs[i], chunk_col(i));
       }
 #pragma unroll
-      for (int i = kShared; i < kChunks; ++i) {
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)(chunk_col(i) * 32), r);
-        tmem_ld_wait();
-        emit(r, chunk_col(i));
+      for (int i = kShared; i < kChunks; i += 2) {
+        tmem_ld_wait();  // ra = chunk i
+        if (i + 1 < kChunks) tmem_ld32(tbase + (uint32_t)(chunk_col(i + 1) * 32), rb);
+        emit(ra, chunk_col(i));
+        if (i + 1 < kChunks) {
+          tmem_ld_wait();  // rb = chunk i + 1
+          if (i + 2 < kChunks) tmem_ld32(tbase + (uint32_t)(chunk_col(i + 2) * 32), ra);
+          emit(rb, chunk_col(i + 1));
+        }
       }
       if constexpr (RS) {
         // DEFERRED arrival: once this tile's stores are issued, the stores of the PREVIOUS tile have long LANDED in its
@@ -884,8 +898,17 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
             else asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.global;" ::: "memory");
             if (p.flags & 32u) {  // timing experiment: no arrival at all
-            } else if (p.flags & 16u) asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
-            else asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+            } else if (p.flags & 16u) {
+              asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+            } else if (rs.pull && !(p.flags & 64u)) {
+              // in-switch mode: the partial tile stays in THIS GPU's memory and the owner reads it through NVLink, i.e. out
+              // of this GPU's L2 -- a gpu-scope fence makes the (completed) TMA stores visible there; a system-scope release
+              // would also wait for this warp's previous arrival to be acknowledged over NVLink, one round trip per tile
+              asm volatile("fence.acq_rel.gpu;" ::: "memory");
+              asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+            } else {
+              asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+            }
           }
           prev_flag = rs.tile_flags[owner] + own_idx;
         }
@@ -908,7 +931,13 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
     if constexpr (RS) {
       if (lane == 0 && prev_flag != nullptr) {
         asm volatile("fence.proxy.async.global;" ::: "memory");
-        if (!(p.flags & 32u)) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+        if (p.flags & 32u) {
+        } else if (rs.pull && !(p.flags & 64u)) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+        } else {
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prev_flag) : "memory");
+        }
       }
     }
     if (WD && blockIdx.x == 0 && warp == 2 && lane == 0) {
@@ -1451,6 +1480,8 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     p.ag_rows = ex->ag_rows;
     p.ag_ticket = ex->ag_ticket;
     p.ag_tp = ex->ag_tp;
+    p.ag_err = ex->ag_err;
+    p.ag_timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
     for (int d = 0; d < ex->ag_tp && d < kMaxTp; ++d) p.ag_consumed[d] = ex->ag_consumed[d];
   }
   p.flags = (uint32_t)options().gemm_debug_flags;

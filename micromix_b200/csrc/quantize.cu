@@ -55,6 +55,9 @@ struct QuantParams {
   uint32_t* ag_issued;
   uint32_t* ag_arrived[kMaxTp];
   int ag_tp;
+  unsigned long long ag_timeout_ns;  // bound on the wait (option tp_timeout_ms): a lost peer must not hang the GPU
+  uint32_t* ag_err;                  // local error word of the tp context: bit 2 = this wait timed out
+  uint32_t ag_dbg;                   // timing experiments (option tp_debug >> 5)
   // GROUPED (Mixtral experts): rows are sorted by group, every 128-row block belongs to one group, and group g permutes
   // its rows with idx + g * K (same split for all groups).  grp_rowblk[row / 128] = group (device memory, written on the
   // stream by the router); a CTA rebuilds its scatter table when the group of its next item changes.
@@ -170,18 +173,36 @@ __device__ __forceinline__ uint32_t squeeze4_fp6(uint32_t w) {
 }
 
 // One row of a thread's 16 channels: 16 floats -> packed codes -> global memory (8 | 12 | 16 contiguous bytes).
+// MC (multicast destination): the codes are STAGED in shared memory -- `dst` is then a shared-memory address carried in a
+// pointer -- and leave later as whole 16-byte lines per lane (QuantKernel::copy_out): an NVLink multicast write of 4 or
+// 8 bytes costs a packet of its own, a warp's 512 contiguous bytes cost four.
 template <int FMT, bool MC>
 __device__ __forceinline__ void convert_store_row(const float (&f)[16], uint8_t* dst) {
-  if constexpr (FMT == 4) {
-    stg_v2<MC>(dst, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
+  if constexpr (MC) {
+    const uint32_t a = (uint32_t)(uintptr_t)dst;
+    if constexpr (FMT == 4) {
+      sts64(a, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
+    } else if constexpr (FMT == 6) {
+      const uint32_t y0 = squeeze4_fp6(cvt4_e3m2(&f[0])), y1 = squeeze4_fp6(cvt4_e3m2(&f[4]));
+      const uint32_t y2 = squeeze4_fp6(cvt4_e3m2(&f[8])), y3 = squeeze4_fp6(cvt4_e3m2(&f[12]));
+      sts32(a, __byte_perm(y0, y1, 0x4210));
+      sts32(a + 4, __byte_perm(y1, y2, 0x5421));
+      sts32(a + 8, __byte_perm(y2, y3, 0x6542));
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(cvt4_e4m3(&f[0])), "r"(cvt4_e4m3(&f[4])),
+                   "r"(cvt4_e4m3(&f[8])), "r"(cvt4_e4m3(&f[12]))
+                   : "memory");
+    }
+  } else if constexpr (FMT == 4) {
+    stg_v2(dst, cvt8_e2m1(&f[0]), cvt8_e2m1(&f[8]));
   } else if constexpr (FMT == 6) {
     const uint32_t y0 = squeeze4_fp6(cvt4_e3m2(&f[0])), y1 = squeeze4_fp6(cvt4_e3m2(&f[4]));
     const uint32_t y2 = squeeze4_fp6(cvt4_e3m2(&f[8])), y3 = squeeze4_fp6(cvt4_e3m2(&f[12]));
-    stg_b32<MC>(dst, __byte_perm(y0, y1, 0x4210));
-    stg_b32<MC>(dst + 4, __byte_perm(y1, y2, 0x5421));
-    stg_b32<MC>(dst + 8, __byte_perm(y2, y3, 0x6542));
+    stg_b32(dst, __byte_perm(y0, y1, 0x4210));
+    stg_b32(dst + 4, __byte_perm(y1, y2, 0x5421));
+    stg_b32(dst + 8, __byte_perm(y2, y3, 0x6542));
   } else {
-    stg_v4<MC>(dst, cvt4_e4m3(&f[0]), cvt4_e4m3(&f[4]), cvt4_e4m3(&f[8]), cvt4_e4m3(&f[12]));
+    stg_v4(dst, cvt4_e4m3(&f[0]), cvt4_e4m3(&f[4]), cvt4_e4m3(&f[8]), cvt4_e4m3(&f[12]));
   }
 }
 
@@ -241,6 +262,7 @@ struct UnitPtrs {
   uint32_t ka512;   // scale bytes of one 128-row block of the segment: katoms * 512
   uint32_t q2;      // log2floor(QMAX) in both 16-bit lanes: 2 | 4 | 8
   uint32_t add2;    // 127 - mantissa threshold (0x40 for QMAX = 6 = 1.5 * 4, 0x60 for 28 | 448 = 1.75 * 2^n) in both lanes
+  uint32_t stoff;   // MC: byte offset of the unit's codes inside a STAGED row (the three segments' packed rows back to back)
 };
 
 // R rows per item, NLD = 16-byte chunks per thread and row (NLD * T * 8 >= K), NP = compute passes
@@ -298,6 +320,7 @@ struct QuantKernel {
     up.ka512 = (uint32_t)p.katoms[sg] * 512u;
     up.q2 = (fmt == 4) ? 0x00020002u : ((fmt == 6) ? 0x00040004u : 0x00080008u);
     up.add2 = (fmt == 4) ? 0x003f003fu : 0x001f001fu;
+    up.stoff = cx.qoff + (sg == 0 ? 0u : (uint32_t)p.rowbytes[0]) + (sg == 2 ? (uint32_t)p.rowbytes[1] : 0u);
     return up;
   }
 
@@ -403,7 +426,8 @@ struct QuantKernel {
   // lanes past the last unit compute on unit 0 and store nothing.
   template <bool FULL>
   static __device__ __forceinline__ void compute_unit(const UnitCtx& cx, const UnitPtrs& up, uint32_t xs_a, int row0,
-                                                      int nvalid, uint32_t wp_a = 0, const float* rinv = nullptr) {
+                                                      int nvalid, uint32_t wp_a = 0, const float* rinv = nullptr,
+                                                      uint32_t stage_a = 0, uint32_t stage_row = 0) {
     const uint32_t meta = cx.meta;
     const bool active = (meta & 64u) != 0;
     const int fmt = (int)(meta & 15u);
@@ -464,21 +488,21 @@ struct QuantKernel {
 
     // ---- scale bytes: the even lane of the pair writes the R bytes of its group (one per row, 4 bytes apart)
     if constexpr (MC) {
-      // multicast stores are 32 bits wide at least: lanes 8q .. 8q+7 hold the four groups of ONE scale atom column
-      // (128 channels, same segment: segments are multiples of 128), the four bytes of a row are contiguous -- lane 8q
-      // collects them from lanes 8q+2, +4, +6 and writes one word per row
+      // multicast stores should be as wide as possible (every one is an NVLink packet): lanes 8q .. 8q+7 hold the four
+      // groups of ONE scale atom (128 channels, same segment: segments are multiples of 128); the item's two rows
+      // l + 64h and l + 64h + 32 own bytes [8h, 8h + 8) of the atom's 16-byte line for row l -- lane 8q collects the four
+      // groups from lanes 8q+2, +4, +6 and writes those 8 bytes with one store
+      static_assert(RW == 1, "two rows per item");
       const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
       uint8_t* d = up.sfp + sfoff;
-#pragma unroll
-      for (int k = 0; k < RW; ++k) {
-        const uint32_t v1 = __shfl_down_sync(0xffffffffu, sfb[k], 2), v2 = __shfl_down_sync(0xffffffffu, sfb[k], 4);
-        const uint32_t v3 = __shfl_down_sync(0xffffffffu, sfb[k], 6);
-        const uint32_t lo01 = __byte_perm(sfb[k], v1, 0x0040), lo23 = __byte_perm(v2, v3, 0x0040);  // row 2k : bytes 0
-        const uint32_t hi01 = __byte_perm(sfb[k], v1, 0x0062), hi23 = __byte_perm(v2, v3, 0x0062);  // row 2k+1: bytes 2
-        if ((meta & 64u) && (threadIdx.x & 7) == 0) {
-          stg_b32<true>(d + 8 * k, __byte_perm(lo01, lo23, 0x5410));
-          if (FULL || 2 * k + 1 < nvalid) stg_b32<true>(d + 8 * k + 4, __byte_perm(hi01, hi23, 0x5410));
-        }
+      const uint32_t v1 = __shfl_down_sync(0xffffffffu, sfb[0], 2), v2 = __shfl_down_sync(0xffffffffu, sfb[0], 4);
+      const uint32_t v3 = __shfl_down_sync(0xffffffffu, sfb[0], 6);
+      const uint32_t lo01 = __byte_perm(sfb[0], v1, 0x0040), lo23 = __byte_perm(v2, v3, 0x0040);  // first row : bytes 0
+      const uint32_t hi01 = __byte_perm(sfb[0], v1, 0x0062), hi23 = __byte_perm(v2, v3, 0x0062);  // second row: bytes 2
+      if ((meta & 64u) && (threadIdx.x & 7) == 0) {
+        const uint32_t w0 = __byte_perm(lo01, lo23, 0x5410), w1 = __byte_perm(hi01, hi23, 0x5410);
+        if (FULL || nvalid > 1) stg_v2<true>(d, w0, w1);
+        else stg_b32<true>(d, w0);
       }
     } else if (meta & 128u) {
       const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
@@ -492,12 +516,35 @@ struct QuantKernel {
 
     // ---- convert + store: 16 codes per row, contiguous bytes
     uint8_t* dst = up.qp + (uint64_t)(uint32_t)row0 * up.rbytes;
-    const int64_t rstride = (int64_t)(32u * up.rbytes);
+    int64_t rstride = (int64_t)(32u * up.rbytes);
+    if constexpr (MC) {  // staged: row j of the item at stage_a + j * stage_row
+      dst = reinterpret_cast<uint8_t*>((uintptr_t)(stage_a + up.stoff));
+      rstride = (int64_t)stage_row;
+    }
     const int nstore = active ? nvalid : 0;
     if (FULL && !active) {
     } else if (fmt == 4) convert_store<4, R, FULL, MC>(g, mult, dst, rstride, nstore);
     else if (fmt == 6) convert_store<6, R, FULL, MC>(g, mult, dst, rstride, nstore);
     else convert_store<8, R, FULL, MC>(g, mult, dst, rstride, nstore);
+  }
+
+  // MC: the staged codes of one item -> the multicast address, 16 bytes per lane, a warp writes 512 contiguous bytes
+  static __device__ __forceinline__ void copy_out(const QuantParams& p, uint32_t stage_a, uint32_t stage_row, int row0,
+                                                  int nvalid, int t, int T) {
+    const uint32_t rb0 = (uint32_t)p.rowbytes[0], rb1 = (uint32_t)p.rowbytes[1], rb2 = (uint32_t)p.rowbytes[2];
+    const uint32_t n16 = stage_row >> 4;
+    for (int j = 0; j < nvalid; ++j) {
+      const int64_t row = row0 + 32 * j;
+      for (uint32_t c = (uint32_t)t; c < n16; c += (uint32_t)T) {
+        const uint32_t o = c << 4;
+        const uint4 v = lds128(stage_a + (uint32_t)j * stage_row + o);
+        uint8_t* g;
+        if (o < rb0) g = p.q[0] + row * rb0 + o;
+        else if (o < rb0 + rb1) g = p.q[1] + row * rb1 + (o - rb0);
+        else g = p.q[2] + row * rb2 + (o - rb0 - rb1);
+        stg_v4<true>(g, v.x, v.y, v.z, v.w);
+      }
+    }
   }
 };
 
@@ -508,15 +555,25 @@ struct QuantKernel {
 // item n-1, which every thread has left before it passes item n's barrier).
 // NORM: ss_a = this item's warp sums of squares [R][128] fp32 (double-buffered with xs), wp_unit = this thread's 16
 // permuted RMSNorm weights.
-template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT, bool NORM>
+// MC: stg_a = the two staging buffers of the packed codes; the PREVIOUS item's codes leave right after this item's barrier
+// (every thread has finished the previous compute by then, and the buffer is not written again before the next barrier).
+template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT, bool NORM, bool MC>
 __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_t* xt, int row0, int n, int t, int T, int K8,
                                              int nunits, uint32_t xs_a, uint32_t tab_a, uint32_t ctx_a,
                                              uint4 (&pre)[NLD][R], int* s_next, const UnitCtx& ctx0, const UnitPtrs& up0,
-                                             uint32_t ss_a, uint32_t wp_unit) {
+                                             uint32_t ss_a, uint32_t wp_unit, uint32_t stg_a, uint32_t stage_row,
+                                             int& prev_row0, int& prev_nvalid) {
   const int rows = (int)p.rows;
   const int nvalid = FULL ? R : min(R, (rows - 1 - row0) / 32 + 1);
   QK::template scatter<FULL, EXACT>(nvalid, t, T, K8, xs_a, tab_a, pre, ss_a);
   __syncthreads();
+  const uint32_t stage_cur = stg_a + (uint32_t)(n & 1) * (uint32_t)R * stage_row;
+  if constexpr (MC) {
+    if (prev_row0 >= 0)
+      QK::copy_out(p, stg_a + (uint32_t)((n + 1) & 1) * (uint32_t)R * stage_row, stage_row, prev_row0, prev_nvalid, t, T);
+    prev_row0 = row0;
+    prev_nvalid = nvalid;
+  }
   float rinv[R];
   if constexpr (NORM) {
     // the top seven levels of the tree over the chunk index: 128 warp sums per row (unused ones are zero), four
@@ -542,7 +599,7 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
   if (t == 0) claimed = atomicAdd(p.sched, 1u);
 
   if constexpr (NP == 1) {
-    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid, wp_unit, rinv);
+    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid, wp_unit, rinv, stage_cur, stage_row);
   } else {
 #pragma unroll
     for (int ps = 0; ps < NP; ++ps) {
@@ -567,7 +624,7 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   static_assert(R == 4 || R == 2, "rows per item");
   static_assert(NBUF == 1 || (NBUF == 2 && TABMODE != 2), "absolute table addresses cannot follow a second xs buffer");
   static_assert(!NORM || NP == 1, "the fused RMSNorm keeps a thread's weights addressable by thread index");
-  static_assert(!MC || R == 2, "the multicast scale-byte path is written for two rows per item");
+  static_assert(!MC || (R == 2 && NP == 1), "the multicast path is written for two rows per item, one unit per thread");
   using QK = QuantKernel<R, NLD, NP, TABMODE, NORM, MC>;
   const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
   extern __shared__ __align__(128) uint8_t smem[];
@@ -580,6 +637,11 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   const uint32_t ctx_a = xs_a + NBUF * xs_bytes;  // NP > 1 only
   const uint32_t wp_a = ctx_a;                    // NORM only (NP == 1): bf16 weights in permuted order [K]
   const uint32_t ss_a = wp_a + (uint32_t)K * 2u;  // NORM only: warp sums of squares [NBUF][R][128] fp32
+  // MC only: two staging buffers of R packed rows (the three segments back to back), behind everything else
+  const uint32_t stage_row = (uint32_t)(p.rowbytes[0] + p.rowbytes[1] + p.rowbytes[2]);
+  const uint32_t stg_a = ctx_a + (NP > 1 ? (uint32_t)(NP * T * 16) : 0u) +
+                         (NORM ? (uint32_t)K * 2u + (uint32_t)(NBUF * R * 512) : 0u);
+  int prev_row0 = -1, prev_nvalid = 0;
   const int t = threadIdx.x;
   const int rows = (int)p.rows;
 
@@ -660,14 +722,19 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ag_consumed) : "memory");
         if ((int32_t)(seen - need) >= 0) break;
         __nanosleep(64);
-        if ((it & 1023u) == 0) {  // bounded (10 s): a lost peer must not hang the GPU
+        if ((it & 1023u) == 0) {  // bounded: a lost peer must not hang the GPU
           unsigned long long now;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
           if (t0 == 0) t0 = now;
-          else if (now - t0 > 10000000000ull) break;
+          else if (now - t0 > p.ag_timeout_ns) {
+            atomicOr(p.ag_err, 4u);
+            break;
+          }
         }
       }
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      // acquire WITHOUT a fence (fence.acq_rel.sys = MEMBAR.ALL.SYS + ERRBAR: ~8 us here, with the first rows' loads in
+      // flight and the whole CTA waiting at the barrier below -- profiles/r02_gather_membar_stalls.txt)
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ag_consumed) : "memory");
     }
   }
   __syncthreads();
@@ -687,14 +754,19 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
     const uint32_t xs_cur = xs_a + ((NBUF == 2 && (n & 1)) ? xs_bytes : 0u);
     const uint32_t ss_cur = ss_a + ((NBUF == 2 && (n & 1)) ? (uint32_t)(R * 512) : 0u);
     if (row0 + 32 * (R - 1) < rows)
-      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT, NORM>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT, NORM, MC>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid);
     else
-      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM, MC>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid);
     ++n;
   }
   if constexpr (MC) {
+    __syncthreads();                      // the last item's codes are staged
+    if (prev_row0 >= 0) QK::copy_out(p, stg_a + (uint32_t)((n + 1) & 1) * (uint32_t)R * stage_row, stage_row, prev_row0, prev_nvalid, t, T);
     __syncthreads();                      // every thread's multicast stores are issued ...
-    if (t == 0) __threadfence_system();   // ... and performed at system scope before this CTA counts as finished
+    if (t == 0) {                         // ... and performed at system scope before this CTA counts as finished
+      if (p.ag_dbg & 1u) __threadfence();  // (timing experiment: device scope only -- NOT sufficient for peer visibility)
+      else __threadfence_system();
+    }
   }
   // the last CTA to leave resets the schedule for the next launch that uses this slot
   if (t == 0) {
@@ -722,7 +794,8 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
   constexpr int TABW = (TABMODE == 2) ? 4 : 2;
   const size_t smem = ((size_t)(p.K * TABW + 127) & ~(size_t)127) + (size_t)NBUF * p.K * 2 * R + (NP > 1 ? (size_t)NP * T * 16 : 0) +
-                      (NORM ? (size_t)p.K * 2 + (size_t)NBUF * R * 512 : 0);
+                      (NORM ? (size_t)p.K * 2 + (size_t)NBUF * R * 512 : 0) +
+                      (MC ? (size_t)2 * R * (size_t)(p.rowbytes[0] + p.rowbytes[1] + p.rowbytes[2]) : 0);
   const int64_t xs_bytes = (int64_t)p.K * 2 * R;
   if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (TABMODE == 0 && xs_bytes > 65536) ||
       (TABMODE == 1 && xs_bytes > 4 * 65536)) {
@@ -841,6 +914,9 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
     p.ag_consumed = ag->consumed;
     p.ag_issued = ag->issued;
     p.ag_tp = ag->tp;
+    p.ag_timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
+    p.ag_err = ag->err;
+    p.ag_dbg = (uint32_t)(options().tp_debug >> 5);
     for (int d = 0; d < ag->tp && d < kMaxTp; ++d) p.ag_arrived[d] = ag->arrived[d];
   }
   p.grp_rowblk = grp_rowblk;

@@ -59,7 +59,9 @@ constexpr int64_t kOffTileFlags = 0;                 // u32 [2][kFlagCap]
 constexpr int64_t kOffConsumed = 2 * kFlagCap * 4;   // u32 [2][kFlagCap]
 constexpr int64_t kOffDone = 4 * kFlagCap * 4;       // u32 [2], 128 bytes apart
 constexpr int64_t kOffTicket = kOffDone + 256;       // u32 [2], 128 bytes apart
-constexpr int64_t kOffErr = kOffTicket + 256;        // u32: 1 = tile wait timed out, 2 = final wait timed out
+constexpr int64_t kOffErr = kOffTicket + 256;        // u32: 1 = tile wait timed out, 2 = final wait timed out,
+                                                     //      4 = gather: consumers never released the channel, 8 = gather:
+                                                     //      a source rank's rows never arrived
 constexpr int64_t kOffDoneBase = kOffErr + 128;      // u32 [2], 128 bytes apart: value of `done` before the current call
 // sequence-parallel gather channel (all counters only ever count up)
 constexpr int64_t kOffAgArrived = kOffDoneBase + 256;            // u32 [kMaxTp], 128 bytes apart: gathers landed from rank s
@@ -143,13 +145,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// (polls are RELAXED loads -- an acquire per poll is a system-scope fence per poll on an SM that is also running the
-// GEMM's epilogue -- and one acquire fence follows the successful poll)
+// (polls are RELAXED loads; the successful poll is followed by ONE ld.acquire.sys of the same word -- LDG.STRONG.SYS +
+// an L1 invalidate.  A fence.acq_rel.sys here is MEMBAR.ALL.SYS + ERRBAR: measured at several microseconds per call with
+// loads in flight, on the one thread the whole CTA is waiting for -- profiles/r02_gather_membar_stalls.txt)
 __device__ bool spin_until(const uint32_t* flag, uint32_t target, unsigned long long timeout_ns) {
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {
     if ((int32_t)(ld_relaxed_sys(flag) - target) >= 0) {  // wrap-safe: `done` counts up for the life of the workspace
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      (void)v;
       return true;
     }
     __nanosleep(64);
@@ -666,17 +671,19 @@ MMX_API int mmx_tp_quantize_allgather(void* ctx, const void* x_shard, int64_t M,
   uint8_t* q[3];
   uint8_t* sf[3];
   uint8_t* mc_base = c->mc + c->L.ag_off;
+  if (options().tp_debug & 16) mc_base = c->ws[c->rank] + c->L.ag_off;  // timing experiment: stores stay on this rank
+  uint8_t* me = c->ws[c->rank];
+  QuantGather ag;
+  memset(&ag, 0, sizeof(ag));
   for (int i = 0; i < 3; ++i) {
     // this rank's rows start at row0 (a multiple of 256): whole packed rows and whole 128-row scale blocks
     q[i] = ks[i] ? mc_base + v.off[i] + row0 * ((int64_t)ks[i] * bits[i] / 8) : nullptr;
     sf[i] = ks[i] ? mc_base + v.off[3 + i] + (row0 / 128) * (int64_t)(ks[i] / 128) * 512 : nullptr;
   }
-  uint8_t* me = c->ws[c->rank];
-  QuantGather ag;
-  memset(&ag, 0, sizeof(ag));
   ag.consumed = reinterpret_cast<const uint32_t*>(me + kOffAgConsumed);
   ag.issued = reinterpret_cast<uint32_t*>(me + kOffAgIssued);
   ag.tp = c->tp;
+  ag.err = reinterpret_cast<uint32_t*>(me + kOffErr);
   for (int d = 0; d < c->tp; ++d)
     ag.arrived[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffAgArrived + 128 * c->rank);
   const int fmt[3] = {4, 6, 8};
@@ -704,6 +711,7 @@ MMX_API int mmx_tp_matmul_gathered(void* ctx, const uint8_t* bn, const uint8_t* 
   ex.ag_rows = (int)mmx_tp_shard_rows(M, c->tp);
   ex.ag_ticket = reinterpret_cast<uint32_t*>(me + kOffAgTicket);
   ex.ag_tp = c->tp;
+  ex.ag_err = reinterpret_cast<uint32_t*>(me + kOffErr);
   for (int d = 0; d < c->tp; ++d) ex.ag_consumed[d] = reinterpret_cast<uint32_t*>(c->ws[d] + kOffAgConsumed);
   return matmul_impl(KN ? local + v.off[0] : nullptr, bn, KS ? local + v.off[1] : nullptr, bs, KO ? local + v.off[2] : nullptr,
                      bo, KN ? local + v.off[3] : nullptr, sfbn, KS ? local + v.off[4] : nullptr, sfbs,

@@ -62,7 +62,8 @@ def route_tables(sel: torch.Tensor, local_slot: torch.Tensor, n_local: int, tile
     key = local_slot[flat]                                    # [T*k], n_local = "not mine"
     order = torch.argsort(key, stable=True)
     ks = key[order]
-    counts = torch.bincount(key, minlength=n_local + 1)[:n_local]
+    # (not torch.bincount: it reads the maximum back to the host -- a synchronisation, and illegal during graph capture)
+    counts = torch.zeros(n_local + 1, dtype=torch.int64, device=dev).scatter_add_(0, key, torch.ones_like(key))[:n_local]
     padded = (counts + tile - 1) // tile * tile
     ends_p = torch.cumsum(padded, 0)
     starts_p = ends_p - padded

@@ -111,22 +111,44 @@ def qwen_tp(args, rank, world, dev):
     idx, p6, p8 = S.make_calibration(cfg, 0)
     b, s = max(1, args.tokens // 2048), 2048
     ws = None
+    sp = bool(args.sp) and world > 1 and args.tp_reduce == "fused"
     if world > 1 and args.tp_reduce == "fused":
         from micromix_b200.parallel_utils import PeerWorkspace
-        ws = PeerWorkspace(b * s, cfg["hidden_size"], group=group, device=dev)
-    q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws)
+        ws = PeerWorkspace(b * s, cfg["hidden_size"], group=group, device=dev,
+                           gather=(b * s, cfg["hidden_size"]) if sp else None)
+    q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws, sequence_parallel=sp,
+                           fused=bool(args.fused))
     del layer
     torch.cuda.empty_cache()
     b, s = max(1, args.tokens // 2048), 2048
     g = torch.Generator(device=dev).manual_seed(721)
     x0 = torch.randn(b, s, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
     pos = S.rope_tables(cfg, b, s, dev)
-    ms, launches = timed(lambda: q(x0, position_embeddings=pos), args.iters, 3, world, dev)
+    if sp:
+        lo, hi = ws.shard_range(b * s)
+        x0 = x0.reshape(b * s, -1)[lo:hi].unsqueeze(0).contiguous()  # this rank's token rows
+    fwd = lambda: q(x0, position_embeddings=pos)
+    ms, launches = timed(fwd, args.iters, 3, world, dev)
+    # the same forward replayed from a CUDA graph: no Python / launch overhead between the layer's ~40 kernels
+    ms_graph = None
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fwd()
+        torch.cuda.synchronize()
+        ms_graph, _ = timed(graph.replay, max(args.iters, 5), 2, world, dev)
+    except Exception as e:  # noqa: BLE001
+        ms_graph = f"capture failed: {e!r}"[:120]
     tokens = b * s
+    how = "NCCL all-reduce" if ws is None else (f"sequence parallel: fused GEMM->reduce-scatter + multicast all-gather of packed "
+                                                 f"codes ({ws.mode})" if sp else f"fused GEMM->all-reduce ({ws.mode})")
+    best = ms_graph if isinstance(ms_graph, float) else ms
     return {"config": f"Qwen2.5-32B-shaped decoder layer, {tokens} tokens, tensor parallel {world} (column qkv/gate_up, "
-                      f"row o/down + {'fused GEMM->all-reduce (' + ws.mode + ')' if ws is not None else 'NCCL all-reduce'})",
-            "ms_per_layer": ms, "tokens_per_s_per_layer": tokens / ms * 1e3,
-            "linear_tflops": layer_flops(cfg, tokens) / ms / 1e9, "n_gpus": world, "mmx_launches_per_forward": launches}
+                      f"row o/down + {how})", "ms_per_layer": ms, "ms_per_layer_cuda_graph": ms_graph,
+            "tokens_per_s_per_layer": tokens / best * 1e3, "linear_tflops": layer_flops(cfg, tokens) / best / 1e9,
+            "n_gpus": world, "mmx_launches_per_forward": launches, "tp_status": ws.status() if ws is not None else None}
 
 
 def mixtral_ep(args, rank, world, dev):
@@ -135,17 +157,48 @@ def mixtral_ep(args, rank, world, dev):
     group = dist.group.WORLD if world > 1 else None
     layer = S.make_layer(cfg, dev, seed=0, moe=True)
     idx, p6, p8 = S.make_calibration(cfg, 0, moe=True)
-    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, ep_group=group, fused=args.fused)
+    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, ep_group=group, fused=args.fused,
+                                 grouped=None if not args.loop else False)
     del layer
     torch.cuda.empty_cache()
     tokens = args.tokens
     g = torch.Generator(device=dev).manual_seed(721)
     x0 = torch.randn(1, tokens, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
     ms, launches = timed(lambda: blk(x0), args.iters, 3, world, dev)
+    ms_graph = None
+    if blk.grouped:  # no host synchronisation anywhere: the whole block is one CUDA graph
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                blk(x0)
+            torch.cuda.synchronize()
+            ms_graph, _ = timed(graph.replay, max(args.iters, 5), 2, world, dev)
+        except Exception as e:  # noqa: BLE001
+            ms_graph = f"capture failed: {e!r}"[:120]
+    best = ms_graph if isinstance(ms_graph, float) else ms
     flops = 2.0 * tokens * cfg["num_experts_per_tok"] * 3 * cfg["hidden_size"] * cfg["intermediate_size"]
-    return {"config": f"Mixtral-8x7B expert FFN (8 experts, top-2), {tokens} tokens, expert parallel {world}",
-            "ms_per_block": ms, "tokens_per_s": tokens / ms * 1e3, "expert_tflops": flops / ms / 1e9, "n_gpus": world,
-            "mmx_launches_per_forward": launches, "fused_act": bool(args.fused)}
+    out = {"config": f"Mixtral-8x7B expert FFN (8 experts, top-2), {tokens} tokens, expert parallel {world}",
+           "path": "grouped (one quantize + one GEMM launch per projection, fused token gather, combine kernel)" if blk.grouped
+           else "python loop over experts (the reference's op sequence)",
+           "ms_per_block": ms, "ms_per_block_cuda_graph": ms_graph, "tokens_per_s": tokens / best * 1e3,
+           "expert_tflops": flops / best / 1e9, "expert_tflops_per_gpu": flops / best / 1e9 / world, "n_gpus": world,
+           "mmx_launches_per_forward": launches, "fused_act": bool(args.fused)}
+    try:  # against the measured MX tensor-pipe peak of this GPU (burst), 5:2:1 split
+        import ctypes
+        lib = mixedgemm._lib.load()
+        pk = []
+        for kind in (0, 1, 2):
+            t = ctypes.c_double()
+            lib.mmx_debug_mma_peak(kind, 2000, 0, 3, ctypes.byref(t), None)
+            pk.append(t.value)
+        peak = 1.0 / (0.625 / pk[0] + 0.25 / pk[1] + 0.125 / pk[2])
+        out["mx_peak_burst_tflops_split_weighted"] = peak
+        out["expert_roofline_frac_per_gpu"] = out["expert_tflops_per_gpu"] / peak
+    except Exception:  # noqa: BLE001
+        pass
+    return out
 
 
 def main():
@@ -157,6 +210,8 @@ def main():
     ap.add_argument("--tokens", type=int, default=16384)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--tp-reduce", default="fused", choices=["fused", "nccl"], help="qwen_tp: row-parallel reduction")
+    ap.add_argument("--loop", action="store_true", help="mixtral_ep: the per-expert Python loop instead of the grouped path")
+    ap.add_argument("--sp", action="store_true", help="qwen_tp: sequence-parallel layer (reduce-scatter + all-gather of codes)")
     ap.add_argument("--fused", action="store_true", help="prefill: RMSNorm and SiLU*up run inside the quantizers (QDecoderLayer(fused=True))")
     args = ap.parse_args()
     rank, world, dev = setup()
