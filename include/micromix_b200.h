@@ -230,15 +230,23 @@ int mmx_tp_matmul_gathered(void* ctx, const uint8_t* bn, const uint8_t* bs, cons
  *       same (KN, KS, KO) for all), grp_rowblk int32 [ceil(M/128)] in DEVICE memory = group of each 128-row block
  *       (padding blocks carry any valid group); row_src int32 [M] (optional, DEVICE memory): sorted row r is row
  *       row_src[r] of x, i.e. the gather of the routed tokens is fused into the quantizer's loads (padding rows carry any
- *       valid row).  Outputs as mmx_reorder_quantize_x.
+ *       valid row); rows_dev int32 (optional, DEVICE memory): rows that actually exist, a multiple of 128 -- row blocks
+ *       past it are not touched.  Outputs as mmx_reorder_quantize_x.
  *   mmx_matmul_grouped               B tensors = the groups' weights stacked on N ([groups*N, Kseg*bits/8], scales likewise);
  *       grp_mblk int32 [M / tile_rows] in DEVICE memory = group of each m-tile or -1 (padding tile: skipped);
- *       tile_rows = 256 (CTA pairs) or 128; C bf16 [M, N].  No host synchronisation anywhere: the tables are written on
- *       the stream by the router.
+ *       tile_rows = 256 (CTA pairs) or 128; rows_dev int32 (optional, DEVICE memory) = rows of A that exist (whole
+ *       m-tiles): the tile walk stops there; C bf16 [M, N].  No host synchronisation anywhere: the tables are written
+ *       on the stream by the router.
  */
 int mmx_reorder_quantize_x_grouped(const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk,
-                                   const int32_t* row_src, int KN, int KS, int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo,
-                                   uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+                                   const int32_t* row_src, const int32_t* rows_dev, int KN, int KS, int KO, uint8_t* xn,
+                                   uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+/* mmx_activate_quantize_x_strided on the first *rows_dev rows only (rows_dev: int32 in DEVICE memory, a multiple of 128;
+ * M = the static upper bound the buffers were sized for): the expert-sorted matrix of the grouped path is padded to a
+ * bound known on the host, its used length only on the device. */
+int mmx_activate_quantize_x_rows(const void* a, const void* b, int64_t ld, int64_t M, const int32_t* rows_dev, int KN, int KS,
+                                 int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
+                                 void* stream);
 /* out[t] = sum over the top_k slots of token t, in ascending expert order, of bf16(y[row[t,s]] * w[t,s]) with a bf16
  * rounding after every add -- exactly what the reference's per-expert `index_add_` loop leaves in its bf16 buffer
  * (model/qMixtralLayer.py:446-450).  row int32 [T, top_k] = row of y holding the pair's expert output, or -1 (expert not on
@@ -248,7 +256,18 @@ int mmx_moe_combine(const void* y, const int32_t* row, const int32_t* expert, co
 int mmx_matmul_grouped(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                        const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
                        const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
-                       int groups, int tile_rows, const int32_t* grp_mblk, void* c, void* stream);
+                       int groups, int tile_rows, const int32_t* grp_mblk, const int32_t* rows_dev, void* c, void* stream);
+
+/*
+ * Rotary position embedding IN PLACE on the first heads*head_dim columns of every row of y (bf16 [M, ld]) -- the q and k
+ * columns of the fused qkv GEMM output.  Extension: the reference keeps RoPE in PyTorch (model/qLlamaLayer.py:25-54,
+ * 271-272); same arithmetic and the same bf16 roundings as HF's apply_rotary_pos_emb:
+ *   y[.., :d/2] = bf16(bf16(x1*cos1) + bf16(-x2*sin1)),   y[.., d/2:] = bf16(bf16(x2*cos2) + bf16(x1*sin2)).
+ * cos, sin bf16 [S, head_dim]; row m uses table row m % S (S = seq_len for a batch of equal-length prefills, S = M for a
+ * table that is already per token).
+ */
+int mmx_rope_inplace(void* y, int64_t ld, int64_t M, int heads, int head_dim, const void* cos, const void* sin, int64_t S,
+                     void* stream);
 
 /* Tensor-pipe peak probe (measurement tool behind bench.py's roofline denominator): every SM issues `stages` x 4
  * back-to-back block-scaled MMAs (M=128, N=256) on shared-memory-resident operands; kind 0 = kind::mxf4 (K=64),

@@ -48,9 +48,11 @@ SYMBOLS = {
     "mmx_tp_quantize_allgather": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, ctypes.c_float,
                                          ctypes.POINTER(_vp), _vp]),
     "mmx_tp_matmul_gathered": (_i32, [_vp] + [_vp] * 6 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "mmx_reorder_quantize_x_grouped": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_reorder_quantize_x_grouped": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_activate_quantize_x_rows": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32] + [_vp] * 7),
+    "mmx_rope_inplace": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),
     "mmx_moe_combine": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "mmx_matmul_grouped": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_matmul_grouped": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mmx_debug_mma_peak": (_i32, [_i32, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double)]),
     "mmx_launch_count": (_i64, []),

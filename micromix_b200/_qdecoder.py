@@ -68,17 +68,21 @@ class FusedQLinear(nn.Module):
         self.in_features, self.out_features = weight.shape[1], weight.shape[0]
 
     @torch.no_grad()
-    def forward(self, x, norm=None):
-        """norm = (weight bf16 [K], eps): x is the UN-normalised input and RMSNorm runs inside the quantizer."""
+    def forward_whole(self, x, norm=None):
+        """The concatenated output [b, s, sum(splits)] (one GEMM); norm = (weight bf16 [K], eps): x is the UN-normalised
+        input and RMSNorm runs inside the quantizer."""
         if norm is None:
-            y = self.inner(x)
-        else:
-            lin = self.inner
-            bsz, q_len, _ = x.shape
-            a = mixedgemm.rmsnorm_quantize_x(x.reshape(bsz * q_len, -1).contiguous(), norm[0], norm[1], lin.reorder_index,
-                                             lin.p4_num, lin.p6_num, lin.p8_num)
-            y = mixedgemm.matmul(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS, a[5], lin.SFBO,
-                                 bias=lin.bias).reshape(bsz, q_len, -1)
+            return self.inner(x)
+        lin = self.inner
+        bsz, q_len, _ = x.shape
+        a = mixedgemm.rmsnorm_quantize_x(x.reshape(bsz * q_len, -1).contiguous(), norm[0], norm[1], lin.reorder_index,
+                                         lin.p4_num, lin.p6_num, lin.p8_num)
+        return mixedgemm.matmul(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS, a[5], lin.SFBO,
+                                bias=lin.bias).reshape(bsz, q_len, -1)
+
+    @torch.no_grad()
+    def forward(self, x, norm=None):
+        y = self.forward_whole(x, norm)
         return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
 
     @torch.no_grad()
@@ -86,12 +90,16 @@ class FusedQLinear(nn.Module):
         """Sequence-parallel form: x_shard = THIS rank's rows of the [M, K] activation.  The rank quantizes only those
         (RMSNorm fused when `norm` is given), the packed codes are multicast into every rank's gather channel, and the
         column-parallel GEMM runs on the gathered operand -> [M, N/tp] splits."""
+        y = self.forward_gathered_whole(x_shard, M, workspace, norm)
+        return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
+
+    @torch.no_grad()
+    def forward_gathered_whole(self, x_shard, M, workspace, norm=None):
         lin = self.inner
         a = workspace.quantize_allgather(x_shard, M, lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num, norm=norm)
         del a  # (the GEMM reads the channel directly)
-        y = workspace.matmul_gathered(M, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), lin.p4_num, lin.p6_num,
-                                      lin.p8_num, bias=lin.bias)
-        return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
+        return workspace.matmul_gathered(M, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), lin.p4_num, lin.p6_num,
+                                         lin.p8_num, bias=lin.bias)
 
 
 def build_input_group(linears, keys, p8_nums, p6_nums, reorder_index, row_slices=None):
@@ -146,6 +154,23 @@ def quantize_int_group(w, nbits, group_size):
     return w.reshape(shape)
 
 
+def rope_tables_2d(position_embeddings, bsz, q_len, head_dim):
+    """(cos, sin) as contiguous bf16 [S, d] tables for mixedgemm.rope_inplace (row m of the flattened [b*s] tokens uses table
+    row m % S), or None when the tables do not have that form (then RoPE stays in torch)."""
+    cos, sin = position_embeddings
+    if cos.dtype != torch.bfloat16 or not cos.is_cuda or cos.shape != sin.shape or cos.dim() != 3 or cos.shape[-1] != head_dim:
+        return None
+    if cos.shape[1] != q_len or cos.shape[0] not in (1, bsz):
+        return None
+    if cos.shape[0] == 1 or (cos.stride(0) == 0 and sin.stride(0) == 0):  # one table for the whole batch (prefill)
+        c, s_ = cos[0], sin[0]
+    else:
+        c, s_ = cos.reshape(bsz * q_len, head_dim), sin.reshape(bsz * q_len, head_dim)
+    if not (c.is_contiguous() and s_.is_contiguous()) or c.data_ptr() % 16 or s_.data_ptr() % 16:
+        return None
+    return c, s_
+
+
 def apply_rope(q, k, cos, sin):
     """q, k: [b, heads, s, d]; cos, sin: [b, s, d] (HF convention: halves rotated, qLlamaLayer.py:25-54)."""
     cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
@@ -197,20 +222,39 @@ class QAttention(nn.Module):
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         past_key_value = kwargs.get("past_key_values", past_key_value)
+        norm = kwargs.pop("mmx_norm", None)
         if self.sp:
             # hidden_states = this rank's token rows [1, rows, hidden]; the batch shape comes from the rotary tables
             bsz, q_len = position_embeddings[0].shape[0], position_embeddings[0].shape[1]
-            q, k, v = self.qkv_proj[0].forward_gathered(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(),
-                                                        bsz * q_len, self.workspace, kwargs.pop("mmx_norm", None))
         else:
             bsz, q_len, _ = hidden_states.size()
-            q, k, v = run_input_group(self.qkv_proj, hidden_states, kwargs.pop("mmx_norm", None))
+        # q, k, v from ONE GEMM: the rotary embedding is applied IN PLACE to the q and k columns of that output by one
+        # kernel (same arithmetic and roundings as the torch ops below) instead of ~10 strided elementwise / cat kernels
+        tables = None
+        if len(self.qkv_proj) == 1 and position_embeddings is not None and self.head_dim % 16 == 0:
+            tables = rope_tables_2d(position_embeddings, bsz, q_len, self.head_dim)
+        if tables is not None:
+            m = self.qkv_proj[0]
+            if self.sp:
+                y = m.forward_gathered_whole(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(), bsz * q_len,
+                                             self.workspace, norm)
+            else:
+                y = m.forward_whole(hidden_states, norm)
+            y = y.reshape(bsz * q_len, -1)
+            mixedgemm.rope_inplace(y, self.num_heads + self.num_key_value_heads, self.head_dim, tables[0], tables[1])
+            q, k, v = y.view(bsz, q_len, -1).split(m.splits, dim=-1)
+        elif self.sp:
+            q, k, v = self.qkv_proj[0].forward_gathered(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(),
+                                                        bsz * q_len, self.workspace, norm)
+        else:
+            q, k, v = run_input_group(self.qkv_proj, hidden_states, norm)
         q = q.view(bsz, q_len, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         v = v.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         if position_embeddings is not None:
             cos, sin = position_embeddings
-            q, k = apply_rope(q, k, cos, sin)
+            if tables is None:
+                q, k = apply_rope(q, k, cos, sin)
         else:
             cos = sin = None
         if past_key_value is not None:

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmicromix_b200.so")
-SOURCES = ["lib.cu", "quantize.cu", "rowquant.cu", "gemm.cu", "tp_reduce.cu", "moe.cu"]
+SOURCES = ["lib.cu", "quantize.cu", "rowquant.cu", "gemm.cu", "tp_reduce.cu", "moe.cu", "rope.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -77,6 +77,7 @@ struct MatmulExtra {
   int grp_n = 0;
   int grp_count = 0;
   int grp_tile_rows = 0;
+  const int* rows_dev = nullptr;  // optional (device memory): rows of A that exist, a multiple of the m-tile
   // gathered A (sequence-parallel hand-over): see GemmParams::ag_*
   const uint32_t* ag_arrived = nullptr;
   uint32_t* ag_taken = nullptr;
@@ -102,7 +103,7 @@ struct QuantGather {
 int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO, const int fmt[3],
                      uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1, uint8_t* s2, void* stream,
                      const void* norm_w, float eps, bool norm, const QuantGather* ag, const int* grp_rowblk = nullptr,
-                     const int* row_src = nullptr);
+                     const int* row_src = nullptr, const int* rows_dev = nullptr);
 int encode_store_tmap(void* ptr, int64_t rows, int64_t cols, void* out /* CUtensorMap* */);
 
 int sm_count();       // cached multiprocessor count of the current device

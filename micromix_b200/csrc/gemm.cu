@@ -100,6 +100,7 @@ struct GemmParams {
   // hold the groups' weights stacked on N.  grp_mblk[m_blk] = group of that m-tile, or -1 = padding tile (skipped).
   const int* grp_mblk;
   int grp_n;             // B rows per group
+  const int* rows_dev;   // grouped, optional (device memory): rows of A that exist; bounds the tile walk
   // GATHERED A (sequence-parallel hand-over, tp_reduce.cu): the A rows of source rank s = row / ag_rows are valid once
   // ag_arrived[32 * s] (one counter per 128-byte line) has reached ag_taken[0] + 1 (the peers' quantizers multicast them
   // and then bump the counter)
@@ -474,7 +475,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader of the pair
   const int group = (CG == 2) ? (blockIdx.x >> 1) : (SK > 1 ? (int)(blockIdx.x / SK) : (int)blockIdx.x);
   const int ngroups = (CG == 2) ? (gridDim.x >> 1) : (SK > 1 ? (int)(gridDim.x / SK) : (int)gridDim.x);
-  const int num_tiles = p.num_tiles;
+  int num_tiles = p.num_tiles;
   // split-K: this CTA's share [sk_lo, sk_hi) of the tile's concatenated stage list (all segments, in order)
   int sk_lo = 0, sk_hi = 0x7fffffff;
   uint32_t krank = 0;
@@ -519,6 +520,12 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);  // provably warp-uniform
   // everything above overlapped the previous kernel's tail; its outputs (our operands) are complete after this
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.rows_dev != nullptr) {
+    // grouped: only the first *rows_dev rows of A exist (whole m-tiles, a prefix of the walk because tiles walk N
+    // fastest); the m-tiles behind them are padding of the static upper bound and are not even looked at
+    const int used_m = __ldg(p.rows_dev) / (CG * BM);
+    num_tiles = min(num_tiles, used_m * p.n_tiles);
+  }
 
   if (warp == 0) {
     // ======================================================================== TMA producer (one lane per CTA)
@@ -1473,6 +1480,7 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   if (grouped) {
     p.grp_mblk = ex->grp_mblk;
     p.grp_n = ex->grp_n;
+    p.rows_dev = ex->rows_dev;
   }
   if (gathered) {
     p.ag_arrived = ex->ag_arrived;
@@ -1664,7 +1672,7 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul_grouped(
     const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
     const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
     const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, int groups, int tile_rows,
-    const int32_t* grp_mblk, void* c, void* stream) {
+    const int32_t* grp_mblk, const int32_t* rows_dev, void* c, void* stream) {
   if (!grp_mblk || groups <= 0) {
     mmx::set_error("matmul_grouped: null group table or no groups");
     return MMX_ERR_INVALID;
@@ -1674,6 +1682,7 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul_grouped(
   ex.grp_n = (int)N;
   ex.grp_count = groups;
   ex.grp_tile_rows = tile_rows;
+  ex.rows_dev = rows_dev;
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, nullptr, c, stream,
                           nullptr, &ex);
 }

@@ -65,6 +65,8 @@ struct QuantParams {
   // ... and row r of the sorted matrix is row row_src[r] of x (the token of that (token, slot) pair; padding rows carry
   // any valid token): the gather of the routed tokens happens in this kernel's loads, not in a staging copy
   const int* row_src;
+  const int* rows_dev;  // optional, device memory: only the first *rows_dev rows exist (the padded row count of the sorted
+                        // matrix is known on the device only); p.rows is the static upper bound the buffers were sized for
 };
 
 __device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
                          (NORM ? (uint32_t)K * 2u + (uint32_t)(NBUF * R * 512) : 0u);
   int prev_row0 = -1, prev_nvalid = 0;
   const int t = threadIdx.x;
-  const int rows = (int)p.rows;
+  int rows = (int)p.rows;
 
   // programmatic dependent launch: let the next kernel in the stream begin its own prologue as SMs free up ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -707,6 +709,11 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   // ... and wait for the previous kernel (which may still be producing X) only now: the table above depends on
   // reorder_index alone, which no kernel of this library writes, so it was built under the previous kernel's tail.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.rows_dev != nullptr) {
+    // (whole 128-row blocks: items past the last used block end this CTA's work like items past the last row)
+    rows = min(rows, __ldg(p.rows_dev));
+    if (row0 >= rows) row0 = rows;
+  }
   if (row0 < rows) {
     if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, row0, t, T, K8, pre);
     else QK::template prefetch<false, EXACT>(p, xt, row0, t, T, K8, pre);
@@ -865,7 +872,7 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
 int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO,
                      const int fmt[3], uint8_t* q0, uint8_t* q1, uint8_t* q2, uint8_t* s0, uint8_t* s1,
                      uint8_t* s2, void* stream, const void* norm_w, float eps, bool norm, const QuantGather* ag,
-                     const int* grp_rowblk, const int* row_src) {
+                     const int* grp_rowblk, const int* row_src, const int* rows_dev) {
   if (rows < 0 || K <= 0 || KN < 0 || KS < 0 || KO < 0 || KN + KS + KO != K) {
     set_error("reorder_quantize: bad shape rows=%lld K=%d (KN,KS,KO)=(%d,%d,%d)", (long long)rows, K, KN, KS, KO);
     return MMX_ERR_INVALID;
@@ -921,6 +928,7 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
   }
   p.grp_rowblk = grp_rowblk;
   p.row_src = row_src;
+  p.rows_dev = rows_dev;
   p.nw = static_cast<const uint16_t*>(norm_w);
   p.eps = eps;
   p.x = static_cast<const uint16_t*>(x);
@@ -1010,14 +1018,16 @@ extern "C" __attribute__((visibility("default"))) int mmx_rmsnorm_quantize_x(con
 // rows sorted by group, each 128-row block owned by ONE group; idx = int16 [groups, K], grp_rowblk = int32 [ceil(M/128)]
 // in device memory (written on the stream -- no host synchronisation), the same (KN, KS, KO) for every group.
 // row_src (optional) = int32 [M]: sorted row r is row row_src[r] of x -- the gather of the routed tokens is fused.
+// rows_dev (optional) = int32 in device memory: rows that actually exist (a multiple of 128); M is the static upper bound.
 extern "C" __attribute__((visibility("default"))) int mmx_reorder_quantize_x_grouped(
-    const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk, const int32_t* row_src, int KN, int KS,
-    int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream) {
+    const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk, const int32_t* row_src,
+    const int32_t* rows_dev, int KN, int KS, int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs,
+    uint8_t* sfo, void* stream) {
   if (!grp_rowblk) {
     mmx::set_error("reorder_quantize_x_grouped: null group table");
     return MMX_ERR_INVALID;
   }
   const int fmt[3] = {4, 6, 8};
   return mmx::reorder_quantize(x, M, K, idx, KN, KS, KO, fmt, xn, xs, xo, sfn, sfs, sfo, stream, nullptr, 0.0f, false, nullptr,
-                               grp_rowblk, row_src);
+                               grp_rowblk, row_src, rows_dev);
 }

@@ -24,7 +24,7 @@ from . import _lib
 
 __all__ = ["matmul", "reorder_quantize_x", "reorder_quantize_w", "reorder_quantize_w4", "rmsnorm_quantize_x",
            "activate_quantize_x", "downproj_quantize_w", "downproj_quantize_w4", "test_function", "launch_count",
-           "reorder_quantize_x_grouped", "matmul_grouped", "moe_combine"]
+           "reorder_quantize_x_grouped", "matmul_grouped", "moe_combine", "rope_inplace"]
 
 
 def _stream() -> int:
@@ -209,9 +209,10 @@ def _rowwise(fn_name, tensors, names, KN, KS, KO, widths):
     return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
 
 
-def activate_quantize_x(A, B, KN, KS, KO):
+def activate_quantize_x(A, B, KN, KS, KO, rows_used=None):
     """SiLU(A) * B -> MX quantize without a permutation (bindings.cpp:307-334): A = gate, B = up, both bf16 [M, K]
     already in down_proj's channel order -> (XN, XS, XO, SFXN, SFXS, SFXO).
+    Extension (rows_used: int32 [1] on the device = rows that exist, strided inputs only; see reorder_quantize_x_grouped).
     Extension: A and B may be column slices of one wider row-major matrix (same row stride, unit column stride), e.g. the
     two halves of a fused gate_up GEMM output; they are then read in place."""
     if (A.dim() == 2 and B.dim() == 2 and not (A.is_contiguous() and B.is_contiguous()) and A.shape == B.shape
@@ -226,7 +227,11 @@ def activate_quantize_x(A, B, KN, KS, KO):
             q = [torch.empty((rows, w), **opts) for w in (KN // 2, KS // 4 * 3, KO)]
             sf = [torch.empty((int(lib.mmx_sf_bytes_act(rows, k)),), **opts) for k in (KN, KS, KO)]
             rc = 0
-            if rows > 0:
+            if rows > 0 and rows_used is not None:  # grouped MoE: the used row count lives on the device
+                rc = lib.mmx_activate_quantize_x_rows(A.data_ptr(), B.data_ptr(), A.stride(0), rows, _ptr(rows_used), KN, KS, KO,
+                                                      _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]),
+                                                      _stream())
+            elif rows > 0:
                 rc = lib.mmx_activate_quantize_x_strided(A.data_ptr(), B.data_ptr(), A.stride(0), rows, KN, KS, KO, _ptr(q[0]),
                                                          _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]), _stream())
         _lib.check(rc, "mmx_activate_quantize_x_strided")
@@ -248,11 +253,13 @@ def downproj_quantize_w4(W, KN, KS, KO):
 
 
 # ---------------------------------------------------------------------------------------------- grouped forms (Mixtral)
-def reorder_quantize_x_grouped(X, reorder_index, group_of_rowblock, KN, KS, KO, row_src=None, rows=None):
+def reorder_quantize_x_grouped(X, reorder_index, group_of_rowblock, KN, KS, KO, row_src=None, rows=None, rows_used=None):
     """Extension (the reference loops over experts in Python, qMixtralLayer.py:437-450): ONE quantize launch over the
     expert-sorted, per-expert-padded token matrix.  reorder_index int16 [groups, K]; group_of_rowblock int32 [rows/128]
     (device); row_src int32 [rows] (device, optional): sorted row r is X[row_src[r]] -- the gather is fused; `rows` = rows
-    of the sorted matrix (defaults to X.size(0)).  -> the six tensors of reorder_quantize_x for the sorted matrix."""
+    of the sorted matrix (defaults to X.size(0)); rows_used int32 [1] (device, optional): rows that actually exist (a multiple
+    of 128) -- `rows` is then only the static upper bound and row blocks past rows_used are not touched.
+    -> the six tensors of reorder_quantize_x for the sorted matrix."""
     lib = _lib.load()
     _check_cuda("X", X, torch.bfloat16, 2)
     _check_cuda("reorder_index", reorder_index, torch.int16, 2)
@@ -277,16 +284,17 @@ def reorder_quantize_x_grouped(X, reorder_index, group_of_rowblock, KN, KS, KO, 
         rc = 0
         if M > 0:
             rc = lib.mmx_reorder_quantize_x_grouped(_ptr(X), M, K, _ptr(reorder_index), _ptr(group_of_rowblock), _ptr(row_src),
-                                                    KN, KS, KO, _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]),
+                                                    _ptr(rows_used), KN, KS, KO, _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]),
                                                     _ptr(sf[2]), _stream())
     _lib.check(rc, "mmx_reorder_quantize_x_grouped")
     return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
 
 
-def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None):
+def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None, rows_used=None):
     """Extension: ONE persistent mixed GEMM over all experts.  A = the six tensors of the sorted, padded activation
     ([M, *]); W = six tensors with the experts' MXFP4 weights stacked on N ([groups * N, *]); group_of_mtile int32
-    [M / tile_rows] (device): expert of each m-tile, -1 = padding tile (skipped) -> bf16 [M, N]."""
+    [M / tile_rows] (device): expert of each m-tile, -1 = padding tile (skipped); rows_used int32 [1] (device, optional):
+    rows that exist -- the tile walk stops there -> bf16 [M, N]."""
     lib = _lib.load()
     for t in list(A) + list(W):
         _check_cuda("operand", t, torch.uint8)
@@ -305,7 +313,8 @@ def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None):
         if M > 0:
             rc = lib.mmx_matmul_grouped(_ptr(A[0]), _ptr(W[0]), _ptr(A[1]), _ptr(W[1]), _ptr(A[2]), _ptr(W[2]), _ptr(A[3]),
                                         _ptr(W[3]), _ptr(A[4]), _ptr(W[4]), _ptr(A[5]), _ptr(W[5]), M, N, KN, KS, KO, 1,
-                                        int(groups), int(tile_rows), _ptr(group_of_mtile), _ptr(out), _stream())
+                                        int(groups), int(tile_rows), _ptr(group_of_mtile), _ptr(rows_used), _ptr(out),
+                                        _stream())
     _lib.check(rc, "mmx_matmul_grouped")
     return out
 
@@ -326,6 +335,25 @@ def moe_combine(Y, row, expert, weight, out=None):
         rc = lib.mmx_moe_combine(_ptr(Y), _ptr(row), _ptr(expert), _ptr(weight), T, k, H, _ptr(out), _stream()) if T else 0
     _lib.check(rc, "mmx_moe_combine")
     return out
+
+
+def rope_inplace(Y, heads, head_dim, cos, sin):
+    """Extension: HF rotary embedding (q * cos + rotate_half(q) * sin, every op rounded to bf16 like the torch ops of
+    qLlamaLayer.py:25-54) applied IN PLACE to the first heads * head_dim columns of the rows of Y (bf16 [M, ld], unit column
+    stride) -- the q and k columns of a fused qkv output.  cos / sin: bf16 [S, head_dim] with M % S == 0 (row m uses m % S)."""
+    lib = _lib.load()
+    if Y.dim() != 2 or Y.dtype != torch.bfloat16 or not Y.is_cuda or Y.stride(1) != 1:
+        raise ValueError("Y must be a CUDA bf16 [M, ld] matrix with unit column stride")
+    _check_cuda("cos", cos, torch.bfloat16, 2)
+    _check_cuda("sin", sin, torch.bfloat16, 2)
+    M, S = Y.size(0), cos.size(0)
+    if cos.shape != sin.shape or cos.size(1) != head_dim or M % S or heads * head_dim > Y.size(1):
+        raise ValueError("cos / sin must be [S, head_dim] with M % S == 0, and heads * head_dim columns must exist")
+    with torch.cuda.device(Y.device):
+        rc = lib.mmx_rope_inplace(Y.data_ptr(), Y.stride(0), M, int(heads), int(head_dim), cos.data_ptr(), sin.data_ptr(), S,
+                                  _stream()) if M else 0
+    _lib.check(rc, "mmx_rope_inplace")
+    return Y
 
 
 def test_function():

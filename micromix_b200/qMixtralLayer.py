@@ -55,6 +55,7 @@ def route_tables(sel: torch.Tensor, local_slot: torch.Tensor, n_local: int, tile
       row_src  int32 [Mp]      token whose activation row sits at padded row r (padding rows: token 0)
       pair_row int32 [T, k]    padded row holding the pair's expert output, -1 = expert not on this rank
       grp_rowblk int32 [Mp/128], grp_mtile int32 [Mp/tile]   expert slot per 128-row block / m-tile (-1 = unused m-tile)
+      rows_used int32 [1]      padded rows in use (<= Mp); the quantizers skip the rest, the GEMM skips the -1 m-tiles
     """
     T, k = sel.shape
     dev = sel.device
@@ -82,7 +83,8 @@ def route_tables(sel: torch.Tensor, local_slot: torch.Tensor, n_local: int, tile
     mt = torch.arange(Mp // tile, device=dev) * tile
     g = torch.searchsorted(ends_p, mt, right=True)
     grp_mtile = torch.where(g < n_local, g, torch.full_like(g, -1)).to(torch.int32)
-    return row_src[:Mp], pair_row[:T * k].view(T, k), grp_rowblk, grp_mtile, Mp
+    rows_used = ends_p[-1:].to(torch.int32)  # padded rows that actually exist (the kernels skip everything past them)
+    return row_src[:Mp], pair_row[:T * k].view(T, k), grp_rowblk, grp_mtile, Mp, rows_used
 
 
 class QMixtralSparseMoeBlock(nn.Module):
@@ -91,13 +93,19 @@ class QMixtralSparseMoeBlock(nn.Module):
     gather of the routed tokens fused into the quantizer's loads and the weighted scatter-add done by one combine kernel;
     no device->host synchronisation anywhere.  `grouped=False` is the reference's op sequence: a Python loop over experts."""
 
-    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False, grouped=None):
+    def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False, grouped=None,
+                 _emulate_ep=None):
+        """_emulate_ep = (ep, rank): profiling aid -- this process plays ONE rank of an ep-way expert-parallel block (its
+        experts only, no combine across ranks), so that the per-rank work can be profiled on one GPU."""
         super().__init__()
         self.num_experts = getattr(originalSparseMoeBlock, "num_experts", len(originalSparseMoeBlock.experts))
         self.top_k = originalSparseMoeBlock.top_k
         self.gate = originalSparseMoeBlock.gate
         self.ep_group = ep_group
         self.ep, self.rank = tp_info(ep_group)
+        self._emulated = _emulate_ep is not None
+        if self._emulated:
+            self.ep, self.rank = int(_emulate_ep[0]), int(_emulate_ep[1])
         self.fused = bool(fused)
         self.local = [j for j in range(self.num_experts) if j % self.ep == self.rank]
         key = lambda j, n: _KEY.format(i, 'block_sparse_moe', 'experts', j, n, 'input')
@@ -168,16 +176,16 @@ class QMixtralSparseMoeBlock(nn.Module):
         T = x.shape[0]
         n_local = len(self.local)
         tile = 256 if T * self.top_k >= 256 * self.num_experts else 128
-        row_src, pair_row, grp_rowblk, grp_mtile, Mp = route_tables(sel, self.local_slot, n_local, tile)
-        a = mixedgemm.reorder_quantize_x_grouped(x, self.idx13, grp_rowblk, *self.s13, row_src=row_src, rows=Mp)
-        h = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile)          # [Mp, 2 * inter]
+        row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = route_tables(sel, self.local_slot, n_local, tile)
+        a = mixedgemm.reorder_quantize_x_grouped(x, self.idx13, grp_rowblk, *self.s13, row_src=row_src, rows=Mp, rows_used=used)
+        h = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile, rows_used=used)   # [Mp, 2 * inter]
         I = self.inter
         if self.fused:
-            a2 = mixedgemm.activate_quantize_x(h[:, :I], h[:, I:], *self.s2)
+            a2 = mixedgemm.activate_quantize_x(h[:, :I], h[:, I:], *self.s2, rows_used=used)
         else:
             act = F.silu(h[:, :I]) * h[:, I:]
-            a2 = mixedgemm.reorder_quantize_x_grouped(act, self.idx2, grp_rowblk, *self.s2)
-        y = mixedgemm.matmul_grouped(a2, self._w("W2"), grp_mtile, n_local, tile)          # [Mp, hidden]
+            a2 = mixedgemm.reorder_quantize_x_grouped(act, self.idx2, grp_rowblk, *self.s2, rows_used=used)
+        y = mixedgemm.matmul_grouped(a2, self._w("W2"), grp_mtile, n_local, tile, rows_used=used)   # [Mp, hidden]
         return mixedgemm.moe_combine(y, pair_row, sel.to(torch.int32), w.contiguous())
 
     @torch.no_grad()
@@ -190,7 +198,7 @@ class QMixtralSparseMoeBlock(nn.Module):
         w = (w / w.sum(dim=-1, keepdim=True)).to(x.dtype)
         if self.grouped:
             out = self._forward_grouped(x.contiguous(), w, sel)
-            if self.ep > 1:
+            if self.ep > 1 and not self._emulated:
                 dist.all_reduce(out, group=self.ep_group)
             return out.view(b, s, h), router_logits
         out = torch.zeros_like(x)
@@ -209,7 +217,7 @@ class QMixtralSparseMoeBlock(nn.Module):
             tok = tok_sorted[lo:lo + n]
             y = expert(x.index_select(0, tok)) * w_sorted[lo:lo + n, None]
             out.index_add_(0, tok, y.to(x.dtype))
-        if self.ep > 1:
+        if self.ep > 1 and not self._emulated:
             dist.all_reduce(out, group=self.ep_group)
         return out.view(b, s, h), router_logits
 

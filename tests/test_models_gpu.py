@@ -72,13 +72,28 @@ def _run(cuda, cfg, cls_path, moe=False, bias=False, bsz=2, seq=96):
     g = torch.Generator(device=cuda).manual_seed(11)
     x = torch.randn(bsz, seq, cfg['hidden_size'], generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
     cos, sin = S.rope_tables(cfg, bsz, seq, cuda)
-    out = qlayer(x, position_embeddings=(cos, sin))
-    assert isinstance(out, tuple) and len(out) == 1
     ref = _unfused_layer(layer, cfg, idx, p6, p8, 1, x, cos, sin, moe=moe)
+    # (1) with RoPE left to the torch ops the layer must equal the reference structure bit for bit
+    import micromix_b200._qdecoder as QD
+    keep = QD.rope_tables_2d
+    QD.rope_tables_2d = lambda *a, **k: None
+    try:
+        out = qlayer(x, position_embeddings=(cos, sin))
+    finally:
+        QD.rope_tables_2d = keep
+    assert isinstance(out, tuple) and len(out) == 1
     torch.cuda.synchronize()
     assert out[0].shape == x.shape and out[0].dtype == torch.bfloat16
     assert torch.isfinite(out[0].float()).all()
     assert torch.equal(out[0], ref), float((out[0].float() - ref.float()).abs().max())
+    # (2) the default path rotates q and k IN PLACE inside the fused qkv output (bit-identical to the torch ops:
+    # test_rope_inplace_matches_hf_ops_bit_for_bit) and hands SDPA strided views of it; the attention library may then pick
+    # another kernel / summation order, so the layer output is compared within the noise that leaves behind
+    out2 = qlayer(x, position_embeddings=(cos, sin))[0]
+    torch.cuda.synchronize()
+    d = (out2.float() - ref.float()).abs()
+    scale = ref.float().pow(2).mean().sqrt()
+    assert float(d.mean() / scale) <= 5e-3 and float(d.max() / scale) <= 0.25, (float(d.mean() / scale), float(d.max() / scale))
     return qlayer, x, cos, sin
 
 
@@ -140,8 +155,39 @@ def test_fused_norm_and_activation_mode(cuda, cls_path, bias):
     b = fused(x, position_embeddings=(cos, sin))[0]
     n2 = mixedgemm.launch_count()
     torch.cuda.synchronize()
-    assert n1 - n0 == 8 and n2 - n1 == 8  # four quantize + four GEMM launches either way; the elementwise kernels are gone
+    # four quantize + four GEMM launches + the in-place RoPE kernel either way; the elementwise kernels are gone
+    assert n1 - n0 == 9 and n2 - n1 == 9
     assert torch.isfinite(b.float()).all()
     d = (a.float() - b.float()).abs()
     scale = a.float().pow(2).mean().sqrt()
     assert float(d.max()) <= 0.05 * float(scale) and float(d.mean()) <= 0.005 * float(scale), (float(d.max()), float(d.mean()), float(scale))
+
+
+@pytest.mark.parametrize("b,s,nh,nkv,d,extra", [(2, 96, 4, 2, 128, 256), (1, 33, 32, 8, 128, 1024), (3, 17, 2, 2, 64, 0)])
+def test_rope_inplace_matches_hf_ops_bit_for_bit(cuda, b, s, nh, nkv, d, extra):
+    """mixedgemm.rope_inplace on the q | k columns of a fused qkv output == HF's q * cos + rotate_half(q) * sin on the
+    transposed views (the torch ops of qLlamaLayer.py:25-54), every bf16 rounding included; the v columns are untouched."""
+    from micromix_b200 import mixedgemm
+    from micromix_b200 import model_shapes as S
+    from micromix_b200._qdecoder import apply_rope, rope_tables_2d
+    g = torch.Generator(device=cuda).manual_seed(b * 100 + s)
+    ld = (nh + nkv) * d + extra
+    y = (torch.randn(b * s, ld, generator=g, device=cuda) * 3).to(torch.bfloat16)
+    y0 = y.clone()
+    cos, sin = S.rope_tables(dict(head_dim=d, rope_theta=10000.0), b, s, cuda)
+    q = y0[:, :nh * d].view(b, s, nh, d).transpose(1, 2)
+    k = y0[:, nh * d:(nh + nkv) * d].view(b, s, nkv, d).transpose(1, 2)
+    qr, kr = apply_rope(q, k, cos, sin)
+    tabs = rope_tables_2d((cos, sin), b, s, d)
+    assert tabs is not None and tabs[0].shape == (s, d)
+    mixedgemm.rope_inplace(y, nh + nkv, d, *tabs)
+    torch.cuda.synchronize()
+    assert torch.equal(y[:, :nh * d].view(b, s, nh, d).transpose(1, 2), qr)
+    assert torch.equal(y[:, nh * d:(nh + nkv) * d].view(b, s, nkv, d).transpose(1, 2), kr)
+    assert torch.equal(y[:, (nh + nkv) * d:], y0[:, (nh + nkv) * d:])
+    # per-token tables (contiguous [b, s, d]) take the S = M form
+    cos2, sin2 = cos.contiguous(), sin.contiguous()
+    tabs2 = rope_tables_2d((cos2, sin2), b, s, d)
+    y2 = y0.clone()
+    mixedgemm.rope_inplace(y2, nh + nkv, d, *tabs2)
+    assert torch.equal(y2, y)

@@ -14,7 +14,7 @@ def test_route_tables_match_per_expert_where(T, k, E, ep, rank, tile):
     slot = torch.full((E,), len(local), dtype=torch.int64)
     for s_, j in enumerate(local):
         slot[j] = s_
-    row_src, pair_row, grp_rowblk, grp_mtile, Mp = route_tables(sel, slot, len(local), tile)
+    row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = route_tables(sel, slot, len(local), tile)
     assert Mp % tile == 0 and row_src.numel() == Mp and row_src.dtype == torch.int32
     assert grp_rowblk.numel() == Mp // 128 and grp_mtile.numel() == Mp // tile
     assert int(row_src.min()) >= 0 and int(row_src.max()) < T  # padding rows point at a valid token
@@ -28,6 +28,6 @@ def test_route_tables_match_per_expert_where(T, k, E, ep, rank, tile):
         assert bool((grp_rowblk[off // 128:(off + pad) // 128] == s_).all())
         assert bool((grp_mtile[off // tile:(off + pad) // tile] == s_).all())
         off += pad
-    assert off <= Mp and bool((grp_mtile[off // tile:] == -1).all())
+    assert off <= Mp and bool((grp_mtile[off // tile:] == -1).all()) and int(used) == off
     assert int(grp_rowblk.min()) >= 0 and int(grp_rowblk.max()) < len(local)
     assert bool((pair_row[slot[sel] == len(local)] == -1).all())  # experts of other ranks

@@ -19,7 +19,10 @@ tokens = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 layer = S.make_layer(cfg, dev, seed=0, moe=True)
 idx, p6, p8 = S.make_calibration(cfg, 0, moe=True)
 x0 = torch.randn(1, tokens, cfg["hidden_size"], device=dev).to(torch.bfloat16)
+ep = int(sys.argv[2]) if len(sys.argv) > 2 else 1  # > 1: this process plays rank 0 of an ep-way expert-parallel block
 for name, kw in (("grouped", {}), ("loop", {"grouped": False})):
+    if ep > 1:
+        kw = dict(kw, _emulate_ep=(ep, 0))
     blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, fused=True, **kw)
     for _ in range(2):
         blk(x0)
