@@ -197,7 +197,7 @@ class HotLinear:
         from micromix_b200.parallel_utils import column_shard_range, row_shard_plan
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import helpers as H
-        self.name, self.mode, self.lib, self.M, self.world = name, mode, lib, M, world
+        self.name, self.mode, self.lib, self.M, self.world, self.seed = name, mode, lib, M, world, seed
         self.ws = workspace if (world > 1 and mode == "row") else None
         self._c_out = ctypes.c_void_p()
         if share is not None:
@@ -261,12 +261,58 @@ class HotLinear:
         else:
             self._row0, self._rows = ctypes.c_int64(), ctypes.c_int64()
 
+    def enable_tpr(self, ws, rank, world):
+        """Token-parallel form of a row-parallel linear (tp_mode "tpr", the alternative design): replicated MXFP4 weight
+        in the rank-blocked channel order, all-to-all of the packed activation codes, full-K GEMM on this rank's rows."""
+        import torch
+        from micromix_b200 import mixedgemm
+        from micromix_b200.parallel_utils import token_parallel_plan
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        if self.mode != "row":
+            return self.enable_sp(ws)
+        self.sp_ws = None
+        if getattr(self, "tpr", None) is None:
+            dev = self.x.device
+            Kf = self.K * world
+            idx = H.make_index(Kf, seed=self.seed)
+            g = torch.Generator(device=dev).manual_seed(1234 + self.seed)  # the same weight HotLinear sharded at construction
+            w = (torch.randn(self.N, Kf, generator=g, device=dev, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+            _, p6, p8 = split_for(Kf)
+            perm, tot, shards = token_parallel_plan(idx, p6, p8, world)
+            me = shards[rank]
+            assert tuple(me["split"]) == tuple(self.split) and torch.equal(me["index"].to(dev), self.idx)
+            Wt = mixedgemm.reorder_quantize_w4(w, perm.to(dev), *tot)
+            del w
+            lo, hi = ws.shard_range(self.M)
+            out = torch.empty((max(hi - lo, 1), self.N), dtype=torch.bfloat16, device=dev)
+            self.tpr = dict(W=Wt, tot=tot, off=me["offset"], perm=perm.to(dev), out=out, lo=lo, hi=hi,
+                            c_tot=(ctypes.c_int32 * 3)(*tot), c_off=(ctypes.c_int32 * 3)(*me["offset"]))
+            p = lambda t: t.data_ptr() if t.numel() else None
+            p4, p6l, p8l = self.split
+            self._xargs = (ws.ctx, self.x.data_ptr(), self.M, self.K, self.idx.data_ptr(), p4, p6l, p8l, self.tpr["c_tot"],
+                           self.tpr["c_off"], None)
+            self._row0, self._rows = ctypes.c_int64(), ctypes.c_int64()
+            self._yargs = (ws.ctx, p(Wt[0]), p(Wt[1]), p(Wt[2]), p(Wt[3]), p(Wt[4]), p(Wt[5]), self.M, self.N, tot[0], tot[1],
+                           tot[2], 1, None, out.data_ptr(), ctypes.byref(self._row0), ctypes.byref(self._rows))
+        self.tpr_on = True
+
     def run(self, stream, events=None):
         """quantize + GEMM of this rank's shard (fused mode: + the reduction, inside the GEMM launch pair)."""
         lib = self.lib
         if events is not None:
             events[0].record()
         sp = getattr(self, "sp_ws", None)
+        if getattr(self, "tpr_on", False) and self.mode == "row":
+            rc = lib.mmx_tp_quantize_alltoall(*self._xargs, stream)
+            if events is not None:
+                events[1].record()
+            rc |= lib.mmx_tp_matmul_exchanged(*self._yargs, stream)
+            if events is not None:
+                events[2].record()
+            if rc:
+                raise RuntimeError(lib.mmx_last_error().decode())
+            return
         if sp is not None and self.mode == "col":
             rc = lib.mmx_tp_quantize_allgather(*self._gargs, stream)
             if events is not None:
@@ -295,6 +341,8 @@ class HotLinear:
         import torch
         from micromix_b200.parallel_utils import _DeviceBytes
         sp = getattr(self, "sp_ws", None)
+        if getattr(self, "tpr_on", False) and self.mode == "row":
+            return self.tpr["out"][: self.tpr["hi"] - self.tpr["lo"]], self.tpr["lo"]
         if self.mode == "row" and (sp is not None or self.ws is not None):
             rows = int(self._rows.value) if sp is not None else self.M
             row0 = int(self._row0.value) if sp is not None else 0
@@ -340,15 +388,17 @@ def run_ours(args, rank, world, local_rank):
         from micromix_b200.parallel_utils import PeerWorkspace
         n_row = max(N for _, N, _, mode in LINEARS if mode == "row")
         k_col = max(K for _, _, K, mode in LINEARS if mode == "col")
-        want_sp = args.tp_mode in ("auto", "sp") and C == 1
+        # (the token-parallel alternative exchanges [M / tp, K] activations of the ROW linears through the same channel)
+        k_col = max(k_col, -(-max(K for _, _, K, mode in LINEARS if mode == "row") // world // 128) * 128)
+        want_sp = args.tp_mode in ("auto", "sp", "tpr") and C == 1
         try:
             # sequence parallel needs the NVSwitch multicast mapping (gather channel); the constructor is collective and
             # raises on EVERY rank when any rank cannot map it
             ws = PeerWorkspace(Mc, n_row, device=dev, gather=(Mc, k_col) if want_sp else None)
-            tp_mode = "sp" if want_sp else "ar"
+            tp_mode = ("tpr" if args.tp_mode == "tpr" else "sp") if want_sp else "ar"
         except Exception as e:  # noqa: BLE001
             ws_note = f"sequence-parallel workspace unavailable ({e!r})"[:200]
-            if args.tp_mode == "sp":
+            if args.tp_mode in ("sp", "tpr"):
                 raise
             try:
                 ws = PeerWorkspace(Mc, n_row, device=dev)
@@ -379,8 +429,11 @@ def run_ours(args, rank, world, local_rank):
         """Everything that is timed, for one tensor-parallel mode: warm-up, real-rank parity, the K timed steps, the evented
         per-kernel pass, the end-to-end leg.  Returns the JSON line of that mode."""
         for l in lins:
+            l.tpr_on = False
             if tp_mode == "sp":
                 l.enable_sp(ws)
+            elif tp_mode == "tpr":
+                l.enable_tpr(ws, rank, world)
             else:
                 l.sp_ws = None
 
@@ -576,7 +629,11 @@ def run_ours(args, rank, world, local_rank):
                 if l.mode != "row":
                     continue
                 full = l.M * l.N * 2.0
-                if tp_mode == "sp":
+                if tp_mode == "tpr":
+                    p4_, p6_, p8_ = l.split
+                    egress = (world - 1) / world * l.M * (p4_ / 2 + p6_ * 3 / 4 + p8_ + l.K / 32)
+                    note = "all-to-all of packed MX codes + scales of this rank's K slice (no partial sums on the wire)"
+                elif tp_mode == "sp":
                     egress = full * (world - 1) / world  # partial rows pulled by / pushed to their owners
                     note = "reduce-scatter: (tp-1)/tp of the bf16 partial leaves each rank, 1/tp of the sum comes back"
                 elif ws is not None and ws.mode == "switch":
@@ -616,10 +673,20 @@ def run_ours(args, rank, world, local_rank):
     # own K timed steps) and reports the faster one as the line, the other under "tp_modes_measured".
     modes = [tp_mode]
     if world > 1 and ws is not None and tp_mode == "sp" and args.tp_mode == "auto":
-        modes = ["ar", "sp"]
+        modes = ["ar", "sp", "tpr"]
     lines = {m: run_mode(m) for m in modes}
-    best = min(lines, key=lambda m: lines[m]["ms_per_step"])
+    # the LINE is the faster of the two forms of the north_star's row-parallel design; the token-parallel alternative
+    # ("tpr": replicated o / down weights, all-to-all of packed codes) is measured the same way and reported NEXT to it
+    best = min((m for m in lines if m != "tpr" or len(lines) == 1), key=lambda m: lines[m]["ms_per_step"])
     line = lines[best]
+    if "tpr" in lines and best != "tpr":
+        t = lines["tpr"]
+        line["alt_token_parallel"] = {
+            "what": "o / down token-parallel: replicated MXFP4 weights, rank-local quantize of the K slice, all-to-all of "
+                    "the packed codes, full-K GEMM on each rank's token rows; qkv / gate_up as in the sequence-parallel form",
+            "ms_per_step": t["ms_per_step"], "value": t["value"], "unit": "TFLOP/s", "tp_parity": t.get("tp_parity"),
+            "e2e": t.get("e2e"), "tp_wire": t.get("tp_wire"),
+            "per_linear_us": {k: [round(v["quant_us"], 1), round(v["gemm_us"], 1)] for k, v in t["per_linear"].items()}}
     if len(lines) > 1:
         line["tp_modes_measured"] = {m: {"ms_per_step": l["ms_per_step"], "value": l["value"],
                                          "e2e_value": (l.get("e2e") or {}).get("value"),
@@ -681,6 +748,30 @@ def check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev):
         got = got.clone()
         if ws is None and l.mode == "row":
             dist.all_reduce(got)  # --tp-reduce nccl: the step's reduction is the separate ncclAllReduce
+        if getattr(l, "tpr_on", False) and l.mode == "row":
+            # token-parallel: the rows this rank holds must equal, bit for bit, the rows of the single-GPU linear over the
+            # full K with the rank-blocked permutation (full activation = the ranks' K slices side by side)
+            parts = [torch.empty_like(l.x) for _ in range(world)]
+            dist.all_gather(parts, l.x)
+            xf = torch.cat(parts, dim=1)
+            del parts
+            a = mixedgemm.reorder_quantize_x(xf, l.tpr["perm"], *l.tpr["tot"])
+            W = l.tpr["W"]
+            ref = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5])
+            ulps = _bf16_ulps(got, ref[row0:row0 + got.shape[0]])
+            del xf, a, ref
+            ok = ulps == 0
+            rec = {"kind": "token-parallel (all-to-all of packed codes, replicated weight)", "rows": [row0, row0 + got.shape[0]],
+                   "max_bf16_steps_vs_single_gpu_full_K_linear": ulps, "bound": 0}
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            worst = torch.tensor([ulps], device=dev)
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            rec["ok_on_all_ranks"] = bool(int(flag.item()))
+            rec["worst_rank_bf16_steps"] = int(worst.item())
+            ok_all = ok_all and rec["ok_on_all_ranks"]
+            out["linears"][l.name] = rec
+            continue
         a = mixedgemm.reorder_quantize_x(l.x, l.idx, *l.split)
         W = l.W
         part = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5])
@@ -749,8 +840,8 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
             xin.append(l.x.cpu().pin_memory())
         # a row-parallel result: each rank returns its 1/N of the rows (sequence parallel: exactly the rows it owns; all-
         # reduce: the result is replicated and the host needs it once); a column-parallel shard is returned whole
-        if sp is not None and l.mode == "row":
-            r0, r1 = sp.shard_range(l.M)
+        if (sp is not None or getattr(l, "tpr_on", False)) and l.mode == "row":
+            r0, r1 = l.ws.shard_range(l.M)
         else:
             r0, r1 = (l.M * rank // world, l.M * (rank + 1) // world) if (world > 1 and l.mode == "row") else (0, l.M)
         yrows.append((r0, r1))
@@ -777,10 +868,15 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
             s_run.wait_event(e_in)
             with torch.cuda.stream(s_run):
                 sp = getattr(l, "sp_ws", None)
-                in_ws = l.mode == "row" and (sp is not None or l.ws is not None)
+                tpr = getattr(l, "tpr_on", False) and l.mode == "row"
+                in_ws = l.mode == "row" and (sp is not None or l.ws is not None) and not tpr
                 if in_ws and i in prev_out:
                     s_run.wait_event(prev_out[i])
-                if sp is not None and l.mode == "col":
+                if tpr:
+                    l.ws.quantize_alltoall(xd, l.M, q.reorder_index, l.split, l.tpr["tot"], l.tpr["off"])
+                    yd, _ = l.ws.matmul_exchanged(l.M, l.tpr["W"], l.tpr["tot"])
+                    r0, r1 = 0, yd.shape[0]  # this rank's rows
+                elif sp is not None and l.mode == "col":
                     sp.quantize_allgather(xd, l.M, q.reorder_index, q.p4_num, q.p6_num, q.p8_num)
                     yd = sp.matmul_gathered(l.M, l.W, q.p4_num, q.p6_num, q.p8_num)
                 elif sp is not None:
@@ -921,7 +1017,7 @@ def main():
     ap.add_argument("--prefill-iters", type=int, default=5)
     ap.add_argument("--set-option", action="append", default=[], metavar="KEY=VALUE",
                     help="mmx_set_option(KEY, VALUE) before the run (tuning sweeps)")
-    ap.add_argument("--tp-mode", default="auto", choices=["auto", "sp", "ar"],
+    ap.add_argument("--tp-mode", default="auto", choices=["auto", "sp", "ar", "tpr"],
                     help="N>1, fused reduction: sp = sequence parallel (reduce-scatter + all-gather of packed codes through "
                          "NVSwitch multicast; the default when the box offers multicast memory), ar = all-reduce")
     ap.add_argument("--tp-reduce", default="fused", choices=["nccl", "fused"],

@@ -223,6 +223,26 @@ int mmx_tp_matmul_gathered(void* ctx, const uint8_t* bn, const uint8_t* bs, cons
                            const void* bias, void* c, void* stream);
 
 /*
+ * TOKEN-PARALLEL row linears (the alternative to the K-sharded GEMM + collective above; no reference counterpart).  The
+ * MXFP4 weights of o_proj / down_proj are replicated; the ranks exchange the PACKED MX CODES of the activation (an
+ * all-to-all of (tp-1)/tp * M * K/tp * ~0.66 bytes per rank) instead of bf16 partial sums ((tp-1)/tp * M * N * 2 bytes):
+ *   mmx_tp_quantize_alltoall(ctx, x_local, M, K_local, idx_local, KN, KS, KO, seg_tot, seg_off, views, stream)
+ *       mmx_reorder_quantize_x of this rank's K slice (x_local bf16 [M, K_local], rank-local permutation and split, as in
+ *       the row-parallel form); the codes and scales of rows [d*shard, (d+1)*shard) are written into rank d's exchange
+ *       buffer (the gather channel), at channel offset seg_off[i] inside segment i of the [shard, K_total] activation whose
+ *       segments hold seg_tot[i] channels (all multiples of 128).  views[0..5]: local addresses of that activation.
+ *   mmx_tp_matmul_exchanged(ctx, <replicated weights>, M, N, KN_tot, KS_tot, KO_tot, w4, bias, c, &row0, &rows, stream)
+ *       the three-segment GEMM over the full K on this rank's rows (c: bf16 [rows, N]) once every rank's columns have
+ *       landed.  Bit-identical to mmx_reorder_quantize_x + mmx_matmul on one GPU with the rank-blocked permutation.
+ * Exactly one mmx_tp_matmul_exchanged must follow each mmx_tp_quantize_alltoall on every rank.
+ */
+int mmx_tp_quantize_alltoall(void* ctx, const void* x_local, int64_t M, int K_local, const int16_t* idx_local, int KN, int KS,
+                             int KO, const int32_t* seg_tot, const int32_t* seg_off, void** views, void* stream);
+int mmx_tp_matmul_exchanged(void* ctx, const uint8_t* bn, const uint8_t* bs, const uint8_t* bo, const uint8_t* sfbn,
+                            const uint8_t* sfbs, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                            const void* bias, void* c, int64_t* row0, int64_t* rows, void* stream);
+
+/*
  * Grouped forms for Mixtral's experts (extension).  The reference runs one Python iteration per expert -- quantize,
  * matmul, quantize, matmul, index_add_ (model/qMixtralLayer.py:437-450, 502-519).  Here the (token, slot) pairs are sorted
  * by expert once, each expert's rows padded to whole m-tiles, and ONE quantize launch + ONE GEMM launch serve all experts:

@@ -48,6 +48,10 @@ SYMBOLS = {
     "mmx_tp_quantize_allgather": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, _vp, ctypes.c_float,
                                          ctypes.POINTER(_vp), _vp]),
     "mmx_tp_matmul_gathered": (_i32, [_vp] + [_vp] * 6 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "mmx_tp_quantize_alltoall": (_i32, [_vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_int32),
+                                        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(_vp), _vp]),
+    "mmx_tp_matmul_exchanged": (_i32, [_vp] + [_vp] * 6 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp,
+                                                         ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
     "mmx_reorder_quantize_x_grouped": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_activate_quantize_x_rows": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32] + [_vp] * 7),
     "mmx_rope_inplace": (_i32, [_vp, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _vp]),

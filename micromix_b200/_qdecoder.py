@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import mixedgemm
-from .parallel_utils import RowParallelQLinear, forward_row_shard
+from .parallel_utils import RowParallelQLinear, TokenParallelQLinear, forward_row_shard
 from .qLinearLayer import QLinearLayer
 
 NAME = 'layers.{}.{}.{}.{}'  # the key template of the reference's calibration dicts (qLlamaLayer.py:211)
@@ -186,9 +186,10 @@ class QAttention(nn.Module):
     """Llama / Qwen2 / Mixtral attention with quantized projections (qLlamaLayer.py:196-321, qQwenLayer.py:205-327)."""
 
     def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None, workspace=None,
-                 sequence_parallel=False):
+                 sequence_parallel=False, token_parallel_rows=False):
         super().__init__()
         self.sp = bool(sequence_parallel)
+        self.tpr = bool(token_parallel_rows) and self.sp
         self.workspace = workspace
         cfg = originalAttn.config
         self.config = cfg
@@ -212,7 +213,10 @@ class QAttention(nn.Module):
         self.qkv_proj = build_input_group([originalAttn.q_proj, originalAttn.k_proj, originalAttn.v_proj], keys, p8_nums,
                                           p6_nums, reorder_index, slices)
         ko = NAME.format(i, 'self_attn', 'o_proj', 'input')
-        if self.tp > 1:
+        if self.tp > 1 and self.tpr:
+            self.o_proj = TokenParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group,
+                                               workspace)
+        elif self.tp > 1:
             self.o_proj = RowParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group,
                                              workspace=workspace)
         else:
@@ -271,7 +275,8 @@ class QAttention(nn.Module):
                                              enable_gqa=self.num_key_value_groups > 1)
         out = out.transpose(1, 2).reshape(bsz, q_len, -1)
         if self.sp:
-            y, _ = forward_row_shard(self.o_proj, out)  # reduce-scatter: this rank's rows only
+            # this rank's rows only: reduce-scatter of the K-sharded product, or the token-parallel full-K product
+            y, _ = self.o_proj(out) if self.tpr else forward_row_shard(self.o_proj, out)
             return y.unsqueeze(0), None, past_key_value
         return self.o_proj(out), None, past_key_value
 
@@ -281,9 +286,10 @@ class QGatedMLP(nn.Module):
 
     def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
                                                                                                'down_proj'),
-                 key_fmt=None, fused_act=False, workspace=None, sequence_parallel=False):
+                 key_fmt=None, fused_act=False, workspace=None, sequence_parallel=False, token_parallel_rows=False):
         super().__init__()
         self.sp = bool(sequence_parallel)
+        self.tpr = bool(token_parallel_rows) and self.sp
         self.workspace = workspace
         self.tp, self.rank = tp_info(tp_group)
         gate, up, down = (getattr(originalMLP, n) for n in names)
@@ -316,7 +322,9 @@ class QGatedMLP(nn.Module):
         self.gate_up_proj = build_input_group([gate, up], [key(names[0]), key(names[1])], p8_nums, p6_nums,
                                               reorder_index, slices)
         kd = key(names[2])
-        if self.tp > 1:
+        if self.tp > 1 and self.tpr:
+            self.down_proj = TokenParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group, workspace)
+        elif self.tp > 1:
             self.down_proj = RowParallelQLinear(down, p8_nums[kd], p6_nums[kd], reorder_index[kd], tp_group,
                                                 workspace=workspace)
         else:
@@ -328,7 +336,8 @@ class QGatedMLP(nn.Module):
             # x = this rank's token rows [1, rows, hidden] of `tokens` in total
             g, u = self.gate_up_proj[0].forward_gathered(x.reshape(-1, x.shape[-1]).contiguous(), int(tokens), self.workspace,
                                                          norm)
-            y, _ = forward_row_shard(self.down_proj, (self.act_fn(g) * u).unsqueeze(0))
+            h = (self.act_fn(g) * u).unsqueeze(0)
+            y, _ = self.down_proj(h) if self.tpr else forward_row_shard(self.down_proj, h)
             return y.unsqueeze(0)
         g, u = run_input_group(self.gate_up_proj, x, norm)
         if not self.fused_act:
@@ -346,22 +355,25 @@ class QDecoderLayer(nn.Module):
     (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
 
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
-                 workspace=None, sequence_parallel=False):
+                 workspace=None, sequence_parallel=False, token_parallel_rows=False):
         """`workspace` (extension): a parallel_utils.PeerWorkspace shared by the model's row-parallel linears -- o_proj and
         down_proj then run as GEMMs fused with their all-reduce instead of GEMM + NCCL all-reduce.
         `sequence_parallel` (extension, needs a workspace with a gather channel): the layer takes and returns THIS rank's
         token rows only ([1, rows, hidden], rows = workspace.shard_range(b*s)): o_proj / down_proj end in a reduce-scatter,
         residual + RMSNorm + quantize run on the shard, and the packed MX codes (not bf16 activations) are all-gathered
-        into the column-parallel GEMMs through NVSwitch multicast."""
+        into the column-parallel GEMMs through NVSwitch multicast.
+        `token_parallel_rows` (with sequence_parallel): o_proj / down_proj keep a REPLICATED MXFP4 weight and exchange the
+        packed codes of their input all-to-all instead of reducing bf16 partial sums (parallel_utils.TokenParallelQLinear)."""
         super().__init__()
         self.fused = bool(fused)
         self.sp = bool(sequence_parallel)
+        self.tpr = bool(token_parallel_rows) and self.sp
         if self.sp and (workspace is None or tp_info(tp_group)[0] < 2 or not workspace.gather[0]):
             raise ValueError("sequence_parallel needs tp >= 2 and a PeerWorkspace(..., gather=(tokens, hidden))")
         self._workspace = workspace
         self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
         self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
-                                    tp_group, workspace, sequence_parallel=self.sp)
+                                    tp_group, workspace, sequence_parallel=self.sp, token_parallel_rows=self.tpr)
         if self.sp and len(self.self_attn.qkv_proj) != 1:
             raise ValueError("sequence_parallel needs q/k/v to share one (reorder_index, p6, p8): one gather feeds ONE GEMM")
         self.mlp = self._build_mlp(originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)
@@ -370,7 +382,7 @@ class QDecoderLayer(nn.Module):
 
     def _build_mlp(self, originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group):
         return QGatedMLP(originalLayer.mlp, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused_act=self.fused,
-                         workspace=self._workspace, sequence_parallel=self.sp)
+                         workspace=self._workspace, sequence_parallel=self.sp, token_parallel_rows=self.tpr)
 
     @torch.no_grad()
     def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,

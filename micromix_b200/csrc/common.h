@@ -98,6 +98,13 @@ struct QuantGather {
   uint32_t* arrived[kMaxTp]; // rank d's (peer-mapped) count of gathers whose rows from THIS rank have landed there
   uint32_t* err;             // local error word (mmx_tp_status): bit 2 = the wait for the consumers timed out
   int tp;
+  // all-to-all form (see QuantParams::a2a_per): rows per destination rank (0 = gather form), per-destination code / scale
+  // base pointers (offset to this rank's columns / atoms), packed-row pitch and scale atoms per row block of the destination
+  int a2a_per;
+  uint8_t* qd[kMaxTp][3];
+  uint8_t* sfd[kMaxTp][3];
+  uint32_t a2a_pitch[3];
+  int a2a_katoms[3];
 };
 // quantize.cu: the reorder+quantize launcher behind mmx_reorder_quantize_* (fmt = bits per segment; norm_w: fused RMSNorm)
 int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int KN, int KS, int KO, const int fmt[3],

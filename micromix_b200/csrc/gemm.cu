@@ -540,37 +540,40 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         ag_target += 1u;
       }
       uint32_t ag_ok_mask = 0;  // gathered A: source ranks whose arrival this CTA has already observed
+      auto ag_wait = [&](int src) {
+        if ((ag_ok_mask >> src) & 1u) return;
+        uint32_t v;
+        unsigned long long t0 = 0;
+        for (uint32_t it = 1;; ++it) {
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
+          if ((int32_t)(v - ag_target) >= 0) break;
+          __nanosleep(64);
+          if ((it & 1023u) == 0) {  // bounded: a lost peer costs wrong rows (flagged), never a hung GPU
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > p.ag_timeout_ns) {
+              atomicOr(p.ag_err, 8u);
+              break;
+            }
+          }
+        }
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
+        asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA loads below read what the peers wrote
+        ag_ok_mask |= 1u << src;
+      };
+      // exchanged A (all-to-all of K slices: ag_rows == 0): every source rank contributes columns to EVERY row
+      if (p.ag_arrived != nullptr && p.ag_rows == 0)
+        for (int src = 0; src < p.ag_tp; ++src) ag_wait(src);
       for (int tile = group; tile < num_tiles && ok; tile += ngroups) {
         int m_blk, n_blk, grp;
         if (!tile_coords(p, tile, m_blk, n_blk, grp)) continue;
         const int a_row = (m_blk * CG + (int)rank) * BM;          // this CTA's A rows
         const int b_row = grp * p.grp_n + n_blk * BN + (int)rank * G::kBRows;  // this CTA's share of the B rows
         const int sfb_blk = (grp * p.grp_n) / 128 + n_blk * 2;
-        if (p.ag_arrived != nullptr) {
-          // the rows of this m-tile were quantized by rank a_row / ag_rows: wait (once per source) until they have landed
-          const int src = a_row / p.ag_rows;
-          if (!((ag_ok_mask >> src) & 1u)) {
-            uint32_t v;
-            unsigned long long t0 = 0;
-            for (uint32_t it = 1;; ++it) {
-              asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
-              if ((int32_t)(v - ag_target) >= 0) break;
-              __nanosleep(64);
-              if ((it & 1023u) == 0) {  // bounded: a lost peer costs wrong rows (flagged), never a hung GPU
-                unsigned long long now;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > p.ag_timeout_ns) {
-                  atomicOr(p.ag_err, 8u);
-                  break;
-                }
-              }
-            }
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_arrived + 32 * src) : "memory");
-            asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA loads below read what the peers wrote
-            ag_ok_mask |= 1u << src;
-          }
-        }
+        // gathered A: the rows of this m-tile were quantized by rank a_row / ag_rows -- wait (once per source) until they
+        // have landed
+        if (p.ag_arrived != nullptr && p.ag_rows > 0) ag_wait(a_row / p.ag_rows);
         int seg_off = 0;  // split-K: stages of the segments before this one
         for (int s = 0; s < p.nseg && ok; ++s) {
           const GemmSeg& sg = p.seg[s];

@@ -55,6 +55,14 @@ struct QuantParams {
   uint32_t* ag_issued;
   uint32_t* ag_arrived[kMaxTp];
   int ag_tp;
+  // ALL-TO-ALL form of the MC kernel (token-parallel row linears): rows [d * a2a_per, (d+1) * a2a_per) go to rank d's
+  // buffer (unicast peer pointers qd / sfd, already offset to THIS rank's columns / scale atoms inside the destination's
+  // [a2a_per, K_total] activation), whose packed rows are a2a_pitch bytes long and whose scale row blocks hold the atoms
+  // of all ranks (katoms[] then counts those).  a2a_per == 0: the gather form (q[] / sf[] are multicast addresses).
+  int a2a_per;
+  uint8_t* qd[kMaxTp][3];
+  uint8_t* sfd[kMaxTp][3];
+  uint32_t a2a_pitch[3];
   unsigned long long ag_timeout_ns;  // bound on the wait (option tp_timeout_ms): a lost peer must not hang the GPU
   uint32_t* ag_err;                  // local error word of the tp context: bit 2 = this wait timed out
   uint32_t ag_dbg;                   // timing experiments (option tp_debug >> 5)
@@ -429,7 +437,8 @@ struct QuantKernel {
   template <bool FULL>
   static __device__ __forceinline__ void compute_unit(const UnitCtx& cx, const UnitPtrs& up, uint32_t xs_a, int row0,
                                                       int nvalid, uint32_t wp_a = 0, const float* rinv = nullptr,
-                                                      uint32_t stage_a = 0, uint32_t stage_row = 0) {
+                                                      uint32_t stage_a = 0, uint32_t stage_row = 0, int a2a_per = 0,
+                                                      uint8_t* const* a2a_sf = nullptr) {
     const uint32_t meta = cx.meta;
     const bool active = (meta & 64u) != 0;
     const int fmt = (int)(meta & 15u);
@@ -495,8 +504,13 @@ struct QuantKernel {
       // l + 64h and l + 64h + 32 own bytes [8h, 8h + 8) of the atom's 16-byte line for row l -- lane 8q collects the four
       // groups from lanes 8q+2, +4, +6 and writes those 8 bytes with one store
       static_assert(RW == 1, "two rows per item");
-      const uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
+      uint32_t sfoff = (uint32_t)(row0 >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
       uint8_t* d = up.sfp + sfoff;
+      if (a2a_per > 0) {  // all-to-all: the row block lives in its owner's buffer (a2a_per is a multiple of 256)
+        const int dst = row0 / a2a_per, rl = row0 - dst * a2a_per;
+        sfoff = (uint32_t)(rl >> 7) * up.ka512 + (uint32_t)(row0 & 31) * 16u + (uint32_t)((row0 >> 5) & 3) * 4u;
+        d = a2a_sf[dst * 3 + ((meta >> 4) & 3u)] + cx.sfo + sfoff;
+      }
       const uint32_t v1 = __shfl_down_sync(0xffffffffu, sfb[0], 2), v2 = __shfl_down_sync(0xffffffffu, sfb[0], 4);
       const uint32_t v3 = __shfl_down_sync(0xffffffffu, sfb[0], 6);
       const uint32_t lo01 = __byte_perm(sfb[0], v1, 0x0040), lo23 = __byte_perm(v2, v3, 0x0040);  // first row : bytes 0
@@ -541,7 +555,13 @@ struct QuantKernel {
         const uint32_t o = c << 4;
         const uint4 v = lds128(stage_a + (uint32_t)j * stage_row + o);
         uint8_t* g;
-        if (o < rb0) g = p.q[0] + row * rb0 + o;
+        if (p.a2a_per > 0) {  // all-to-all: a peer-mapped unicast address in the row's owner
+          const int dst = (int)(row / p.a2a_per);
+          const int64_t rl = row - (int64_t)dst * p.a2a_per;
+          if (o < rb0) g = p.qd[dst][0] + rl * p.a2a_pitch[0] + o;
+          else if (o < rb0 + rb1) g = p.qd[dst][1] + rl * p.a2a_pitch[1] + (o - rb0);
+          else g = p.qd[dst][2] + rl * p.a2a_pitch[2] + (o - rb0 - rb1);
+        } else if (o < rb0) g = p.q[0] + row * rb0 + o;
         else if (o < rb0 + rb1) g = p.q[1] + row * rb1 + (o - rb0);
         else g = p.q[2] + row * rb2 + (o - rb0 - rb1);
         stg_v4<true>(g, v.x, v.y, v.z, v.w);
@@ -601,7 +621,8 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
   if (t == 0) claimed = atomicAdd(p.sched, 1u);
 
   if constexpr (NP == 1) {
-    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid, wp_unit, rinv, stage_cur, stage_row);
+    QK::template compute_unit<FULL>(ctx0, up0, xs_a, row0, nvalid, wp_unit, rinv, stage_cur, stage_row, MC ? p.a2a_per : 0,
+                                    MC ? &p.sfd[0][0] : nullptr);
   } else {
 #pragma unroll
     for (int ps = 0; ps < NP; ++ps) {
@@ -923,6 +944,14 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
     p.ag_tp = ag->tp;
     p.ag_timeout_ns = (unsigned long long)options().tp_timeout_ms * 1000000ull;
     p.ag_err = ag->err;
+    p.a2a_per = ag->a2a_per;
+    if (ag->a2a_per > 0) {
+      for (int d = 0; d < ag->tp && d < kMaxTp; ++d)
+        for (int i = 0; i < 3; ++i) {
+          p.qd[d][i] = ag->qd[d][i];
+          p.sfd[d][i] = ag->sfd[d][i];
+        }
+    }
     p.ag_dbg = (uint32_t)(options().tp_debug >> 5);
     for (int d = 0; d < ag->tp && d < kMaxTp; ++d) p.ag_arrived[d] = ag->arrived[d];
   }
@@ -944,6 +973,12 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
     p.rowbytes[i] = (int64_t)ks[i] * fmt[i] / 8;
     p.q[i] = q[i];
     p.sf[i] = s[i];
+  }
+  if (ag != nullptr && ag->a2a_per > 0) {
+    for (int i = 0; i < 3; ++i) {
+      p.katoms[i] = ag->a2a_katoms[i];       // scale row blocks of the DESTINATION hold the atoms of all ranks
+      p.a2a_pitch[i] = ag->a2a_pitch[i];
+    }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int force = (int)options().quant_rows;

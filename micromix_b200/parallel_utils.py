@@ -74,6 +74,30 @@ def row_shard_plan(reorder_index: torch.Tensor, p6_num: int, p8_num: int, tp: in
     return k0, k1, local.contiguous(), p4, p6, p8
 
 
+def token_parallel_plan(reorder_index: torch.Tensor, p6_num: int, p8_num: int, tp: int):
+    """The rank-blocked permutation of a K-sharded linear whose activation CODES are exchanged instead of its partial sums
+    (TokenParallelQLinear).  Rank r quantizes its slice exactly as in the row-parallel form (row_shard_plan: rank-local
+    permutation and split); concatenating the ranks' FP4 channels, then their FP6, then their FP8 channels gives ONE
+    global permutation and split under which a single three-segment GEMM over the full K reproduces the same quantization
+    groups.  Returns (perm int16 [K], (P4, P6, P8) totals, shards) with shards[r] = dict(k0, k1, index, split, offset):
+    offset[i] = first channel of rank r's block inside total segment i."""
+    K = reorder_index.numel()
+    shards, seg = [], [[], [], []]
+    tot = [0, 0, 0]
+    for r in range(tp):
+        k0, k1, lidx, p4, p6, p8 = row_shard_plan(reorder_index, int(p6_num), int(p8_num), tp, r)
+        g = lidx.to(torch.int64) + k0
+        parts = (g[:p4], g[p4:p4 + p6], g[p4 + p6:])
+        off = tuple(tot)
+        for i in range(3):
+            seg[i].append(parts[i])
+            tot[i] += parts[i].numel()
+        shards.append(dict(k0=k0, k1=k1, index=lidx, split=(p4, p6, p8), offset=off))
+    perm = torch.cat([torch.cat(seg[0]), torch.cat(seg[1]), torch.cat(seg[2])]).to(torch.int16)
+    assert perm.numel() == K
+    return perm.contiguous(), tuple(tot), shards
+
+
 def all_reduce_sum(t: torch.Tensor, group=None, async_op: bool = False):
     """Sum over the tensor-parallel group (NCCL on GPUs, gloo in the CPU tests); no-op without a group."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -213,8 +237,8 @@ class PeerWorkspace:
         import ctypes
         from . import _lib
         lib = _lib.load()
-        if gather and tp != 1:
-            raise ValueError("the simulated gather channel needs tp == 1 (no multicast mapping inside one process)")
+        # (tp > 1 with a gather channel: only the all-to-all forms work -- they use unicast pointers; quantize_allgather
+        # needs the multicast mapping, which one process can only stand in for at tp == 1)
         nbytes = int(lib.mmx_tp_workspace_bytes_ex(M_cap, N_cap, tp, *(gather or (0, 0))))
         ptrs = []
         for _ in range(tp):
@@ -225,7 +249,7 @@ class PeerWorkspace:
         out = [cls(M_cap, N_cap, _sim=(tp, r, ptrs), gather=gather) for r in range(tp)]
         for r, w in enumerate(out):
             w.own = ptrs[r]
-            if gather:
+            if gather and tp == 1:
                 w.multicast_ptr = ptrs[r]
                 _lib.check(lib.mmx_tp_ctx_set_multicast(w.ctx, ptrs[r], 0), "mmx_tp_ctx_set_multicast")
         return out
@@ -335,6 +359,40 @@ class PeerWorkspace:
         from . import _lib
         _lib.check(rc, "mmx_tp_matmul_gathered")
         return out
+
+    # ---- token-parallel row linears: all-to-all of packed codes (mmx_tp_quantize_alltoall / mmx_tp_matmul_exchanged)
+    def quantize_alltoall(self, x_local, M, index_local, split_local, seg_tot, seg_off):
+        """Quantize this rank's K slice of all M rows (x_local bf16 [M, K/tp]) and write the codes of every row into the
+        exchange buffer of the rank that owns the row, at this rank's channel block of each segment."""
+        ctypes = self._ctypes
+        KN, KS, KO = (int(v) for v in split_local)
+        if x_local.dim() != 2 or x_local.shape != (M, KN + KS + KO) or x_local.dtype != torch.bfloat16 or not x_local.is_contiguous():
+            raise ValueError(f"x_local must be contiguous bf16 [{M}, {KN + KS + KO}], got {tuple(x_local.shape)} {x_local.dtype}")
+        tot = (ctypes.c_int32 * 3)(*[int(v) for v in seg_tot])
+        off = (ctypes.c_int32 * 3)(*[int(v) for v in seg_off])
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_tp_quantize_alltoall(self.ctx, x_local.data_ptr(), M, KN + KS + KO, index_local.data_ptr(), KN, KS,
+                                                   KO, tot, off, None, torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_tp_quantize_alltoall")
+
+    def matmul_exchanged(self, M, W, seg_tot, bias=None, out=None):
+        """The GEMM over the full K on THIS rank's rows of the exchanged activation -> (bf16 [rows, N], row0)."""
+        ctypes = self._ctypes
+        N = W[0].size(0)
+        lo, hi = self.shard_range(M)
+        p = lambda t: t.data_ptr() if t is not None and t.numel() > 0 else None
+        if out is None:
+            out = torch.empty((hi - lo, N), dtype=torch.bfloat16, device=self.device)
+        r0, rows = ctypes.c_int64(), ctypes.c_int64()
+        with torch.cuda.device(self.device):
+            rc = self.lib.mmx_tp_matmul_exchanged(self.ctx, p(W[0]), p(W[1]), p(W[2]), p(W[3]), p(W[4]), p(W[5]), M, N,
+                                                  int(seg_tot[0]), int(seg_tot[1]), int(seg_tot[2]), 1, p(bias),
+                                                  out.data_ptr() if out.numel() else None, ctypes.byref(r0), ctypes.byref(rows),
+                                                  torch.cuda.current_stream().cuda_stream)
+        from . import _lib
+        _lib.check(rc, "mmx_tp_matmul_exchanged")
+        return out, int(r0.value)
 
     def _tick(self, every: int = 256):
         """A lost / slow peer costs a timeout and POISONED (NaN) rows, never silently wrong activations; the error word is
@@ -458,6 +516,38 @@ class RowParallelQLinear(nn.Module):
             if w is not None:
                 w.wait()
         return y.reshape(bsz, q_len, -1)
+
+
+class TokenParallelQLinear(nn.Module):
+    """o / down as a TOKEN-parallel linear: the alternative to RowParallelQLinear (see include/micromix_b200.h,
+    "TOKEN-PARALLEL row linears").  The MXFP4 weight is replicated (quantized once with the rank-blocked permutation of
+    token_parallel_plan); forward(x_local [b, s, K/tp]) quantizes this rank's K slice of all tokens, exchanges the packed
+    codes all-to-all over NVLink and returns (bf16 [rows, N], row0): this rank's token rows of the FULL-K product --
+    bit-identical to QLinearLayer(weight, perm, P8, P6) on one GPU, and sequence-sharded like a reduce-scatter's output."""
+
+    def __init__(self, originalLayer: nn.Linear, p8_num, p6_num, reorder_index, tp_group, workspace: PeerWorkspace):
+        super().__init__()
+        from .qLinearLayer import QLinearLayer
+        if workspace is None or not workspace.gather[0]:
+            raise ValueError("TokenParallelQLinear needs a PeerWorkspace with a gather channel")
+        self.workspace = workspace
+        self.tp, self.rank = workspace.tp, workspace.rank
+        perm, tot, shards = token_parallel_plan(reorder_index, int(p6_num), int(p8_num), self.tp)
+        self.seg_tot = tot
+        me = shards[self.rank]
+        self.k_range = (me["k0"], me["k1"])
+        self.split_local, self.seg_off = me["split"], me["offset"]
+        self.register_buffer("index_local", me["index"].to(torch.int16).cuda().contiguous())
+        self.linear = QLinearLayer(originalLayer, tot[2], tot[1], perm)  # replicated MXFP4 weight, rank-blocked order
+        self.in_features, self.out_features = me["k1"] - me["k0"], originalLayer.out_features
+
+    @torch.no_grad()
+    def forward(self, x):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        M = x2.shape[0]
+        self.workspace.quantize_alltoall(x2, M, self.index_local, self.split_local, self.seg_tot, self.seg_off)
+        lin = self.linear
+        return self.workspace.matmul_exchanged(M, (lin.BN, lin.BS, lin.BO, lin.SFBN, lin.SFBS, lin.SFBO), self.seg_tot, lin.bias)
 
 
 def forward_row_shard(layer: "RowParallelQLinear", x):

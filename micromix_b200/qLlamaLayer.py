@@ -14,6 +14,6 @@ from ._qdecoder import QGatedMLP as QLlamaMLP  # noqa: F401  (qLlamaLayer.py:324
 
 class QLlamaDecoderLayer(QDecoderLayer):
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
-                 workspace=None, sequence_parallel=False):
+                 workspace=None, sequence_parallel=False, token_parallel_rows=False):
         super().__init__(originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group, fused, workspace,
-                         sequence_parallel)
+                         sequence_parallel, token_parallel_rows)

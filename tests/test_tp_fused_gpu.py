@@ -259,3 +259,47 @@ def test_tp_layers_multiprocess(cuda):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"ok": true' in r.stdout
+
+
+@pytest.mark.parametrize("tp,M,N,K", [(1, 300, 512, 1024), (2, 1024, 512, 2048), (4, 1500, 768, 4096), (8, 2100, 512, 4096),
+                                      (2, 200, 256, 1024)])
+def test_token_parallel_exchange_equals_single_gpu_linear(cuda, mmx_lib, tp, M, N, K):
+    """The all-to-all of packed codes (mmx_tp_quantize_alltoall -> mmx_tp_matmul_exchanged), `tp` simulated ranks on one GPU
+    (the exchange uses unicast peer pointers only): rank r's rows must equal, bit for bit, the rows of ONE QLinearLayer over
+    the full K with the rank-blocked permutation of token_parallel_plan -- three rounds, so the channel counters are re-used,
+    ranks with no rows included (M = 200 at tp = 2)."""
+    import torch.nn as nn
+    from micromix_b200.parallel_utils import PeerWorkspace, TokenParallelQLinear, token_parallel_plan
+    from micromix_b200.qLinearLayer import QLinearLayer
+    mmx_lib.mmx_set_option(b"tp_timeout_ms", 4000)
+    try:
+        idx = H.make_index(K, seed=tp)
+        p8, p6 = (K // 8) // 128 * 128, (K // 4) // 128 * 128
+        lin = nn.Linear(K, N, bias=False).to(torch.bfloat16)
+        lin.weight.data = H.make_weights(N, K, seed=7)
+        perm, tot, shards = token_parallel_plan(idx, p6, p8, tp)
+        single = QLinearLayer(lin, tot[2], tot[1], perm)
+        works = PeerWorkspace.simulate(tp, M, N, gather=(M, K))
+        layers = [TokenParallelQLinear(lin, p8, p6, idx, None, works[r]) for r in range(tp)]
+        streams = [torch.cuda.Stream() for _ in range(tp)]
+        per = works[0].shard_rows(M)
+        for rnd in range(3):
+            x = H.make_activations(M, K, idx, seed=300 + rnd).to(cuda)
+            want = single(x.unsqueeze(0)).squeeze(0)
+            torch.cuda.synchronize()
+            outs = []
+            for r in range(tp):
+                k0, k1 = layers[r].k_range
+                with torch.cuda.stream(streams[r]):
+                    outs.append(layers[r](x[:, k0:k1].unsqueeze(0)))
+            torch.cuda.synchronize()
+            for r in range(tp):
+                y, row0 = outs[r]
+                lo, hi = min(M, per * r), min(M, per * (r + 1))
+                assert works[r].status() == 0, f"rank {r}: a wait timed out (round {rnd})"
+                assert row0 == lo and y.shape == (hi - lo, N)
+                assert torch.equal(y, want[lo:hi]), f"rank {r} round {rnd}"
+        for w in works:
+            w.close()
+    finally:
+        mmx_lib.mmx_set_option(b"tp_timeout_ms", 10000)

@@ -111,13 +111,14 @@ def qwen_tp(args, rank, world, dev):
     idx, p6, p8 = S.make_calibration(cfg, 0)
     b, s = max(1, args.tokens // 2048), 2048
     ws = None
-    sp = bool(args.sp) and world > 1 and args.tp_reduce == "fused"
+    sp = bool(args.sp or args.tpr) and world > 1 and args.tp_reduce == "fused"
     if world > 1 and args.tp_reduce == "fused":
         from micromix_b200.parallel_utils import PeerWorkspace
         ws = PeerWorkspace(b * s, cfg["hidden_size"], group=group, device=dev,
-                           gather=(b * s, cfg["hidden_size"]) if sp else None)
+                           gather=(b * s, max(cfg["hidden_size"], -(-cfg["intermediate_size"] // world // 128) * 128))
+                           if sp else None)
     q = QQwen2DecoderLayer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws, sequence_parallel=sp,
-                           fused=bool(args.fused))
+                           fused=bool(args.fused), token_parallel_rows=bool(args.tpr))
     del layer
     torch.cuda.empty_cache()
     b, s = max(1, args.tokens // 2048), 2048
@@ -144,6 +145,8 @@ def qwen_tp(args, rank, world, dev):
     tokens = b * s
     how = "NCCL all-reduce" if ws is None else (f"sequence parallel: fused GEMM->reduce-scatter + multicast all-gather of packed "
                                                  f"codes ({ws.mode})" if sp else f"fused GEMM->all-reduce ({ws.mode})")
+    if args.tpr and sp:
+        how = "token-parallel o/down (replicated MXFP4 weights, all-to-all of packed codes) + multicast all-gather of codes"
     best = ms_graph if isinstance(ms_graph, float) else ms
     return {"config": f"Qwen2.5-32B-shaped decoder layer, {tokens} tokens, tensor parallel {world} (column qkv/gate_up, "
                       f"row o/down + {how})", "ms_per_layer": ms, "ms_per_layer_cuda_graph": ms_graph,
@@ -212,6 +215,7 @@ def main():
     ap.add_argument("--tp-reduce", default="fused", choices=["fused", "nccl"], help="qwen_tp: row-parallel reduction")
     ap.add_argument("--loop", action="store_true", help="mixtral_ep: the per-expert Python loop instead of the grouped path")
     ap.add_argument("--sp", action="store_true", help="qwen_tp: sequence-parallel layer (reduce-scatter + all-gather of codes)")
+    ap.add_argument("--tpr", action="store_true", help="qwen_tp: sequence-parallel layer with token-parallel o / down")
     ap.add_argument("--fused", action="store_true", help="prefill: RMSNorm and SiLU*up run inside the quantizers (QDecoderLayer(fused=True))")
     args = ap.parse_args()
     rank, world, dev = setup()

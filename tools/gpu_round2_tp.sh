@@ -23,6 +23,8 @@ if [ "$3" != "quick" ]; then
   echo "qwen sp rc=$?" >> $OUT/rc.txt
   timeout 200 $TR --master-port 29716 tools/bench_models.py qwen_tp --iters 3 --fused --tp-reduce nccl > $OUT/qwen_nccl_tp$N.json 2> $OUT/qwen_nccl_tp$N.err
   echo "qwen nccl rc=$?" >> $OUT/rc.txt
+  timeout 200 $TR --master-port 29719 tools/bench_models.py qwen_tp --iters 3 --tpr > $OUT/qwen_tpr_tp$N.json 2> $OUT/qwen_tpr_tp$N.err
+  echo "qwen tpr rc=$?" >> $OUT/rc.txt
   # 4. BASELINE config 5: Mixtral 8x7B expert FFN, expert parallel N: grouped path (fused SiLU*up) and the expert loop
   timeout 200 $TR --master-port 29717 tools/bench_models.py mixtral_ep --iters 3 --fused > $OUT/mixtral_grouped_ep$N.json 2> $OUT/mixtral_grouped_ep$N.err
   echo "mixtral grouped rc=$?" >> $OUT/rc.txt

@@ -105,9 +105,10 @@ def main():
     del fused
     ws.close()
 
-    y4 = None
+    y4 = y5 = None
     try:
-        ws2 = PeerWorkspace(M, cfg["hidden_size"], group=group, device=dev, gather=(M, cfg["hidden_size"]))
+        ws2 = PeerWorkspace(M, cfg["hidden_size"], group=group, device=dev,
+                            gather=(M, max(cfg["hidden_size"], -(-cfg["intermediate_size"] // world // 128) * 128)))
     except Exception as e:  # noqa: BLE001
         ws2 = None
         res["sp_note"] = f"sequence parallel unavailable: {e!r}"[:160]
@@ -126,6 +127,16 @@ def main():
         res["sp_mode"] = ws2.mode
         res["sp_status"] = ws2.status()
         del sp
+        # (5) the same with token-parallel o / down (replicated weights, all-to-all of packed codes)
+        tl = Layer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws2, sequence_parallel=True, token_parallel_rows=True)
+        for _ in range(2):
+            yt = tl(xs, position_embeddings=pos)[0].reshape(hi - lo, cfg["hidden_size"])
+        buf.zero_()
+        buf[: hi - lo] = yt
+        dist.all_gather(parts, buf)
+        y5 = torch.cat(parts, 0)[:M].reshape(b, s, -1)
+        res["tpr_status"] = ws2.status()
+        del tl
         ws2.close()
 
     def check(name, a, ref, mx_tol, mean_tol):
@@ -144,6 +155,23 @@ def main():
         # the sequence-parallel layer against the all-reduce layer with the same fused RMSNorm: same codes, same GEMMs, same sums
         exact4 = world == 2 and res.get("sp_mode") == "push"
         check("sp_vs_nccl_fused_norm", y4, y2f, 0.0 if exact4 else 2e-1, 0.0 if exact4 else 2e-3)
+    if y5 is not None:
+        # token-parallel o / down == ONE GPU running o_proj / down_proj with the rank-blocked permutation (the same quantization
+        # groups as the K-sharded layers, one fp32 accumulation over the full K): rebuilt here on every rank, bit for bit
+        from micromix_b200.parallel_utils import token_parallel_plan
+        idx6, p66, p86 = dict(idx), dict(p6), dict(p8)
+        for key in ("layers.0.self_attn.o_proj.input", "layers.0.mlp.down_proj.input"):
+            perm, tot, _ = token_parallel_plan(idx[key], int(p6[key]), int(p8[key]), world)
+            idx6[key], p66[key], p86[key] = perm, tot[1], tot[2]
+        one = Layer(layer, False, p86, p66, idx6, 0)
+        one.fused = True  # RMSNorm inside the quantizer like the parallel layers; SiLU * up stays a torch op like theirs
+        y6 = one(x0, position_embeddings=pos)[0]
+        del one
+        check("tpr_vs_single_gpu_rank_blocked", y5, y6, 0.0, 0.0)
+        # ... and against the K-sharded layers: bf16-rounded partial sums vs one accumulator (reported, loose bound)
+        check("tpr_vs_nccl_fused_norm", y5, y2f, 1.0, 5e-2)
+        e5 = rel(y5, yf)
+        res["tpr_quant_error_vs_float"] = {"max_rel": e5[0], "mean_rel": e5[1]}
     # against the unsharded layer the K-sharded linears quantize OTHER 32-channel groups (rank-local permutation), so the
     # outputs differ by quantization noise, not rounding.  The yardstick is the unquantized layer: tensor parallelism must not
     # make the quantization error worse than the 1-GPU layer's (both errors are reported).
