@@ -793,8 +793,16 @@ def check_tp_parity(lins, lib, ws, tp_mode, rank, world, dev):
             ulps = _bf16_ulps(got, ref[row0:row0 + rows])
             ulps_nccl = _bf16_ulps(got, nccl[row0:row0 + rows])
             ok = ulps == 0 if exact_expected else ulps <= 1
+            if ws is None:
+                # --tp-reduce nccl (the baseline arm): ncclAllReduce rounds to bf16 at every hop of its ring / tree, so near
+                # a cancellation its sum can sit on the other side of zero -- bounded in absolute terms instead of in steps
+                err = float((got.float() - ref[row0:row0 + rows].float()).abs().max() / ref.float().pow(2).mean().sqrt())
+                ok = err <= 1e-1  # (measured at tp = 4: a few per cent of the rms at the worst of 33 M elements)
             rec = {"kind": "row-parallel", "rows": [row0, row0 + rows], "max_bf16_steps_vs_fp32_rank_order_sum": ulps,
-                   "max_bf16_steps_vs_matmul+ncclAllReduce": ulps_nccl, "bound": 0 if exact_expected else 1}
+                   "max_bf16_steps_vs_matmul+ncclAllReduce": ulps_nccl,
+                   "bound": "max |diff| <= 1e-1 rms (NCCL arm)" if ws is None else (0 if exact_expected else 1)}
+            if ws is None:
+                rec["max_abs_diff_over_rms_vs_fp32_rank_order_sum"] = err
             if tp_mode != "sp":  # all-reduce: every rank must hold the same bits
                 h = got.view(torch.int16).to(torch.int64).sum().reshape(1)
                 hs = [torch.empty_like(h) for _ in range(world)]

@@ -103,6 +103,9 @@ def main():
     res["fused_mode"] = ws.mode
     res["fused_status"] = ws.status()
     del fused
+    fusedf = Layer(layer, False, p8, p6, idx, 0, tp_group=group, workspace=ws, fused=True)  # + RMSNorm inside the quantizer
+    y3f = fusedf(x0, position_embeddings=pos)[0].clone()
+    del fusedf
     ws.close()
 
     y4 = y5 = None
@@ -148,13 +151,18 @@ def main():
     # same shards, different reduction paths: a bf16 rounding step of the summed output (and its propagation through the
     # MLP's quantizers: a flipped 4-bit code moves one product term by up to half a quantization step).  At tp = 2 on the
     # push data path every path computes bf16(fp32(a) + fp32(b)): the results are bit-identical.
+    # Where the two paths sum the SAME bf16 partials in another order (NVSwitch vs NCCL's ring), single bf16 steps of the
+    # summed output flip 4-bit codes in the next quantizer: the layer outputs then agree at the 1-2 % level (mean), not at
+    # rounding level -- the exact invariants are the ones marked 0.0 below.
     exact = world == 2 and res.get("fused_mode") == "push"
-    check("fused_vs_nccl", y3, y2, 0.0 if exact else 2e-1, 0.0 if exact else 2e-3)
+    check("fused_vs_nccl", y3, y2, 0.0 if exact else 1.0, 0.0 if exact else 5e-2)
     check("fused_repeat", y3b, y3, 0.0, 0.0)
     if y4 is not None:
-        # the sequence-parallel layer against the all-reduce layer with the same fused RMSNorm: same codes, same GEMMs, same sums
+        # the sequence-parallel layer against the FUSED all-reduce layer with the same fused RMSNorm: same codes, same GEMMs,
+        # the same reduction (rank-ordered fp32 sum on the push path, the switch's sum in-switch): bit-identical
+        check("sp_vs_fused_allreduce_fused_norm", y4, y3f, 0.0, 0.0)
         exact4 = world == 2 and res.get("sp_mode") == "push"
-        check("sp_vs_nccl_fused_norm", y4, y2f, 0.0 if exact4 else 2e-1, 0.0 if exact4 else 2e-3)
+        check("sp_vs_nccl_fused_norm", y4, y2f, 0.0 if exact4 else 1.0, 0.0 if exact4 else 5e-2)
     if y5 is not None:
         # token-parallel o / down == ONE GPU running o_proj / down_proj with the rank-blocked permutation (the same quantization
         # groups as the K-sharded layers, one fp32 accumulation over the full K): rebuilt here on every rank, bit for bit
