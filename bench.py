@@ -70,6 +70,33 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and, by first touch, its pinned host buffers) to the NUMA node the GPU hangs off: with one process
+    per GPU, eight ranks staging their host copies through one socket's memory controllers is what bounded the round-1
+    end-to-end numbers at N > 1.  Best effort: returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]  # 0000:xx:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return "no NUMA node reported for the GPU"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return f"GPU on NUMA node {node}, none of its CPUs allowed here"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to NUMA node {node} ({len(allowed)} CPUs)"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({e!r})"[:120]
+
+
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
@@ -373,6 +400,7 @@ def run_ours(args, rank, world, local_rank):
             raise ValueError(lib.mmx_last_error().decode())
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa_note = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else "off"
     M = args.tokens
     peaks = load_peaks()
     # token chunks: at N > 1 the step runs as C micro-batches so that the all-reduce of one chunk's row-parallel
@@ -597,7 +625,7 @@ def run_ours(args, rank, world, local_rank):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "mxfp4/mxfp6/mxfp8 x mxfp4 -> fp32 acc -> bf16",
                 "data": "synthetic", "tokens_per_s": M / ms_step * 1e3, "config": workload_config(args, world),
-                "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks,
+                "gpu_launches": int(launches), "e2e": e2e, "clocks": clocks, "host_numa": numa_note,
                 "roofline": {"kernel": "mixed_gemm_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": peak_eff,
                              "unit": "TFLOP/s", "frac": gemm_tflops / peak_eff, "traffic": traffic,
                              "traffic_note": "DRAM bytes of the step's GEMM launches (sum; per launch under per_linear) from the "
@@ -924,9 +952,42 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # What bounds it: the same bytes over the same two copy streams with NO kernels in between (all ranks at once, so the
+    # contention for the host's memory / PCIe root ports is the same as in the timed step).
+    ydev = [torch.empty((y.shape[0], y.shape[1]), dtype=torch.bfloat16, device=dev) for y in yout]
+
+    def copies_only():
+        for x, y, yd in zip(xin, yout, ydev):
+            with torch.cuda.stream(s_in):
+                xd = x.to(dev, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                y.copy_(yd, non_blocking=True)
+            del xd
+
+    copies_only()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        copies_only()
+    torch.cuda.synchronize()
+    dc = (time.perf_counter() - t0) / n
+    if world > 1:
+        t = torch.tensor([dc], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dc = float(t.item())
+    if dc >= 0.75 * dt:
+        bound = ("host<->device copies: the step's bytes alone (no kernels, all ranks copying at once) take %.2f ms of the "
+                 "%.2f ms step" % (dc * 1e3, dt * 1e3))
+    else:
+        bound = ("not the copies (%.2f ms alone of a %.2f ms step): host-side enqueue and cross-rank launch skew"
+                 % (dc * 1e3, dt * 1e3))
     return {"value": total_flops / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "tokens_per_s": M / dt,
-            "steps_timed": n,
+            "steps_timed": n, "copies_only_ms": dc * 1e3, "bound": bound,
+            "pcie_gbps_per_rank": {"h2d": h2d / dt / 1e9, "d2h": d2h / dt / 1e9,
+                                   "copies_only_h2d": h2d / dc / 1e9, "copies_only_d2h": d2h / dc / 1e9},
             "api": "QLinearLayer.forward on pinned host tensors; per linear: H2D copy, quantize, GEMM (+ reduction), D2H "
                    "copy, on three streams (copy-in / layers / copy-out), steps pipelined, one synchronize at the end of the "
                    "timed region; bytes are per rank.  Sequence-parallel mode: a rank uploads only ITS rows of a replicated "
@@ -1019,6 +1080,7 @@ def main():
     ap.add_argument("--gemm-ctas", type=int, default=0, help="N>1: cap the persistent GEMM grid (SMs left to NCCL)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-prefill", action="store_true", help="skip the 32-layer Llama-3-8B prefill leg (N = 1)")
     ap.add_argument("--prefill-batch", type=int, default=8)
     ap.add_argument("--prefill-seq", type=int, default=2048)
