@@ -290,7 +290,14 @@ struct UnitPtrs {
 // each aligned 8-channel chunk (exactly the 16 bytes one thread loads), then a perfect binary tree over the chunk
 // index -- five shuffle levels inside a warp, the warp sums through shared memory, seven more levels redone by every
 // warp.  y = bf16((x * w) * rinv) is applied in the compute phase with the weight staged in PERMUTED order.
-template <int R, int NLD, int NP, int TABMODE, bool NORM = false, bool MC = false>
+//
+// DEPTH > 0 (EXPERIMENT, option quant_variant = 2 | 3; not the default): the rows of the next DEPTH items are in flight at
+// any time, copied by cp.async into a per-thread ring of raw 16-byte chunks in shared memory (a thread reads back only
+// what it copied itself: no barrier, no bank conflicts) instead of ONE item held in registers.  Measured SLOWER than the
+// register prefetch at every shape (profiles/r02_quantize_depth.log: 8192 x 4096 22.9 vs 21.0 us, 65536 x 4096 144.9 vs
+// 128.3 us): the kernel is not short of bytes in flight -- four CTAs per SM with one 16 KB item each already cover the
+// DRAM latency; the extra shared-memory round trip costs more than the deeper queue gains.
+template <int R, int NLD, int NP, int TABMODE, bool NORM = false, bool MC = false, int DEPTH = 0>
 struct QuantKernel {
   static constexpr int RW = R / 2;          // 32-bit words per slot (two rows per word)
   static constexpr int SLOT = 2 * R;        // bytes per slot
@@ -338,7 +345,7 @@ struct QuantKernel {
   // EXACT: NLD * T * 8 == K, no chunk predicate.  FULL: all R rows exist.
   template <bool FULL, bool EXACT>
   static __device__ __forceinline__ void prefetch(const QuantParams& p, const uint16_t* xt, int row0, int t, int T, int K8,
-                                                  uint4 (&pre)[NLD][R]) {
+                                                  uint4 (&pre)[NLD][R], uint32_t raw_a = 0) {
     const int K = p.K;
     const uint16_t* b0 = xt + (int64_t)row0 * K;
     const int64_t rs = (int64_t)32 * K;  // elements between two rows of the item
@@ -351,8 +358,25 @@ struct QuantKernel {
         bj = xt + (int64_t)__ldg(p.row_src + ((FULL || j < nvalid) ? row0 + 32 * j : row0)) * K;
 #pragma unroll
       for (int i = 0; i < NLD; ++i)
-        if (EXACT || i * T + t < K8) pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
+        if (EXACT || i * T + t < K8) {
+          if constexpr (DEPTH > 0)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_a + 16u * (uint32_t)((j * NLD + i) * T + t)),
+                         "l"(bj + (size_t)i * T * 8)
+                         : "memory");
+          else
+            pre[i][j] = ld_stream_v4(bj + (size_t)i * T * 8);
+        }
     }
+  }
+
+  // DEPTH > 0: this thread's chunks of the oldest item in the ring -> registers
+  template <bool EXACT>
+  static __device__ __forceinline__ void load_raw(uint32_t raw_a, int t, int T, int K8, uint4 (&pre)[NLD][R]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+      for (int i = 0; i < NLD; ++i)
+        if (EXACT || i * T + t < K8) pre[i][j] = lds128(raw_a + 16u * (uint32_t)((j * NLD + i) * T + t));
   }
 
   // ---- scatter: prefetched registers -> shared memory at the PERMUTED channel position, rows interleaved
@@ -579,14 +603,21 @@ struct QuantKernel {
 // permuted RMSNorm weights.
 // MC: stg_a = the two staging buffers of the packed codes; the PREVIOUS item's codes leave right after this item's barrier
 // (every thread has finished the previous compute by then, and the buffer is not written again before the next barrier).
-template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT, bool NORM, bool MC>
-__device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_t* xt, int row0, int n, int t, int T, int K8,
-                                             int nunits, uint32_t xs_a, uint32_t tab_a, uint32_t ctx_a,
+// DEPTH > 0: s_next is a ring of DEPTH + 1 entries (item n + k at slot (n + k) % (DEPTH + 1)); the rows of items n ..
+// n + DEPTH - 1 are in flight on entry (cp.async groups, oldest first), item n + DEPTH is issued here.
+template <typename QK, int R, int NLD, int NP, int NBUF, bool FULL, bool EXACT, bool NORM, bool MC, int DEPTH>
+__device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_t* xt, int row0, int rows, int n, int t, int T,
+                                             int K8, int nunits, uint32_t xs_a, uint32_t tab_a, uint32_t ctx_a,
                                              uint4 (&pre)[NLD][R], int* s_next, const UnitCtx& ctx0, const UnitPtrs& up0,
                                              uint32_t ss_a, uint32_t wp_unit, uint32_t stg_a, uint32_t stage_row,
-                                             int& prev_row0, int& prev_nvalid) {
-  const int rows = (int)p.rows;
+                                             int& prev_row0, int& prev_nvalid, uint32_t raw_a, uint32_t raw_bytes) {
+  constexpr int DE = DEPTH > 0 ? DEPTH : 1, RING = DE + 1;
   const int nvalid = FULL ? R : min(R, (rows - 1 - row0) / 32 + 1);
+  const uint32_t raw_cur = raw_a + (uint32_t)(n % DE) * raw_bytes;
+  if constexpr (DEPTH > 0) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    QK::template load_raw<EXACT>(raw_cur, t, T, K8, pre);
+  }
   QK::template scatter<FULL, EXACT>(nvalid, t, T, K8, xs_a, tab_a, pre, ss_a);
   __syncthreads();
   const uint32_t stage_cur = stg_a + (uint32_t)(n & 1) * (uint32_t)R * stage_row;
@@ -610,13 +641,15 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
       rinv[j] = __frcp_rn(__fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)p.K), p.eps)));
     }
   }
-  // the next item's rows: in flight during the compute below
-  const int next_row0 = s_next[(n + 1) & 1];
-  if (next_row0 < rows) {
-    if (next_row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, next_row0, t, T, K8, pre);
-    else QK::template prefetch<false, EXACT>(p, xt, next_row0, t, T, K8, pre);
+  // the rows of item n + DE: in flight during the compute below (and, DEPTH > 1, during the next DEPTH - 1 items)
+  const int next_row0 = s_next[(n + 1) % RING];
+  const int pf_row0 = (DE == 1) ? next_row0 : s_next[(n + DE) % RING];
+  if (pf_row0 < rows) {
+    if (pf_row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, pf_row0, t, T, K8, pre, raw_cur);
+    else QK::template prefetch<false, EXACT>(p, xt, pf_row0, t, T, K8, pre, raw_cur);
   }
-  // dynamic schedule: thread 0 claims the item after next now; the answer is needed one whole item later
+  if constexpr (DEPTH > 0) asm volatile("cp.async.commit_group;" ::: "memory");
+  // dynamic schedule: thread 0 claims item n + DE + 1 now; the answer is needed one whole item later
   unsigned int claimed = 0;
   if (t == 0) claimed = atomicAdd(p.sched, 1u);
 
@@ -637,18 +670,19 @@ __device__ __forceinline__ int quant_process(const QuantParams& p, const uint16_
       QK::template compute_unit<FULL>(cx, up, xs_a, row0, nvalid);
     }
   }
-  if (t == 0) s_next[n & 1] = QK::item_row0((int)(claimed + 2u * gridDim.x), p.num_items, rows);
+  if (t == 0) s_next[n % RING] = QK::item_row0((int)(claimed + (unsigned)RING * gridDim.x), p.num_items, (int)p.rows);
   if constexpr (NBUF == 1) __syncthreads();  // every read of xs is done before the next item's scatter overwrites it
   return next_row0;
 }
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT, bool NORM, bool MC = false>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool EXACT, bool NORM, bool MC = false, int DEPTH = 0>
 __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __grid_constant__ QuantParams p) {
   static_assert(R == 4 || R == 2, "rows per item");
   static_assert(NBUF == 1 || (NBUF == 2 && TABMODE != 2), "absolute table addresses cannot follow a second xs buffer");
   static_assert(!NORM || NP == 1, "the fused RMSNorm keeps a thread's weights addressable by thread index");
   static_assert(!MC || (R == 2 && NP == 1), "the multicast path is written for two rows per item, one unit per thread");
-  using QK = QuantKernel<R, NLD, NP, TABMODE, NORM, MC>;
+  using QK = QuantKernel<R, NLD, NP, TABMODE, NORM, MC, DEPTH>;
+  constexpr int DE = DEPTH > 0 ? DEPTH : 1, RING = DE + 1;
   const int T = blockDim.x;  // a multiple of 32 chosen by the launcher so that NP passes of T threads cover K/16 units
   extern __shared__ __align__(128) uint8_t smem[];
   const int K = p.K;
@@ -664,6 +698,9 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   const uint32_t stage_row = (uint32_t)(p.rowbytes[0] + p.rowbytes[1] + p.rowbytes[2]);
   const uint32_t stg_a = ctx_a + (NP > 1 ? (uint32_t)(NP * T * 16) : 0u) +
                          (NORM ? (uint32_t)K * 2u + (uint32_t)(NBUF * R * 512) : 0u);
+  // DEPTH > 0 only: the ring of raw rows, R * NLD * T chunks of 16 bytes per item, behind everything else
+  const uint32_t raw_a = stg_a + (MC ? 2u * (uint32_t)R * stage_row : 0u);
+  const uint32_t raw_bytes = (uint32_t)(R * NLD * 16) * (uint32_t)T;
   int prev_row0 = -1, prev_nvalid = 0;
   const int t = threadIdx.x;
   int rows = (int)p.rows;
@@ -672,12 +709,12 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   uint4 pre[NLD][R];  // prefetched rows of the next item
-  __shared__ int s_next[2];
+  __shared__ int s_next[RING];
   const int num_items = p.num_items;
-  // schedule: the first two rounds are static (item = blockIdx.x, blockIdx.x + gridDim.x), later items are claimed
-  // from a global counter one item ahead of their prefetch, so SMs that run ahead simply take more items
+  // schedule: the first RING rounds are static (item = blockIdx.x + k * gridDim.x), later items are claimed from a global
+  // counter one item ahead of their prefetch, so SMs that run ahead simply take more items
   int row0 = QK::item_row0((int)blockIdx.x, num_items, rows);
-  if (t == 0) s_next[1] = QK::item_row0((int)(blockIdx.x + gridDim.x), num_items, rows);
+  if (t >= 1 && t < RING) s_next[t] = QK::item_row0((int)(blockIdx.x + (unsigned)t * gridDim.x), num_items, rows);
 
   // ---- one-time per CTA: inverse permutation as swizzled slot positions.  Eight consecutive permuted positions
   // j = 8*j8 + e occupy 8*SLOT contiguous bytes of xs whose chunks share one swizzle mask, so position e is at
@@ -735,9 +772,14 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
     rows = min(rows, __ldg(p.rows_dev));
     if (row0 >= rows) row0 = rows;
   }
-  if (row0 < rows) {
-    if (row0 + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, row0, t, T, K8, pre);
-    else QK::template prefetch<false, EXACT>(p, xt, row0, t, T, K8, pre);
+#pragma unroll
+  for (int k = 0; k < DE; ++k) {  // the first DE items' rows
+    const int rk = (k == 0) ? row0 : QK::item_row0((int)(blockIdx.x + (unsigned)k * gridDim.x), num_items, (int)p.rows);
+    if (rk < rows) {
+      if (rk + 32 * (R - 1) < rows) QK::template prefetch<true, EXACT>(p, xt, rk, t, T, K8, pre, raw_a + (uint32_t)k * raw_bytes);
+      else QK::template prefetch<false, EXACT>(p, xt, rk, t, T, K8, pre, raw_a + (uint32_t)k * raw_bytes);
+    }
+    if constexpr (DEPTH > 0) asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if constexpr (MC) {
     // the gather buffers may be overwritten once EVERY rank has finished reading the previous gather (normally long ago)
@@ -782,9 +824,9 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
     const uint32_t xs_cur = xs_a + ((NBUF == 2 && (n & 1)) ? xs_bytes : 0u);
     const uint32_t ss_cur = ss_a + ((NBUF == 2 && (n & 1)) ? (uint32_t)(R * 512) : 0u);
     if (row0 + 32 * (R - 1) < rows)
-      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT, NORM, MC>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, true, EXACT, NORM, MC, DEPTH>(p, xt, row0, rows, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid, raw_a, raw_bytes);
     else
-      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM, MC>(p, xt, row0, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid);
+      row0 = quant_process<QK, R, NLD, NP, NBUF, false, EXACT, NORM, MC, DEPTH>(p, xt, row0, rows, n, t, T, K8, nunits, xs_cur, tab_a, ctx_a, pre, s_next, ctx0, up0, ss_cur, wp_unit, stg_a, stage_row, prev_row0, prev_nvalid, raw_a, raw_bytes);
     ++n;
   }
   if constexpr (MC) {
@@ -816,14 +858,15 @@ __global__ void __launch_bounds__(TMAX, MINB) reorder_quantize_kernel(const __gr
 
 __device__ unsigned int g_quant_sched[64][2];  // rotating schedule slots (zero-initialised, self-resetting)
 
-template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool NORM = false, bool MC = false>
+template <int R, int TMAX, int NLD, int NP, int MINB, int TABMODE, int NBUF, bool NORM = false, bool MC = false, int DEPTH = 0>
 static int launch_quant(QuantParams& p, cudaStream_t stream) {
   // threads: NP passes of T threads cover the K/16 compute units exactly (T a multiple of 32)
   const int T = ((p.K / 16 + NP - 1) / NP + 31) & ~31;
   constexpr int TABW = (TABMODE == 2) ? 4 : 2;
   const size_t smem = ((size_t)(p.K * TABW + 127) & ~(size_t)127) + (size_t)NBUF * p.K * 2 * R + (NP > 1 ? (size_t)NP * T * 16 : 0) +
                       (NORM ? (size_t)p.K * 2 + (size_t)NBUF * R * 512 : 0) +
-                      (MC ? (size_t)2 * R * (size_t)(p.rowbytes[0] + p.rowbytes[1] + p.rowbytes[2]) : 0);
+                      (MC ? (size_t)2 * R * (size_t)(p.rowbytes[0] + p.rowbytes[1] + p.rowbytes[2]) : 0) +
+                      (size_t)DEPTH * R * NLD * 16 * T;
   const int64_t xs_bytes = (int64_t)p.K * 2 * R;
   if (smem > 227 * 1024 || T > TMAX || (int64_t)NLD * T * 8 < p.K || (TABMODE == 0 && xs_bytes > 65536) ||
       (TABMODE == 1 && xs_bytes > 4 * 65536)) {
@@ -832,8 +875,8 @@ static int launch_quant(QuantParams& p, cudaStream_t stream) {
     return MMX_ERR_INVALID;
   }
   const bool exact = (int64_t)NLD * T * 8 == p.K && (int64_t)NP * T * 16 == p.K;
-  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM, MC>
-                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM, MC>;
+  auto kern = exact ? reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, true, NORM, MC, DEPTH>
+                    : reorder_quantize_kernel<R, TMAX, NLD, NP, MINB, TABMODE, NBUF, false, NORM, MC, DEPTH>;
   // per-device, per-variant launch facts (dynamic shared memory opt-in, occupancy), guarded: callers may be threads
   struct Cache {
     size_t attr_smem = 0;  // largest opt-in granted so far
@@ -1006,16 +1049,23 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
     if (K <= 8192) return launch_quant<2, 512, 2, 1, 1, 0, 2, true>(p, st);
     return launch_quant<2, 1024, 2, 1, 1, 0, 2, true>(p, st);
   }
+  // quant_variant: 0 = default, 1 = the other xs buffering, 2 / 3 = cp.async ring of 2 / 3 items (experiments)
   if (K <= 4096) {
     if (force == 4) return launch_quant<4, 256, 2, 1, 2, 0, 2>(p, st);
     if (var == 1) return launch_quant<2, 256, 2, 1, 4, 0, 2>(p, st);
+    if (var == 2) return launch_quant<2, 256, 2, 1, 4, 0, 1, false, false, 2>(p, st);
+    if (var == 3) return launch_quant<2, 256, 2, 1, 3, 0, 1, false, false, 3>(p, st);
     return launch_quant<2, 256, 2, 1, 4, 0, 1>(p, st);
   }
   if (K <= 8192) {
     if (force == 4) return launch_quant<4, 512, 2, 1, 1, 0, 2>(p, st);
+    if (var == 2) return launch_quant<2, 512, 2, 1, 2, 0, 1, false, false, 2>(p, st);
     return var == 1 ? launch_quant<2, 512, 2, 1, 2, 0, 1>(p, st) : launch_quant<2, 512, 2, 1, 2, 0, 2>(p, st);
   }
-  if (K <= 16384) return var == 1 ? launch_quant<2, 1024, 2, 1, 1, 0, 1>(p, st) : launch_quant<2, 1024, 2, 1, 1, 0, 2>(p, st);
+  if (K <= 16384) {
+    if (var == 2) return launch_quant<2, 1024, 2, 1, 1, 0, 1, false, false, 2>(p, st);
+    return var == 1 ? launch_quant<2, 1024, 2, 1, 1, 0, 1>(p, st) : launch_quant<2, 1024, 2, 1, 1, 0, 2>(p, st);
+  }
   return launch_quant<2, 1024, 4, 2, 1, 1, 1>(p, st);
 }
 
