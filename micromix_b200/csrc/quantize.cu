@@ -1064,6 +1064,8 @@ int reorder_quantize(const void* x, int64_t rows, int K, const int16_t* idx, int
   }
   if (K <= 16384) {
     if (var == 2) return launch_quant<2, 1024, 2, 1, 1, 0, 1, false, false, 2>(p, st);
+    // two units per thread, two CTAs per SM: 9 % faster at K = 11008, 19 % slower at 14336 (profiles/r02_quantize_depth.log)
+    if (var == 4 || (var == 0 && K <= 11264)) return launch_quant<2, 512, 4, 2, 2, 0, 1>(p, st);
     return var == 1 ? launch_quant<2, 1024, 2, 1, 1, 0, 1>(p, st) : launch_quant<2, 1024, 2, 1, 1, 0, 2>(p, st);
   }
   return launch_quant<2, 1024, 4, 2, 1, 1, 1>(p, st);
