@@ -50,6 +50,10 @@ constexpr uint32_t kTmemCols = 512;
 // the MMAs of tile i+1 start after ~kAccOverlap/256 of a drain instead of a whole one (TMEM cannot hold two full
 // 128x256 accumulators plus scales).
 constexpr uint32_t kSFSlot = 24;     // scale columns of one stage: SFA 8 = 2 atoms x 4, SFB 16 = 2 n-blocks x 2 atoms x 4
+// (Round 2 experiment: ONE slot and a 32-column overlap -- tcgen05.cp is ordered behind earlier MMAs of the same thread, the
+// way CUTLASS's block-scaled sm100 mainloop uses a single scale buffer -- passes every GEMM test and changes nothing:
+// qkv 104.3 / o 68.3 / gate_up 428.6 us against 103.3 / 68.4 / 425.5 us, profiles/r02_gemm_overlap32.txt.  The step runs
+// under sw_power_cap: the tensor pipe's duty cycle is set by the power limit, not by the drain the next tile waits for.)
 constexpr uint32_t kNumSFSlots = 4;  // rotating slots: a stage's tcgen05.cp never lands on scales that MMAs in flight read
 constexpr uint32_t kAccOverlap = 96;  // >= kSFSlot * kNumSFSlots, multiple of 32 (epilogue chunk)
 constexpr uint32_t kColAcc1 = 256 - kAccOverlap;
