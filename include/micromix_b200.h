@@ -111,6 +111,25 @@ int mmx_activate_quantize_x(const void* a, const void* b, int64_t M, int KN, int
 int mmx_activate_quantize_x_strided(const void* a, const void* b, int64_t ld, int64_t M, int KN, int KS, int KO, uint8_t* xn,
                                     uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
 
+/* matmul + activate_quantize_x in ONE kernel (extension; the reference runs mixedgemm.matmul for gate_proj / up_proj,
+ * model/qLlamaLayer.py:324-387, then activate_quantize_x on the two bf16 results): the GEMM epilogue rounds its accumulators
+ * to bf16 (what mmx_matmul would have stored), evaluates silu(gate) * up and MX-quantizes it -- the [M, 2 * inter] bf16
+ * intermediate never exists in memory.  Weight layout: the B tensors hold gate and up rows INTERLEAVED per 128 activation
+ * channels: rows [256 t, 256 t + 128) = gate rows of channels [128 t, 128 t + 128) (in down_proj's channel order), rows
+ * [256 t + 128, 256 t + 256) = the up rows of the same channels; N = 2 * (DN + DS + DO).  (DN, DS, DO) = FP4 | FP6 | FP8
+ * split of the activation, multiples of 128, DN > 0.  No bias.  Outputs are bit-identical to
+ * mmx_activate_quantize_x(gate half, up half of mmx_matmul's result), including the 0x7F scale bytes of padding rows. */
+int mmx_matmul_activate_quantize(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas,
+                                 const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN,
+                                 int KS, int KO, int w4, int DN, int DS, int DO, uint8_t* xn, uint8_t* xs, uint8_t* xo,
+                                 uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+
+/* Test hook for the epilogue above: fp32 bits of silu(x) for EVERY bf16 x (index = bit pattern, 65536 entries, device
+ * memory) through the branch-free sequence the epilogue uses (`fast`) and through the reference sequence (`ref`); the two
+ * must agree for 2^-60 <= |x| <= 32, the range the epilogue uses the fast one on. */
+int mmx_debug_silu_table(uint32_t* fast, uint32_t* ref, void* stream);
+
 /*
  * mixedgemm.downproj_quantize_w(W, KN, KS, KO)                          bindings.cpp:336-360
  *   -> run_downproj_bf16_mixed -> downproj_quantize_kernel_with_cute_layout   activate.cu:554-592, 204-349

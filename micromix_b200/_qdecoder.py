@@ -7,9 +7,11 @@ constructors and forward signatures and changes what the hot path costs:
   * q/k/v (and gate/up) read the same activation with the same reorder_index and split, so they are ONE QLinearLayer
     over the row-concatenated weight: one reorder+quantize and one mixed GEMM instead of three (two);
   * `fused=True` (extension, off by default = the reference's op sequence): the two RMSNorms run inside the quantizer
-    (`rmsnorm_quantize_x`: no normalised [M, hidden] round trip through HBM) and SiLU(gate) * up runs inside the quantizer of
-    down_proj (`activate_quantize_x` on the two halves of the gate_up GEMM output, read in place); for that the rows of
-    gate_proj / up_proj are stored in down_proj's channel order at construction, so the intermediate activation is born
+    (`rmsnorm_quantize_x`: no normalised [M, hidden] round trip through HBM) and SiLU(gate) * up + the quantization of
+    down_proj's operand run in the EPILOGUE of the gate_up GEMM (`matmul_activate_quantize`: the [M, 2 * intermediate] bf16
+    result never exists in HBM; bit-identical to `matmul` followed by the reference's `activate_quantize_x`, which remains
+    the path when gate / up have biases or different calibrations); for that the rows of gate_proj / up_proj are stored in
+    down_proj's channel order, interleaved per 128 channels, at construction, so the intermediate activation is born
     permuted (the reference's abandoned `out_reorder_index` idea, qLinearLayer.py:27, qLlamaLayer.py:341,354);
   * with a `tp_group`, qkv / gate_up are column-parallel (no collective) and o / down row-parallel with an NCCL all-reduce
     (micromix_b200.parallel_utils); heads are sharded so every rank runs attention on its own heads only.
@@ -84,6 +86,19 @@ class FusedQLinear(nn.Module):
     def forward(self, x, norm=None):
         y = self.forward_whole(x, norm)
         return y.split(self.splits, dim=-1) if len(self.splits) > 1 else (y,)
+
+    @torch.no_grad()
+    def forward_activated(self, x, dsplit, norm=None):
+        """This module holds gate / up rows interleaved per 128 channels (mixedgemm.interleave_gate_up): one quantize + one
+        GEMM whose epilogue emits the MX-quantized SiLU(gate) * up -> the six operand tensors of the down projection."""
+        lin = self.inner
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        if norm is None:
+            a = mixedgemm.reorder_quantize_x(x2, lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num)
+        else:
+            a = mixedgemm.rmsnorm_quantize_x(x2, norm[0], norm[1], lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num)
+        return mixedgemm.matmul_activate_quantize(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS,
+                                                  a[5], lin.SFBO, *dsplit)
 
     @torch.no_grad()
     def forward_gathered(self, x_shard, M, workspace, norm=None):
@@ -286,8 +301,10 @@ class QGatedMLP(nn.Module):
 
     def __init__(self, originalMLP, p8_nums, p6_nums, reorder_index, i, tp_group=None, names=('gate_proj', 'up_proj',
                                                                                                'down_proj'),
-                 key_fmt=None, fused_act=False, workspace=None, sequence_parallel=False, token_parallel_rows=False):
+                 key_fmt=None, fused_act=False, workspace=None, sequence_parallel=False, token_parallel_rows=False,
+                 act_epilogue=True):
         super().__init__()
+        self.act_epilogue = False
         self.sp = bool(sequence_parallel)
         self.tpr = bool(token_parallel_rows) and self.sp
         self.workspace = workspace
@@ -305,10 +322,22 @@ class QGatedMLP(nn.Module):
             perm = reorder_index[kd].to(torch.int64)
             pw = lambda l: _meta_linear(l.weight.data[perm.to(l.weight.device)],
                                         None if l.bias is None else l.bias.data[perm.to(l.bias.device)])
-            self.gate_up_proj = build_input_group([pw(gate), pw(up)], [key(names[0]), key(names[1])], p8_nums, p6_nums,
-                                                  reorder_index, None)
             self.d_p8, self.d_p6 = int(p8_nums[kd]), int(p6_nums[kd])
             self.d_p4 = inter - self.d_p8 - self.d_p6
+            kg, ku = key(names[0]), key(names[1])
+            shared = (_same(reorder_index[kg], reorder_index[ku]) and _same(p8_nums[kg], p8_nums[ku])
+                      and _same(p6_nums[kg], p6_nums[ku]))
+            # SiLU * up + quantize in the gate_up GEMM's epilogue: one calibration for both projections, no biases
+            self.act_epilogue = bool(act_epilogue and shared and gate.bias is None and up.bias is None and inter % 128 == 0
+                                     and self.d_p4 > 0)
+            if self.act_epilogue:
+                w = mixedgemm.interleave_gate_up(gate.weight.data[perm.to(gate.weight.device)],
+                                                 up.weight.data[perm.to(up.weight.device)])
+                self.gate_up_proj = nn.ModuleList([FusedQLinear([_meta_linear(w, None)], p8_nums[kg], p6_nums[kg],
+                                                                reorder_index[kg])])
+                del w
+            else:
+                self.gate_up_proj = build_input_group([pw(gate), pw(up)], [kg, ku], p8_nums, p6_nums, reorder_index, None)
             wd = down.weight.data.to(device='cuda', dtype=torch.bfloat16)[:, perm.cuda()].contiguous()
             self.dW = mixedgemm.downproj_quantize_w4(wd, self.d_p4, self.d_p6, self.d_p8)
             del wd
@@ -339,13 +368,18 @@ class QGatedMLP(nn.Module):
             h = (self.act_fn(g) * u).unsqueeze(0)
             y, _ = self.down_proj(h) if self.tpr else forward_row_shard(self.down_proj, h)
             return y.unsqueeze(0)
+        W = self.dW if self.fused_act else None
+        if self.act_epilogue:
+            bsz, q_len, _ = x.shape
+            a = self.gate_up_proj[0].forward_activated(x, (self.d_p4, self.d_p6, self.d_p8), norm)
+            y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias)
+            return y.reshape(bsz, q_len, -1)
         g, u = run_input_group(self.gate_up_proj, x, norm)
         if not self.fused_act:
             return self.down_proj(self.act_fn(g) * u)
         bsz, q_len, inter = g.shape
         a = mixedgemm.activate_quantize_x(g.reshape(bsz * q_len, inter), u.reshape(bsz * q_len, inter), self.d_p4, self.d_p6,
                                           self.d_p8)
-        W = self.dW
         y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias)
         return y.reshape(bsz, q_len, -1)
 

@@ -86,6 +86,11 @@ struct MatmulExtra {
   uint32_t* ag_consumed[kMaxTp] = {};
   int ag_tp = 0;
   uint32_t* ag_err = nullptr;  // local error word (mmx_tp_status): bit 3 = a source rank's rows never arrived
+  // fused SiLU(gate) * up + MX quantize (see GemmParams::act_*): outputs and the FP4 | FP6 | FP8 split of the activation
+  // (N == 2 * (act_k[0] + act_k[1] + act_k[2]), B rows interleaved gate | up per 128 channels); act_q[0] != nullptr enables it
+  uint8_t* act_q[3] = {};
+  uint8_t* act_sf[3] = {};
+  int act_k[3] = {};
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,

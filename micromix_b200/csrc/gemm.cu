@@ -34,6 +34,7 @@
 #include <type_traits>
 #include <unordered_map>
 
+#include "act_math.h"
 #include "common.h"
 
 namespace mmx {
@@ -118,6 +119,16 @@ struct GemmParams {
   int ag_tp;
   uint32_t* ag_err;
   unsigned long long ag_timeout_ns;
+  // FUSED ACTIVATION (ACT kernels, mmx_matmul_activate_quantize): B = gate / up rows INTERLEAVED in blocks of 128 channels
+  // (tile n_blk: columns 0..127 = gate of channels [128 n_blk, +128), columns 128..255 = up of the same channels), and the
+  // epilogue does not write C: it rounds both accumulators to bf16 (what the plain GEMM would have stored), evaluates
+  // v = silu(gate) * up in fp32 and MX-quantizes v over its 32-channel groups exactly like mmx_activate_quantize_x
+  // (rowquant.cu) -- codes and scale bytes of the down projection's operand leave the kernel directly.
+  uint8_t* act_q[3];
+  uint8_t* act_sf[3];
+  int act_cend[3];       // cumulative channel ends of the FP4 | FP6 | FP8 segments of the activation
+  int act_katoms[3];     // scale atoms per row block of each segment
+  int64_t act_rowbytes[3];
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
@@ -457,11 +468,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 // contiguous 1/SK of the tile's K stages in their own TMEM, park the fp32 accumulator in their (now idle) stage buffers,
 // and CTA r of the cluster sums column slice r of all SK copies through distributed shared memory -- in CTA order, so the
 // result does not depend on timing -- and writes bf16.  One tile per cluster, no global workspace, no atomics.
-template <int CG, bool WD, bool RS, int SK = 1>
+template <int CG, bool WD, bool RS, int SK = 1, bool ACT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p,
                   const __grid_constant__ std::conditional_t<RS, RsParams, NoRsParams> rs) {
   static_assert(SK == 1 || (CG == 1 && !WD && !RS), "split-K is a variant of the plain single-CTA kernel");
+  static_assert(!ACT || (SK == 1 && !WD && !RS), "the fused activation is a variant of the plain kernels");
   using G = Geo<CG, RS>;
   constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
@@ -824,6 +836,150 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         }
         tc_fence_before();
         break;  // one tile per cluster; the reduction follows the role branches
+      }
+      if constexpr (ACT) {
+        // ---- fused SiLU(gate) * up + MX quantize: this lane owns row row0 + lane; 32-column chunk i < 4 holds the gate,
+        // chunk i + 4 the up accumulators of channels [128 n_blk + 32 i, + 32) -- one scale group per (lane, i)
+        constexpr int kShared = (int)kAccOverlap / 32;
+        static_assert(kShared <= 4, "the shared columns lie inside one half of the tile");
+        const int ch0 = n_blk * 128;
+        const int sg = (ch0 >= p.act_cend[1]) ? 2 : (ch0 >= p.act_cend[0] ? 1 : 0);
+        const int cb = (sg == 0) ? 0 : p.act_cend[sg - 1];
+        const int fmt = 4 + 2 * sg;
+        const float qmax = (sg == 0) ? 6.0f : (sg == 1 ? 28.0f : 448.0f);
+        const bool row_ok = row0 + lane < p.M;
+        uint8_t* qrow = p.act_q[sg] + (int64_t)(row0 + lane) * p.act_rowbytes[sg] + (((ch0 - cb) * fmt) >> 3);
+        uint32_t sfword = 0;
+        // one scale group: gw / uw = the bf16-rounded gate / up accumulators of 32 channels, two per word
+        auto act_group = [&](const uint32_t (&gw)[16], const uint32_t (&uw)[16], int pr) {
+          // fast_silu on all 32 channels as straight-line code (this warp is alone on its scheduler: only instruction-
+          // level parallelism hides the ~100-cycle chain of one element); the rare group with a gate value outside the
+          // range fast_silu is exact on takes the reference sequence instead
+          uint32_t lo2 = 0xffffffffu, hi2 = 0u;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t ab = gw[e] & 0x7fff7fffu;
+            lo2 = __vminu2(lo2, ab);
+            hi2 = __vmaxu2(hi2, ab);
+          }
+          float v[32];
+          if (min(lo2 & 0xffffu, lo2 >> 16) >= kFastSiluLo && max(hi2 & 0xffffu, hi2 >> 16) <= kFastSiluHi) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              v[2 * e] = __fmul_rn(fast_silu(__uint_as_float(gw[e] << 16)), __uint_as_float(uw[e] << 16));
+              v[2 * e + 1] = __fmul_rn(fast_silu(__uint_as_float(gw[e] & 0xffff0000u)), __uint_as_float(uw[e] & 0xffff0000u));
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              v[2 * e] = __fmul_rn(ref_silu(__uint_as_float(gw[e] << 16)), __uint_as_float(uw[e] << 16));
+              v[2 * e + 1] = __fmul_rn(ref_silu(__uint_as_float(gw[e] & 0xffff0000u)), __uint_as_float(uw[e] & 0xffff0000u));
+            }
+          }
+          float m = 0.0f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) m = fmaxf(m, fabsf(v[e]));
+          int n = 0;
+          if (m > 1e-6f) n = ref_scale_exp(m, qmax);
+          const float rsc = __uint_as_float((uint32_t)(127 - n) << 23);  // 2^-n, exact multiplier
+          sfword |= (uint32_t)(n + 127) << (8 * pr);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __fmul_rn(v[e], rsc);
+          if (row_ok) {
+            if (sg == 0) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                w[k] = rq_cvt4_e2m1(v[8 * k], v[8 * k + 1], v[8 * k + 2], v[8 * k + 3]) |
+                       (rq_cvt4_e2m1(v[8 * k + 4], v[8 * k + 5], v[8 * k + 6], v[8 * k + 7]) << 16);
+              *reinterpret_cast<uint4*>(qrow + pr * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else if (sg == 1) {
+              uint32_t y[8];  // 24 bits each
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                y[k] = rq_squeeze4_fp6(rq_cvt4_e3m2(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {  // four 24-bit words -> three 32-bit words
+                const uint32_t a0 = y[4 * k] | (y[4 * k + 1] << 24);
+                const uint32_t a1 = (y[4 * k + 1] >> 8) | (y[4 * k + 2] << 16);
+                const uint32_t a2 = (y[4 * k + 2] >> 16) | (y[4 * k + 3] << 8);
+                uint32_t* d = reinterpret_cast<uint32_t*>(qrow + pr * 24 + k * 12);
+                d[0] = a0;
+                d[1] = a1;
+                d[2] = a2;
+              }
+            } else {
+              uint32_t w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) w[k] = rq_cvt4_e4m3(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              *reinterpret_cast<uint4*>(qrow + pr * 32) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(qrow + pr * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+        };
+        auto pack32 = [&](const uint32_t (&r)[32], uint32_t (&o)[16]) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = pack_bf16(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+        };
+        // the columns shared with the other accumulator leave TMEM first (the top chunks of acc0 = up chunks, the bottom
+        // chunks of acc1 = gate chunks), already rounded to bf16; then the MMA warp may start the next tile
+        uint32_t sh[kShared][16];
+        {
+          uint32_t raw[32];
+#pragma unroll
+          for (int i = 0; i < kShared; ++i) {
+            tmem_ld32(tbase + (uint32_t)((odd ? i : 7 - i) * 32), raw);
+            tmem_ld_wait();
+            pack32(raw, sh[i]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+        }
+        // pairs in the order that uses the pre-loaded chunks first (acc0: pairs 3, 2, 1, 0 -- up chunk 7 - k is sh[k];
+        // acc1: pairs 0, 1, 2, 3 -- gate chunk k is sh[k]); one copy of the group code, the loop is not unrolled
+        uint32_t gw[16], uw[16];
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int pr = odd ? k : 3 - k;
+          const bool pre = k < kShared;
+          uint32_t raw[32];
+          if (!(pre && odd)) {
+            tmem_ld32(tbase + (uint32_t)(pr * 32), raw);
+            tmem_ld_wait();
+            pack32(raw, gw);
+          }
+          if (!(pre && !odd)) {
+            tmem_ld32(tbase + (uint32_t)((pr + 4) * 32), raw);
+            tmem_ld_wait();
+            pack32(raw, uw);
+          }
+          if (pre) {
+#pragma unroll
+            for (int j = 0; j < kShared; ++j) {
+              if (k == j) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (odd) gw[i] = sh[j][i];
+                  else uw[i] = sh[j][i];
+                }
+              }
+            }
+          }
+          act_group(gw, uw, pr);
+        }
+        // the row block's scale bytes of this tile's atom: four groups of row (lane, q) are one aligned 32-bit word
+        const int rowblk = m_blk * CG + (int)rank;
+        if ((int64_t)rowblk * BM < p.M) {
+          uint8_t* d = p.act_sf[sg] + ((int64_t)rowblk * p.act_katoms[sg] + ((ch0 - cb) >> 7)) * 512 + lane * 16 + q * 4;
+          *reinterpret_cast<uint32_t*>(d) = sfword;
+        }
+        tc_fence_before();
+        tphase ^= 1;
+        ++tcount;
+        continue;
       }
       const bool do_store = row0 < p.M && !(WD && (p.flags & 4u));
       const uint32_t nstore_tile0 = nstore;
@@ -1203,7 +1359,7 @@ static uint32_t make_idesc(int kind, int a_bits, int b_bits, int mma_m) {
 }
 
 template <int CG>
-static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs) {
+static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs, bool act = false) {
   const int smem_bytes = rs != nullptr ? Geo<CG, true>::kSmemBytes : Geo<CG, false>::kSmemBytes;
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
@@ -1237,7 +1393,7 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static bool attr_done[kMaxDevices][3] = {};
+  static bool attr_done[kMaxDevices][4] = {};
   static std::mutex attr_mu;
   const int dev = current_device_slot();
   auto prepare = [&](auto kern, int slot) -> cudaError_t {
@@ -1251,6 +1407,11 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
     auto kern = mixed_gemm_kernel<CG, false, true>;
     MMX_CUDA_TRY(prepare(kern, 2));
     MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, *rs));
+  } else if (act) {
+    const NoRsParams none = {0};
+    auto kern = mixed_gemm_kernel<CG, false, false, 1, true>;
+    MMX_CUDA_TRY(prepare(kern, 3));
+    MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, none));
   } else {
     const NoRsParams none = {0};
     auto kern = wd ? mixed_gemm_kernel<CG, true, false> : mixed_gemm_kernel<CG, false, false>;
@@ -1351,7 +1512,25 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     set_error("matmul: N=%lld must be a multiple of 128", (long long)N);
     return MMX_ERR_INVALID;
   }
-  if (rsl == nullptr && (!c || ((uintptr_t)c & 15))) {
+  const bool act = ex != nullptr && ex->act_q[0] != nullptr;
+  if (act) {
+    const int ka = ex->act_k[0] + ex->act_k[1] + ex->act_k[2];
+    if (ex->act_k[0] <= 0 || ex->act_k[1] < 0 || ex->act_k[2] < 0 || (ex->act_k[0] % 128) || (ex->act_k[1] % 128) ||
+        (ex->act_k[2] % 128) || N != 2 * (int64_t)ka) {
+      set_error("matmul_activate_quantize: N=%lld must be twice the activation width (%d,%d,%d), segments multiples of 128",
+                (long long)N, ex->act_k[0], ex->act_k[1], ex->act_k[2]);
+      return MMX_ERR_INVALID;
+    }
+    if (bias != nullptr || rsl != nullptr || ex->grp_mblk != nullptr || ex->ag_arrived != nullptr) {
+      set_error("matmul_activate_quantize: no bias, no tensor-parallel or grouped form");
+      return MMX_ERR_INVALID;
+    }
+    for (int i = 0; i < 3; ++i)
+      if (ex->act_k[i] && (!ex->act_q[i] || !ex->act_sf[i] || (((uintptr_t)ex->act_q[i] | (uintptr_t)ex->act_sf[i]) & 15))) {
+        set_error("matmul_activate_quantize: outputs of segment %d must be non-null 16-byte aligned pointers", i);
+        return MMX_ERR_INVALID;
+      }
+  } else if (rsl == nullptr && (!c || ((uintptr_t)c & 15))) {
     set_error("matmul: output must be a non-null 16-byte aligned pointer");
     return MMX_ERR_INVALID;
   }
@@ -1370,7 +1549,7 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     set_error("matmul (grouped): rows per group of B must be a multiple of 256, the padded M a multiple of the m-tile");
     return MMX_ERR_INVALID;
   }
-  if (rsl == nullptr && !grouped && !gathered && options().gemm_watchdog == 0 && M <= 512 &&
+  if (rsl == nullptr && !grouped && !gathered && !act && options().gemm_watchdog == 0 && M <= 512 &&
       options().gemm_cta_group != 2) {
     const int64_t tiles1 = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int stages = (KN + 255) / 256 + KS / 128 + KO / 128;
@@ -1466,6 +1645,17 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     if (rsl->pull) {
       if (int rc = get_c_tmap(rsl->c_local, M, N, &tm.c)) return rc;
     }
+  } else if (act) {
+    int cacc = 0;
+    for (int i = 0; i < 3; ++i) {
+      cacc += ex->act_k[i];
+      p.act_cend[i] = cacc;
+      p.act_katoms[i] = ex->act_k[i] / 128;
+      p.act_rowbytes[i] = (int64_t)ex->act_k[i] * (4 + 2 * i) / 8;
+      p.act_q[i] = ex->act_q[i];
+      p.act_sf[i] = ex->act_sf[i];
+    }
+    tm.c = tm.a[0];  // never used: the ACT epilogue stores through plain pointers (a valid map keeps the prefetch happy)
   } else if (int rc = get_c_tmap(c, M, N, &tm.c)) {
     return rc;
   }
@@ -1511,7 +1701,7 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     if (sk == 4) return launch_gemm_splitk<4>(tm, p, st, false, nullptr);
     return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
   }
-  const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp) : launch_gemm<1>(tm, p, st, rsp);
+  const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp, act) : launch_gemm<1>(tm, p, st, rsp, act);
   if (rc == MMX_OK && rsl != nullptr) {
     rsl->cg = cg;
     rsl->m_tiles = p.m_tiles;
@@ -1535,6 +1725,33 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul(const uint8_t* 
                           int64_t N, int KN, int KS, int KO, int w4, const void* bias, void* c, void* stream) {
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c,
                           stream, nullptr);
+}
+
+// Fused gate_up GEMM + SiLU(gate) * up + MX quantize (extension; the reference runs matmul, then activate_quantize_x,
+// /root/reference/mgemm/src/activate.cu:510-552, on the bf16 result): B holds the gate and up rows INTERLEAVED per 128
+// channels of the activation (rows [256 t, 256 t + 128) = gate of channels [128 t, +128), the next 128 rows = up of the same
+// channels), N = 2 * (DN + DS + DO).  Outputs are exactly those of mmx_activate_quantize_x(matmul's gate half, up half).
+extern "C" __attribute__((visibility("default"))) int mmx_matmul_activate_quantize(
+    const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
+    const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+    const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, int DN, int DS, int DO, uint8_t* xn, uint8_t* xs,
+    uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream) {
+  mmx::MatmulExtra ex;
+  ex.act_q[0] = xn;
+  ex.act_q[1] = xs;
+  ex.act_q[2] = xo;
+  ex.act_sf[0] = sfn;
+  ex.act_sf[1] = sfs;
+  ex.act_sf[2] = sfo;
+  ex.act_k[0] = DN;
+  ex.act_k[1] = DS;
+  ex.act_k[2] = DO;
+  if (xn == nullptr) {
+    mmx::set_error("matmul_activate_quantize: the FP4 segment of the activation must not be empty");
+    return MMX_ERR_INVALID;
+  }
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, nullptr, nullptr,
+                          stream, nullptr, &ex);
 }
 
 // ------------------------------------------------------------------------------------------------ tensor-pipe peak probe

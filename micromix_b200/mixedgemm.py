@@ -154,6 +154,65 @@ def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None
     return out
 
 
+def interleave_gate_up(gate, up, block=128):
+    """Row layout matmul_activate_quantize expects of the fused weight: [gate rows of channels 0..127 | up rows of channels
+    0..127 | gate 128..255 | up 128..255 | ...] (any tensors whose dim 0 is the channel; dim 0 a multiple of `block`)."""
+    if gate.shape != up.shape or gate.shape[0] % block:
+        raise ValueError(f"gate / up must have equal shapes with dim 0 a multiple of {block}, got {tuple(gate.shape)}, "
+                         f"{tuple(up.shape)}")
+    n = gate.shape[0] // block
+    g = gate.reshape(n, block, *gate.shape[1:])
+    u = up.reshape(n, block, *up.shape[1:])
+    return torch.stack((g, u), dim=1).reshape(2 * gate.shape[0], *gate.shape[1:]).contiguous()
+
+
+def matmul_activate_quantize(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, DN, DS, DO):
+    """Extension: matmul(...) against gate / up weights interleaved per 128 channels (interleave_gate_up), followed by
+    activate_quantize_x(gate, up, DN, DS, DO) -- in the GEMM's epilogue, without the bf16 [M, 2 * inter] round trip.
+    -> (XN, XS, XO, SFXN, SFXS, SFXO) of the down projection's operand, bit-identical to the two separate ops."""
+    lib = _lib.load()
+    names = ("AN", "BN", "AS", "BS", "AO", "BO", "SFAN", "SFBN", "SFAS", "SFBS", "SFAO", "SFBO")
+    tensors = (AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO)
+    for n, t in zip(names[:6], tensors[:6]):
+        _check_cuda(n, t, torch.uint8, 2)
+    for n, t in zip(names[6:], tensors[6:]):
+        _check_cuda(n, t, torch.uint8)
+    M, N = AN.size(0), BN.size(0)
+    KN, KS, KO = AN.size(1) * 2, AS.size(1) * 4 // 3, AO.size(1)
+    sym = AS.size(1) == BS.size(1) and AO.size(1) == BO.size(1)
+    w4 = 0 if sym else 1
+    if KS == 0 and KO == 0:
+        w4 = 1
+    exp_b = (KN // 2, KS // 2 if w4 else KS // 4 * 3, KO // 2 if w4 else KO)
+    for n, t, w in zip(("BN", "BS", "BO"), (BN, BS, BO), exp_b):
+        if t.size(0) != N or t.size(1) != w:
+            raise ValueError(f"{n} must be [{N}, {w}], got {tuple(t.shape)}")
+    for n, t in zip(("AS", "AO"), (AS, AO)):
+        if t.size(0) != M:
+            raise ValueError(f"{n} must have M={M} rows, got {tuple(t.shape)}")
+    for n, t, k in zip(("SFAN", "SFAS", "SFAO"), (SFAN, SFAS, SFAO), (KN, KS, KO)):
+        if t.numel() < -(-M // 128) * 128 * k // 32:
+            raise ValueError(f"{n} has {t.numel()} bytes, too small for M={M}, K={k}")
+    for n, t, k in zip(("SFBN", "SFBS", "SFBO"), (SFBN, SFBS, SFBO), (KN, KS, KO)):
+        if t.numel() < N * k // 32:
+            raise ValueError(f"{n} has {t.numel()} bytes, too small for N={N}, K={k}")
+    DN, DS, DO = _check_split(N // 2, DN, DS, DO)
+    if N != 2 * (DN + DS + DO) or DN <= 0:
+        raise ValueError(f"N={N} must be 2 * (DN + DS + DO) with DN > 0, got ({DN}, {DS}, {DO})")
+    opts = dict(dtype=torch.uint8, device=AN.device)
+    with torch.cuda.device(AN.device):
+        q = [torch.empty((M, w), **opts) for w in (DN // 2, DS // 4 * 3, DO)]
+        sf = [torch.empty((int(lib.mmx_sf_bytes_act(M, k)),), **opts) for k in (DN, DS, DO)]
+        rc = 0
+        if M > 0:
+            rc = lib.mmx_matmul_activate_quantize(_ptr(AN), _ptr(BN), _ptr(AS), _ptr(BS), _ptr(AO), _ptr(BO), _ptr(SFAN),
+                                                  _ptr(SFBN), _ptr(SFAS), _ptr(SFBS), _ptr(SFAO), _ptr(SFBO), M, N, KN, KS, KO,
+                                                  w4, DN, DS, DO, _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]),
+                                                  _ptr(sf[2]), _stream())
+    _lib.check(rc, "mmx_matmul_activate_quantize")
+    return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
+
+
 def rmsnorm_quantize_x(X, W, eps, reorder_index, KN, KS, KO):
     """RMSNorm fused into reorder+quantize (bindings.cpp:257-303): X bf16 [M, K], W bf16 [K] -> the six tensors of
     reorder_quantize_x computed on bf16((x * w) * rsqrt(mean(x^2) + eps)).  Any K <= 16384 (the reference: four K)."""

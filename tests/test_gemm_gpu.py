@@ -278,3 +278,80 @@ def test_tp_shard_shapes_vs_oracle(cuda, N, K):
     """The per-rank GEMM shapes of the tensor-parallel runs (K_local 512 / 1792, N 768 / 3584, the Qwen K = 27648 shards)
     at M = 8192 against the oracle: short-K and narrow-N tiles take other code paths than the square prefill shapes."""
     _big_case(cuda, 8192, N, K, _shard_split(K), seed=K % 11 + N % 5)
+
+
+# ---- fused SiLU(gate) * up + MX quantize in the GEMM epilogue (mmx_matmul_activate_quantize): bit-identical to the two ops
+@pytest.mark.parametrize("M,K,dsplit", [(128, 512, (128, 0, 0)), (64, 512, (256, 128, 128)), (300, 1024, (256, 128, 128)),
+                                        (129, 512, (384, 0, 128)), (1000, 1024, (1024, 512, 256)),
+                                        (2048, 4096, (9216, 3584, 1536)), (515, 640, (640, 256, 128))])
+def test_matmul_activate_quantize_matches_two_ops(cuda, M, K, dsplit):
+    from micromix_b200 import mixedgemm
+    inter = sum(dsplit)
+    p8 = (K // 8) // 128 * 128
+    p6 = (K // 4) // 128 * 128
+    split = (K - p6 - p8, p6, p8)
+    idx = H.make_index(K, seed=M + K)
+    x = H.make_activations(M, K, idx, seed=5 + M)
+    wg, wu = H.make_weights(inter, K, seed=77 + M), H.make_weights(inter, K, seed=78 + M)
+    a = mixedgemm.reorder_quantize_x(x.to(cuda), idx.to(cuda), *split)
+    # the two separate ops on the plain [gate; up] weight
+    b = mixedgemm.reorder_quantize_w4(torch.cat([wg, wu]).to(cuda), idx.to(cuda), *split)
+    y = _mm(a, b)
+    ref = mixedgemm.activate_quantize_x(y[:, :inter], y[:, inter:], *dsplit)
+    # the fused kernel on the interleaved weight
+    bi = mixedgemm.reorder_quantize_w4(mixedgemm.interleave_gate_up(wg, wu).to(cuda), idx.to(cuda), *split)
+    got = mixedgemm.matmul_activate_quantize(a[0], bi[0], a[1], bi[1], a[2], bi[2], a[3], bi[3], a[4], bi[4], a[5], bi[5],
+                                             *dsplit)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert torch.equal(got[i], ref[i]), f"codes of segment {i} differ"
+    for i, k in enumerate(dsplit):
+        g, r = H.u8(got[3 + i]), H.u8(ref[3 + i])
+        assert g.shape == r.shape
+        valid = -(-M // 128) * (k // 128) * 512  # whole row blocks, padding rows included (0x7F); the rest is never written
+        assert np.array_equal(g[:valid], r[:valid]), f"scale bytes of segment {i} differ"
+
+
+def test_matmul_activate_quantize_special_values_and_errors(cuda):
+    """Zero rows of X (all-zero groups -> scale byte 0x7F), large gate magnitudes (silu saturation on both sides)."""
+    from micromix_b200 import mixedgemm
+    M, K, dsplit = 256, 512, (256, 128, 128)
+    inter = sum(dsplit)
+    split = (256, 128, 128)
+    idx = H.make_index(K, seed=3)
+    x = H.make_activations(M, K, idx, seed=9)
+    x[5] = 0
+    x[200:210] *= 64.0
+    wg, wu = H.make_weights(inter, K, seed=1) * 8.0, H.make_weights(inter, K, seed=2)
+    a = mixedgemm.reorder_quantize_x(x.to(cuda), idx.to(cuda), *split)
+    b = mixedgemm.reorder_quantize_w(torch.cat([wg, wu]).to(cuda), idx.to(cuda), *split)
+    y = _mm(a, b)
+    ref = mixedgemm.activate_quantize_x(y[:, :inter].contiguous(), y[:, inter:].contiguous(), *dsplit)
+    bi = mixedgemm.reorder_quantize_w(mixedgemm.interleave_gate_up(wg, wu).to(cuda), idx.to(cuda), *split)
+    got = mixedgemm.matmul_activate_quantize(a[0], bi[0], a[1], bi[1], a[2], bi[2], a[3], bi[3], a[4], bi[4], a[5], bi[5],
+                                             *dsplit)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert torch.equal(got[i], ref[i]), i
+    for i, k in enumerate(dsplit):
+        valid = -(-M // 128) * (k // 128) * 512
+        assert torch.equal(got[3 + i][:valid], ref[3 + i][:valid]), i
+    with pytest.raises(ValueError):
+        mixedgemm.matmul_activate_quantize(a[0], bi[0], a[1], bi[1], a[2], bi[2], a[3], bi[3], a[4], bi[4], a[5], bi[5],
+                                           256, 128, 0)
+
+
+def test_fast_silu_equals_reference_sequence_on_every_bf16_in_range(cuda, mmx_lib):
+    """The epilogue's branch-free silu against the reference instruction sequence, exhaustively: all bf16 gate values with
+    2^-60 <= |x| <= 32 (outside that range the epilogue itself falls back to the reference sequence)."""
+    fast = torch.empty(65536, dtype=torch.int32, device=cuda)
+    ref = torch.empty(65536, dtype=torch.int32, device=cuda)
+    rc = mmx_lib.mmx_debug_silu_table(fast.data_ptr(), ref.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    bits = torch.arange(65536, device=cuda)
+    mag = bits & 0x7fff
+    inr = (mag >= 0x2180) & (mag <= 0x4200)
+    assert int(inr.sum()) == 2 * (0x4200 - 0x2180 + 1)
+    bad = inr & (fast != ref)
+    assert int(bad.sum()) == 0, [hex(int(b)) for b in bits[bad][:8]]

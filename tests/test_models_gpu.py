@@ -155,9 +155,18 @@ def test_fused_norm_and_activation_mode(cuda, cls_path, bias):
     b = fused(x, position_embeddings=(cos, sin))[0]
     n2 = mixedgemm.launch_count()
     torch.cuda.synchronize()
-    # four quantize + four GEMM launches + the in-place RoPE kernel either way; the elementwise kernels are gone
-    assert n1 - n0 == 9 and n2 - n1 == 9
+    # plain: four quantize + four GEMM launches + the in-place RoPE kernel; fused: down_proj's quantizer is the gate_up
+    # GEMM's epilogue, one launch less; the elementwise kernels are gone
+    assert n1 - n0 == 9 and n2 - n1 == 8
     assert torch.isfinite(b.float()).all()
+    # the epilogue form is bit-identical to gate_up GEMM -> activate_quantize_x (the reference's op pair)
+    from micromix_b200._qdecoder import QGatedMLP, fusable_rmsnorm
+    two_ops = QGatedMLP(layer.mlp, p8, p6, idx, 1, fused_act=True, act_epilogue=False)
+    assert fused.mlp.act_epilogue and two_ops.fused_act and not two_ops.act_epilogue
+    norm = fusable_rmsnorm(layer.post_attention_layernorm)
+    assert norm is not None
+    assert torch.equal(fused.mlp(x, norm), two_ops(x, norm))
+    assert torch.equal(fused.mlp(x), two_ops(x))
     d = (a.float() - b.float()).abs()
     scale = a.float().pow(2).mean().sqrt()
     assert float(d.max()) <= 0.05 * float(scale) and float(d.mean()) <= 0.005 * float(scale), (float(d.max()), float(d.mean()), float(scale))
