@@ -111,6 +111,14 @@ int mmx_activate_quantize_x(const void* a, const void* b, int64_t M, int KN, int
 int mmx_activate_quantize_x_strided(const void* a, const void* b, int64_t ld, int64_t M, int KN, int KS, int KO, uint8_t* xn,
                                     uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
 
+/* mmx_matmul with a residual input (extension; the reference adds the residual with a torch op after the linear,
+ * model/qLlamaLayer.py:116-158): c = bf16(residual + y) with y = mmx_matmul's bf16 result (bias included) -- torch's bf16
+ * add, bit for bit, in the GEMM's epilogue.  residual: bf16 [M, N], 16-byte aligned, may alias c. */
+int mmx_matmul_residual(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                        const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                        const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                        const void* bias, const void* residual, void* c, void* stream);
+
 /* matmul + activate_quantize_x in ONE kernel (extension; the reference runs mixedgemm.matmul for gate_proj / up_proj,
  * model/qLlamaLayer.py:324-387, then activate_quantize_x on the two bf16 results): the GEMM epilogue rounds its accumulators
  * to bf16 (what mmx_matmul would have stored), evaluates silu(gate) * up and MX-quantizes it -- the [M, 2 * inter] bf16

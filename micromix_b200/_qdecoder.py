@@ -242,6 +242,7 @@ class QAttention(nn.Module):
                 output_attentions=False, use_cache=False, cache_position=None, position_embeddings=None, **kwargs):
         past_key_value = kwargs.get("past_key_values", past_key_value)
         norm = kwargs.pop("mmx_norm", None)
+        res = kwargs.pop("mmx_residual", None)  # returned as residual + o_proj(...), added in the GEMM's epilogue
         if self.sp:
             # hidden_states = this rank's token rows [1, rows, hidden]; the batch shape comes from the rotary tables
             bsz, q_len = position_embeddings[0].shape[0], position_embeddings[0].shape[1]
@@ -293,6 +294,8 @@ class QAttention(nn.Module):
             # this rank's rows only: reduce-scatter of the K-sharded product, or the token-parallel full-K product
             y, _ = self.o_proj(out) if self.tpr else forward_row_shard(self.o_proj, out)
             return y.unsqueeze(0), None, past_key_value
+        if res is not None:
+            return self.o_proj(out, residual=res), None, past_key_value
         return self.o_proj(out), None, past_key_value
 
 
@@ -360,7 +363,8 @@ class QGatedMLP(nn.Module):
             self.down_proj = QLinearLayer(down, p8_nums[kd], p6_nums[kd], reorder_index[kd])
 
     @torch.no_grad()
-    def forward(self, x, norm=None, tokens=None):
+    def forward(self, x, norm=None, tokens=None, residual=None):
+        """`residual` (single-GPU forms): returns residual + down(...), added in down_proj's GEMM epilogue."""
         if self.sp:
             # x = this rank's token rows [1, rows, hidden] of `tokens` in total
             g, u = self.gate_up_proj[0].forward_gathered(x.reshape(-1, x.shape[-1]).contiguous(), int(tokens), self.workspace,
@@ -372,15 +376,21 @@ class QGatedMLP(nn.Module):
         if self.act_epilogue:
             bsz, q_len, _ = x.shape
             a = self.gate_up_proj[0].forward_activated(x, (self.d_p4, self.d_p6, self.d_p8), norm)
-            y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias)
+            r2 = None if residual is None else residual.reshape(bsz * q_len, -1).contiguous()
+            y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias,
+                                 residual=r2)
             return y.reshape(bsz, q_len, -1)
         g, u = run_input_group(self.gate_up_proj, x, norm)
         if not self.fused_act:
+            if residual is not None:
+                return self.down_proj(self.act_fn(g) * u, residual=residual)
             return self.down_proj(self.act_fn(g) * u)
         bsz, q_len, inter = g.shape
         a = mixedgemm.activate_quantize_x(g.reshape(bsz * q_len, inter), u.reshape(bsz * q_len, inter), self.d_p4, self.d_p6,
                                           self.d_p8)
-        y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias)
+        r2 = None if residual is None else residual.reshape(bsz * q_len, -1).contiguous()
+        y = mixedgemm.matmul(a[0], W[0], a[1], W[1], a[2], W[2], a[3], W[3], a[4], W[4], a[5], W[5], bias=self.d_bias,
+                             residual=r2)
         return y.reshape(bsz, q_len, -1)
 
 
@@ -453,20 +463,32 @@ class QDecoderLayer(nn.Module):
             hidden_states = self.input_layernorm(hidden_states)
         else:
             kwargs["mmx_norm"] = norm1  # RMSNorm runs inside the qkv quantizer
+        # fused, single GPU: the two residual adds run in the epilogues of o_proj / down_proj (same rounding as the torch add)
+        res_o = self.fused and isinstance(self.self_attn.o_proj, QLinearLayer)
+        if res_o:
+            kwargs["mmx_residual"] = residual
         hidden_states, attn_weights, present = self.self_attn(
             hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
             past_key_value=past_key_value, output_attentions=output_attentions, use_cache=use_cache,
             cache_position=cache_position, position_embeddings=position_embeddings, **kwargs)
-        hidden_states = residual + hidden_states
+        if not res_o:
+            hidden_states = residual + hidden_states
         residual = hidden_states
-        norm2 = fusable_rmsnorm(self.post_attention_layernorm) if (self.fused and isinstance(self.mlp, QGatedMLP)) else None
+        gated = isinstance(self.mlp, QGatedMLP)
+        norm2 = fusable_rmsnorm(self.post_attention_layernorm) if (self.fused and gated) else None
+        res_d = self.fused and gated and self.mlp.tp == 1
         if norm2 is None:
-            hidden_states = self.mlp(self.post_attention_layernorm(hidden_states))
+            hidden_states = self.post_attention_layernorm(hidden_states)
+        if res_d:
+            hidden_states = self.mlp(hidden_states, norm2, residual=residual)
+        elif norm2 is None:
+            hidden_states = self.mlp(hidden_states)
         else:
             hidden_states = self.mlp(hidden_states, norm2)
         if isinstance(hidden_states, tuple):  # MoE blocks return (hidden_states, router_logits)
             hidden_states = hidden_states[0]
-        hidden_states = residual + hidden_states
+        if not res_d:
+            hidden_states = residual + hidden_states
         outputs = (hidden_states,)
         if output_attentions:
             outputs += (attn_weights,)

@@ -91,6 +91,7 @@ struct MatmulExtra {
   uint8_t* act_q[3] = {};
   uint8_t* act_sf[3] = {};
   int act_k[3] = {};
+  const void* residual = nullptr;  // bf16 [M, N]: c = bf16(residual + product), see GemmParams::residual
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,

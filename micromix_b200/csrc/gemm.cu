@@ -132,6 +132,10 @@ struct GemmParams {
   int64_t M, N;
   __nv_bfloat16* c;
   const __nv_bfloat16* bias;
+  // optional bf16 [M, N] (row stride N), added AFTER the product was rounded to bf16 (and after the bias):
+  // c = bf16(residual + bf16(acc)) -- the decoder layer's `residual + o_proj(...)` / `residual + down_proj(...)`
+  // (model/qLlamaLayer.py:116-158) without a separate elementwise kernel; may alias c
+  const __nv_bfloat16* residual;
   uint32_t* dbg;
   uint32_t flags;  // watchdog build only: 1 = skip SF copies, 2 = skip MMAs, 4 = skip C stores
 };
@@ -419,6 +423,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 // 32 fp32 accumulator columns of one row -> 16 packed bf16x2 words (+bias, rounded like the reference's separate add)
+// y = bf16(y + r) on packed pairs (torch's bf16 add: fp32 sum, one rounding)
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t y, uint32_t r) {
+  return pack_bf16(__uint_as_float(y << 16) + __uint_as_float(r << 16),
+                   __uint_as_float(y & 0xffff0000u) + __uint_as_float(r & 0xffff0000u));
+}
+__device__ __forceinline__ void add_residual(uint32_t* o, const uint4 (&res)[4]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    o[4 * v] = add_bf16x2(o[4 * v], res[v].x);
+    o[4 * v + 1] = add_bf16x2(o[4 * v + 1], res[v].y);
+    o[4 * v + 2] = add_bf16x2(o[4 * v + 2], res[v].z);
+    o[4 * v + 3] = add_bf16x2(o[4 * v + 3], res[v].w);
+  }
+}
+
 __device__ __forceinline__ void pack_chunk(const uint32_t (&r)[32], uint32_t* o, const __nv_bfloat16* bias) {
   if (bias != nullptr) {
     const uint4* bp = reinterpret_cast<const uint4*>(bias);
@@ -1003,11 +1022,30 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       // ones of acc1.  Once those are in registers the MMA warp may start the next tile.
       constexpr int kChunks = BN / 32, kShared = (int)kAccOverlap / 32;
       auto chunk_col = [&](int i) { return odd ? i : (kChunks - 1 - i); };
-      auto emit = [&](const uint32_t (&r)[32], int sc) {  // 32 rows x 32 columns: bf16, staged, TMA-stored
+      // residual rows: this lane's 64 bytes of chunk number i (in emit order) travel two chunks ahead of their use
+      auto res_issue = [&](int i, uint4 (&dst)[4]) {
+        const int col0 = n_blk * BN + chunk_col(i) * 32;
+        if (row0 + lane < p.M && col0 < p.N) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (int64_t)(row0 + lane) * p.N + col0);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) dst[v] = __ldg(rp + v);
+        }
+      };
+      uint4 rres0[4] = {}, rres1[4] = {};
+      const bool has_res = !RS && p.residual != nullptr;
+      if (has_res) {
+        res_issue(0, rres0);
+        res_issue(1, rres1);
+      }
+      auto emit = [&](const uint32_t (&r)[32], int sc, uint4 (&res)[4], int inext) {  // 32 rows x 32 columns: bf16, staged, TMA-stored
         const int col0 = n_blk * BN + sc * 32;
         if (col0 < p.N) {  // warp-uniform
           uint32_t o[16];
           pack_chunk(r, o, p.bias ? p.bias + col0 : nullptr);
+          if (has_res) {
+            add_residual(o, res);
+            if (inext < kChunks) res_issue(inext, res);
+          }
           const uint32_t buf = sbuf + (nstore & 1u) * kEpiBuf;
           // the store issued from this buffer two chunks ago must have finished READING it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -1041,17 +1079,22 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         }
         tmem_ld32(tbase + (uint32_t)(chunk_col(kShared) * 32), ra);  // first private chunk: under the shared chunks' emit
 #pragma unroll
-        for (int i = 0; i < kShared; ++i) emit(rs[i], chunk_col(i));
+        for (int i = 0; i < kShared; ++i) {
+          if (i & 1) emit(rs[i], chunk_col(i), rres1, i + 2);
+          else emit(rs[i], chunk_col(i), rres0, i + 2);
+        }
       }
 #pragma unroll
       for (int i = kShared; i < kChunks; i += 2) {
         tmem_ld_wait();  // ra = chunk i
         if (i + 1 < kChunks) tmem_ld32(tbase + (uint32_t)(chunk_col(i + 1) * 32), rb);
-        emit(ra, chunk_col(i));
+        if (i & 1) emit(ra, chunk_col(i), rres1, i + 2);
+        else emit(ra, chunk_col(i), rres0, i + 2);
         if (i + 1 < kChunks) {
           tmem_ld_wait();  // rb = chunk i + 1
           if (i + 2 < kChunks) tmem_ld32(tbase + (uint32_t)(chunk_col(i + 2) * 32), ra);
-          emit(rb, chunk_col(i + 1));
+          if ((i + 1) & 1) emit(rb, chunk_col(i + 1), rres1, i + 3);
+          else emit(rb, chunk_col(i + 1), rres0, i + 3);
         }
       }
       if constexpr (RS) {
@@ -1150,6 +1193,11 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
                          __uint_as_float(w0 & 0xffff0000u) + __uint_as_float(bv.x & 0xffff0000u));
           w1 = pack_bf16(__uint_as_float(w1 << 16) + __uint_as_float(bv.y << 16),
                          __uint_as_float(w1 & 0xffff0000u) + __uint_as_float(bv.y & 0xffff0000u));
+        }
+        if (p.residual != nullptr) {
+          const uint2 rv = __ldg(reinterpret_cast<const uint2*>(p.residual + grow * p.N + gcol));
+          w0 = add_bf16x2(w0, rv.x);
+          w1 = add_bf16x2(w1, rv.y);
         }
         *reinterpret_cast<uint2*>(p.c + grow * p.N + gcol) = make_uint2(w0, w1);
       }
@@ -1664,6 +1712,13 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
   p.N = N;
   p.c = static_cast<__nv_bfloat16*>(c);
   p.bias = static_cast<const __nv_bfloat16*>(bias);
+  if (ex != nullptr && ex->residual != nullptr) {
+    if (act || rsl != nullptr || grouped || ((uintptr_t)ex->residual & 15)) {
+      set_error("matmul: the residual input (16-byte aligned bf16 [M, N]) goes with the plain GEMM only");
+      return MMX_ERR_INVALID;
+    }
+    p.residual = static_cast<const __nv_bfloat16*>(ex->residual);
+  }
   static uint32_t* dbg_addr[kMaxDevices] = {};  // the symbol's address differs from device to device
   {
     const int dev = current_device_slot();
@@ -1725,6 +1780,20 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul(const uint8_t* 
                           int64_t N, int KN, int KS, int KO, int w4, const void* bias, void* c, void* stream) {
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c,
                           stream, nullptr);
+}
+
+// mmx_matmul with a residual input (extension): c = bf16(residual + y), y = mmx_matmul's result (bias included) -- the
+// `residual + self_attn(...)` / `residual + mlp(...)` adds of the decoder layer (model/qLlamaLayer.py:116-158) in the GEMM's
+// epilogue, with torch's rounding (one fp32 add, one rounding to bf16).  residual: bf16 [M, N], may be c itself.
+extern "C" __attribute__((visibility("default"))) int mmx_matmul_residual(
+    const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
+    const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+    const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, const void* bias, const void* residual, void* c,
+    void* stream) {
+  mmx::MatmulExtra ex;
+  ex.residual = residual;
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c, stream,
+                          nullptr, &ex);
 }
 
 // Fused gate_up GEMM + SiLU(gate) * up + MX quantize (extension; the reference runs matmul, then activate_quantize_x,

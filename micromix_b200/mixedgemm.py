@@ -102,11 +102,12 @@ def reorder_quantize_w4(W, reorder_index, KN, KS, KO):
                              lambda kn, ks, ko: (kn // 2, ks // 2, ko // 2), False)
 
 
-def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None, out=None):
+def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None, out=None, residual=None):
     """output = A @ B^T over the three mixed-MX segments (bindings.cpp:50-102) -> bf16 [M, N].
 
-    `bias` (bf16 [N]) and `out` are extensions: bias is added in the epilogue with the rounding of the reference's
-    separate `y + self.bias` (model/qLinearLayer.py:70-71).
+    `bias` (bf16 [N]), `out` and `residual` are extensions: bias is added in the epilogue with the rounding of the
+    reference's separate `y + self.bias` (model/qLinearLayer.py:70-71); `residual` (bf16 [M, N], may be `out`) is then added
+    with the rounding of the decoder layer's separate `residual + hidden_states` (model/qLlamaLayer.py:116-158).
     """
     lib = _lib.load()
     names = ("AN", "BN", "AS", "BS", "AO", "BO", "SFAN", "SFBN", "SFAS", "SFBS", "SFAO", "SFBO")
@@ -146,7 +147,15 @@ def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None
             if tuple(out.shape) != (M, N):
                 raise ValueError(f"out must be [{M}, {N}]")
         rc = 0
-        if M > 0:
+        if residual is not None:
+            _check_cuda("residual", residual, torch.bfloat16, 2)
+            if tuple(residual.shape) != (M, N) or not residual.is_contiguous():
+                raise ValueError(f"residual must be a contiguous [{M}, {N}] tensor")
+            if M > 0:
+                rc = lib.mmx_matmul_residual(_ptr(AN), _ptr(BN), _ptr(AS), _ptr(BS), _ptr(AO), _ptr(BO), _ptr(SFAN), _ptr(SFBN),
+                                             _ptr(SFAS), _ptr(SFBS), _ptr(SFAO), _ptr(SFBO), M, N, KN, KS, KO, w4, _ptr(bias),
+                                             _ptr(residual), _ptr(out), _stream())
+        elif M > 0:
             rc = lib.mmx_matmul(_ptr(AN), _ptr(BN), _ptr(AS), _ptr(BS), _ptr(AO), _ptr(BO), _ptr(SFAN), _ptr(SFBN),
                                 _ptr(SFAS), _ptr(SFBS), _ptr(SFAO), _ptr(SFBO), M, N, KN, KS, KO, w4, _ptr(bias),
                                 _ptr(out), _stream())

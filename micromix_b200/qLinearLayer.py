@@ -109,11 +109,15 @@ class QLinearLayer(nn.Module):
         return self
 
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """`residual` (extension, bf16 [bsz, q_len, out_features]): returns residual + linear(x), added in the GEMM's
+        epilogue with the rounding of the separate torch add."""
         bsz, q_len, _ = x.shape
         x = x.reshape(bsz * q_len, -1).contiguous()
         AN, AS, AO, SFAN, SFAS, SFAO = mixedgemm.reorder_quantize_x(
             x, self.reorder_index, self.p4_num, self.p6_num, self.p8_num)
+        if residual is not None:
+            residual = residual.reshape(bsz * q_len, -1).contiguous()
         y = mixedgemm.matmul(AN, self.BN, AS, self.BS, AO, self.BO, SFAN, self.SFBN, SFAS, self.SFBS, SFAO,
-                             self.SFBO, bias=self.bias)
+                             self.SFBO, bias=self.bias, residual=residual)
         return y.reshape(bsz, q_len, -1)

@@ -355,3 +355,26 @@ def test_fast_silu_equals_reference_sequence_on_every_bf16_in_range(cuda, mmx_li
     assert int(inr.sum()) == 2 * (0x4200 - 0x2180 + 1)
     bad = inr & (fast != ref)
     assert int(bad.sum()) == 0, [hex(int(b)) for b in bits[bad][:8]]
+
+
+@pytest.mark.parametrize("M,N,split,bias", [(1, 512, (256, 128, 128), False), (64, 1152, (640, 256, 128), True),
+                                            (200, 512, (256, 128, 128), False), (1000, 1024, (640, 256, 128), True),
+                                            (515, 4096, (2560, 1024, 512), False)])
+def test_residual_epilogue_matches_separate_add(cuda, M, N, split, bias):
+    """matmul(..., residual=r) == r + matmul(...) (torch's bf16 add), bit for bit: the decoder layer's residual adds in the
+    GEMM epilogue, split-K (M <= 128), single-CTA and pair kernels, with and without the bias epilogue, in place too."""
+    K = sum(split)
+    idx = H.make_index(K, seed=N)
+    x, w = H.make_activations(M, K, idx, seed=3 + M), H.make_weights(N, K, seed=4 + M)
+    a, b = _quantize(cuda, x, w, idx, split, False)
+    g = torch.Generator(device=cuda).manual_seed(M)
+    r = torch.randn(M, N, generator=g, device=cuda, dtype=torch.float32).to(torch.bfloat16)
+    bv = (torch.randn(N, generator=g, device=cuda, dtype=torch.float32) * 0.1).to(torch.bfloat16) if bias else None
+    want = r + _mm(a, b, bias=bv)
+    got = _mm(a, b, bias=bv, residual=r)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    r2 = r.clone()
+    _mm(a, b, bias=bv, residual=r2, out=r2)
+    torch.cuda.synchronize()
+    assert torch.equal(r2, want)
