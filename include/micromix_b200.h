@@ -288,6 +288,15 @@ int mmx_tp_matmul_exchanged(void* ctx, const uint8_t* bn, const uint8_t* bs, con
 int mmx_reorder_quantize_x_grouped(const void* x, int64_t M, int K, const int16_t* idx, const int32_t* grp_rowblk,
                                    const int32_t* row_src, const int32_t* rows_dev, int KN, int KS, int KO, uint8_t* xn,
                                    uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
+/* mmx_matmul_grouped with the epilogue of mmx_matmul_activate_quantize: every group's block of B rows holds its gate (w1) and
+ * up (w3) rows interleaved per 128 channels, N = B rows per group = 2 * (DN + DS + DO); outputs = the operand tensors of the
+ * grouped down (w2) GEMM over the same sorted rows (rows of skipped padding tiles are not written). */
+int mmx_matmul_grouped_activate_quantize(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs,
+                                         const uint8_t* ao, const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn,
+                                         const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao, const uint8_t* sfbo,
+                                         int64_t M, int64_t N, int KN, int KS, int KO, int w4, int groups, int tile_rows,
+                                         const int32_t* grp_mblk, const int32_t* rows_dev, int DN, int DS, int DO, uint8_t* xn,
+                                         uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream);
 /* mmx_activate_quantize_x_strided on the first *rows_dev rows only (rows_dev: int32 in DEVICE memory, a multiple of 128;
  * M = the static upper bound the buffers were sized for): the expert-sorted matrix of the grouped path is padded to a
  * bound known on the host, its used length only on the device. */

@@ -1569,8 +1569,8 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
                 (long long)N, ex->act_k[0], ex->act_k[1], ex->act_k[2]);
       return MMX_ERR_INVALID;
     }
-    if (bias != nullptr || rsl != nullptr || ex->grp_mblk != nullptr || ex->ag_arrived != nullptr) {
-      set_error("matmul_activate_quantize: no bias, no tensor-parallel or grouped form");
+    if (bias != nullptr || rsl != nullptr || ex->ag_arrived != nullptr) {
+      set_error("matmul_activate_quantize: no bias, no tensor-parallel form");
       return MMX_ERR_INVALID;
     }
     for (int i = 0; i < 3; ++i)
@@ -1978,6 +1978,38 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul_grouped(
   ex.rows_dev = rows_dev;
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, nullptr, c, stream,
                           nullptr, &ex);
+}
+
+// mmx_matmul_grouped with the SiLU(gate) * up + MX quantize epilogue of mmx_matmul_activate_quantize: every group's B block
+// holds its gate (w1) and up (w3) rows interleaved per 128 channels, N = rows per group = 2 * (DN + DS + DO); the outputs are
+// the operand tensors of the grouped down (w2) GEMM over the same sorted rows.
+extern "C" __attribute__((visibility("default"))) int mmx_matmul_grouped_activate_quantize(
+    const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
+    const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+    const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, int groups, int tile_rows,
+    const int32_t* grp_mblk, const int32_t* rows_dev, int DN, int DS, int DO, uint8_t* xn, uint8_t* xs, uint8_t* xo,
+    uint8_t* sfn, uint8_t* sfs, uint8_t* sfo, void* stream) {
+  if (!grp_mblk || groups <= 0 || !xn) {
+    mmx::set_error("matmul_grouped_activate_quantize: null group table, no groups or an empty FP4 segment");
+    return MMX_ERR_INVALID;
+  }
+  mmx::MatmulExtra ex;
+  ex.grp_mblk = grp_mblk;
+  ex.grp_n = (int)N;
+  ex.grp_count = groups;
+  ex.grp_tile_rows = tile_rows;
+  ex.rows_dev = rows_dev;
+  ex.act_q[0] = xn;
+  ex.act_q[1] = xs;
+  ex.act_q[2] = xo;
+  ex.act_sf[0] = sfn;
+  ex.act_sf[1] = sfs;
+  ex.act_sf[2] = sfo;
+  ex.act_k[0] = DN;
+  ex.act_k[1] = DS;
+  ex.act_k[2] = DO;
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, nullptr, nullptr,
+                          stream, nullptr, &ex);
 }
 
 extern "C" __attribute__((visibility("default"))) int mmx_gemm_debug_status(uint32_t* out, int n) {

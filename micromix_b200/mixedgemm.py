@@ -358,11 +358,13 @@ def reorder_quantize_x_grouped(X, reorder_index, group_of_rowblock, KN, KS, KO, 
     return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
 
 
-def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None, rows_used=None):
+def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None, rows_used=None, act_split=None):
     """Extension: ONE persistent mixed GEMM over all experts.  A = the six tensors of the sorted, padded activation
     ([M, *]); W = six tensors with the experts' MXFP4 weights stacked on N ([groups * N, *]); group_of_mtile int32
     [M / tile_rows] (device): expert of each m-tile, -1 = padding tile (skipped); rows_used int32 [1] (device, optional):
-    rows that exist -- the tile walk stops there -> bf16 [M, N]."""
+    rows that exist -- the tile walk stops there -> bf16 [M, N].
+    act_split = (DN, DS, DO): every expert's rows are interleave_gate_up(w1, w3) and the epilogue emits the MX-quantized
+    SiLU(w1 x) * (w3 x) instead -> the six operand tensors of the grouped w2 GEMM (see matmul_activate_quantize)."""
     lib = _lib.load()
     for t in list(A) + list(W):
         _check_cuda("operand", t, torch.uint8)
@@ -374,6 +376,21 @@ def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None, rows_used=
     N = W[0].size(0) // groups
     if tile_rows not in (128, 256) or M % tile_rows or group_of_mtile.numel() < M // tile_rows:
         raise ValueError("M must be padded to whole m-tiles (128 | 256 rows), one group id per m-tile")
+    if act_split is not None:
+        DN, DS, DO = _check_split(N // 2, *act_split)
+        opts = dict(dtype=torch.uint8, device=A[0].device)
+        with torch.cuda.device(A[0].device):
+            q = [torch.empty((M, w), **opts) for w in (DN // 2, DS // 4 * 3, DO)]
+            sf = [torch.empty((int(lib.mmx_sf_bytes_act(M, k)),), **opts) for k in (DN, DS, DO)]
+            rc = 0
+            if M > 0:
+                rc = lib.mmx_matmul_grouped_activate_quantize(
+                    _ptr(A[0]), _ptr(W[0]), _ptr(A[1]), _ptr(W[1]), _ptr(A[2]), _ptr(W[2]), _ptr(A[3]), _ptr(W[3]), _ptr(A[4]),
+                    _ptr(W[4]), _ptr(A[5]), _ptr(W[5]), M, N, KN, KS, KO, 1, int(groups), int(tile_rows), _ptr(group_of_mtile),
+                    _ptr(rows_used), DN, DS, DO, _ptr(q[0]), _ptr(q[1]), _ptr(q[2]), _ptr(sf[0]), _ptr(sf[1]), _ptr(sf[2]),
+                    _stream())
+        _lib.check(rc, "mmx_matmul_grouped_activate_quantize")
+        return (q[0], q[1], q[2], sf[0], sf[1], sf[2])
     with torch.cuda.device(A[0].device):
         if out is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=A[0].device)

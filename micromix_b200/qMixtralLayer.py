@@ -94,7 +94,7 @@ class QMixtralSparseMoeBlock(nn.Module):
     no device->host synchronisation anywhere.  `grouped=False` is the reference's op sequence: a Python loop over experts."""
 
     def __init__(self, originalSparseMoeBlock, p8_nums, p6_nums, reorder_index, i, ep_group=None, fused=False, grouped=None,
-                 _emulate_ep=None):
+                 _emulate_ep=None, act_epilogue=True):
         """_emulate_ep = (ep, rank): profiling aid -- this process plays ONE rank of an ep-way expert-parallel block (its
         experts only, no combine across ranks), so that the per-rank work can be profiled on one GPU."""
         super().__init__()
@@ -107,6 +107,8 @@ class QMixtralSparseMoeBlock(nn.Module):
         if self._emulated:
             self.ep, self.rank = int(_emulate_ep[0]), int(_emulate_ep[1])
         self.fused = bool(fused)
+        # fused + grouped: SiLU(w1 x) * (w3 x) and the quantization of w2's operand run in the w1||w3 GEMM's epilogue
+        self.act_epilogue = bool(act_epilogue) and self.fused
         self.local = [j for j in range(self.num_experts) if j % self.ep == self.rank]
         key = lambda j, n: _KEY.format(i, 'block_sparse_moe', 'experts', j, n, 'input')
         same = lambda n: all(int(p8_nums[key(j, n)]) == int(p8_nums[key(self.local[0], n)]) and
@@ -148,7 +150,13 @@ class QMixtralSparseMoeBlock(nn.Module):
                 W2.append(mixedgemm.downproj_quantize_w4(w2[:, perm].contiguous(), *self.s2))
             else:
                 W2.append(mixedgemm.reorder_quantize_w4(w2.contiguous(), i2, *self.s2))
-            W13.append(mixedgemm.reorder_quantize_w4(torch.cat([w1, w3], 0).contiguous(), i13, *self.s13))
+            if self.act_epilogue and self.inter % 128 == 0 and self.s2[0] > 0:
+                w13 = mixedgemm.interleave_gate_up(w1, w3)
+            else:
+                self.act_epilogue = False
+                w13 = torch.cat([w1, w3], 0).contiguous()
+            W13.append(mixedgemm.reorder_quantize_w4(w13, i13, *self.s13))
+            del w13
             idx13.append(i13)
             idx2.append(i2)
             del w1, w2, w3
@@ -178,8 +186,12 @@ class QMixtralSparseMoeBlock(nn.Module):
         tile = 256 if T * self.top_k >= 256 * self.num_experts else 128
         row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = route_tables(sel, self.local_slot, n_local, tile)
         a = mixedgemm.reorder_quantize_x_grouped(x, self.idx13, grp_rowblk, *self.s13, row_src=row_src, rows=Mp, rows_used=used)
-        h = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile, rows_used=used)   # [Mp, 2 * inter]
         I = self.inter
+        if self.fused and self.act_epilogue:
+            a2 = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile, rows_used=used, act_split=self.s2)
+            y = mixedgemm.matmul_grouped(a2, self._w("W2"), grp_mtile, n_local, tile, rows_used=used)   # [Mp, hidden]
+            return mixedgemm.moe_combine(y, pair_row, sel.to(torch.int32), w.contiguous())
+        h = mixedgemm.matmul_grouped(a, self._w("W13"), grp_mtile, n_local, tile, rows_used=used)   # [Mp, 2 * inter]
         if self.fused:
             a2 = mixedgemm.activate_quantize_x(h[:, :I], h[:, I:], *self.s2, rows_used=used)
         else:

@@ -119,3 +119,10 @@ def test_moe_block_grouped_equals_expert_loop(cuda, fused, tokens):
     assert torch.equal(la, lb)
     assert torch.isfinite(b.float()).all()
     assert torch.equal(a, b), f"max diff {(a.float() - b.float()).abs().max().item()}"
+    if fused:
+        # the grouped GEMM's SiLU * up + quantize epilogue against the two separate kernels (grouped GEMM -> activate_quantize_x)
+        two = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, fused=True, act_epilogue=False)
+        assert grp.act_epilogue and not two.act_epilogue
+        c, _ = two(x)
+        torch.cuda.synchronize()
+        assert torch.equal(c, b)
