@@ -998,7 +998,8 @@ def measure_prefill(args, dev):
     """BASELINE config 3 -- the metric's "prefill tokens/s" half: ALL 32 Llama-3-8B decoder layers (random-init weights,
     synthetic reorder_index, 5-bit split), batch 8 x seq 2048 = 16384 tokens (/root/reference/prof_micromix.sh:1), through
     QLlamaDecoderLayer(fused=True) -- RMSNorm inside the quantizer, SiLU*up inside down_proj's quantizer -- replayed from
-    ONE CUDA graph.  Attention is torch SDPA, RoPE / residual adds are torch ops: only the linears are the hot path."""
+    ONE CUDA graph.  fused=True: SiLU*up + down_proj's quantizer run in the gate_up GEMM's epilogue, the residual adds in the
+    o_proj / down_proj epilogues, RoPE in place on the qkv output (library kernel); attention is torch SDPA (cuDNN)."""
     import torch
     from micromix_b200 import mixedgemm
     from micromix_b200 import model_shapes as S
@@ -1054,7 +1055,8 @@ def measure_prefill(args, dev):
            "iters": n, "cuda_graph": True, "mmx_launches_per_prefill": int(launches), "output_finite": finite,
            "fused_norm_act": True,
            "note": "decoder layers only (no embedding / lm_head, as in the reference's layer-wise eval); attention = torch "
-                   "SDPA, RoPE / residual adds = torch ops; one CUDA-graph replay per prefill"}
+                   "SDPA (cuDNN); RoPE = the library's in-place kernel; SiLU*up + quantize and the residual adds run in GEMM epilogues; "
+                   "one CUDA-graph replay per prefill"}
     del graph, layers, y
     torch.cuda.empty_cache()
     return out
