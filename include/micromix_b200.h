@@ -119,6 +119,17 @@ int mmx_matmul_residual(const uint8_t* an, const uint8_t* bn, const uint8_t* as,
                         const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
                         const void* bias, const void* residual, void* c, void* stream);
 
+/* mmx_matmul with the rotary position embedding of the q / k heads in the epilogue (extension; the reference applies HF's
+ * apply_rotary_pos_emb with torch ops, model/qLlamaLayer.py:25-54, 271-272).  The first rope_cols columns of C (a multiple of
+ * 128) are heads of 128 channels whose B and bias rows are stored PAIR-ADJACENT: row 2j of a head = channel j, row 2j + 1 =
+ * channel j + 64.  The epilogue computes q * cos + rotate_half(q) * sin with the torch ops' three bf16 roundings and stores
+ * every value at its ORIGINAL column: C = mmx_matmul on the unpermuted weight followed by mmx_rope_inplace, bit for bit.
+ * cos / sin: bf16 [S, 128], 16-byte aligned; row m uses table row m % S.  Columns >= rope_cols are plain. */
+int mmx_matmul_rope(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
+                    const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,
+                    const uint8_t* sfao, const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4,
+                    const void* bias, const void* cos, const void* sin, int64_t S, int rope_cols, void* c, void* stream);
+
 /* matmul + activate_quantize_x in ONE kernel (extension; the reference runs mixedgemm.matmul for gate_proj / up_proj,
  * model/qLlamaLayer.py:324-387, then activate_quantize_x on the two bf16 results): the GEMM epilogue rounds its accumulators
  * to bf16 (what mmx_matmul would have stored), evaluates silu(gate) * up and MX-quantizes it -- the [M, 2 * inter] bf16

@@ -70,17 +70,20 @@ class FusedQLinear(nn.Module):
         self.in_features, self.out_features = weight.shape[1], weight.shape[0]
 
     @torch.no_grad()
-    def forward_whole(self, x, norm=None):
+    def forward_whole(self, x, norm=None, rope=None):
         """The concatenated output [b, s, sum(splits)] (one GEMM); norm = (weight bf16 [K], eps): x is the UN-normalised
-        input and RMSNorm runs inside the quantizer."""
-        if norm is None:
+        input and RMSNorm runs inside the quantizer; rope = (cos, sin, rope_cols): see mixedgemm.matmul."""
+        if norm is None and rope is None:
             return self.inner(x)
         lin = self.inner
         bsz, q_len, _ = x.shape
-        a = mixedgemm.rmsnorm_quantize_x(x.reshape(bsz * q_len, -1).contiguous(), norm[0], norm[1], lin.reorder_index,
-                                         lin.p4_num, lin.p6_num, lin.p8_num)
+        x2 = x.reshape(bsz * q_len, -1).contiguous()
+        if norm is None:
+            a = mixedgemm.reorder_quantize_x(x2, lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num)
+        else:
+            a = mixedgemm.rmsnorm_quantize_x(x2, norm[0], norm[1], lin.reorder_index, lin.p4_num, lin.p6_num, lin.p8_num)
         return mixedgemm.matmul(a[0], lin.BN, a[1], lin.BS, a[2], lin.BO, a[3], lin.SFBN, a[4], lin.SFBS, a[5], lin.SFBO,
-                                bias=lin.bias).reshape(bsz, q_len, -1)
+                                bias=lin.bias, rope=rope).reshape(bsz, q_len, -1)
 
     @torch.no_grad()
     def forward(self, x, norm=None):
@@ -201,7 +204,10 @@ class QAttention(nn.Module):
     """Llama / Qwen2 / Mixtral attention with quantized projections (qLlamaLayer.py:196-321, qQwenLayer.py:205-327)."""
 
     def __init__(self, originalAttn, kv_cache, p8_nums, p6_nums, reorder_index, i, tp_group=None, workspace=None,
-                 sequence_parallel=False, token_parallel_rows=False):
+                 sequence_parallel=False, token_parallel_rows=False, rope_epilogue=False):
+        """rope_epilogue (extension, single GPU): the q / k weight rows are stored pair-adjacent inside each head
+        (mixedgemm.pair_adjacent_rows) and the qkv GEMM's epilogue applies the rotary embedding (matmul(..., rope=)); the
+        output is bit-identical to GEMM + rope_inplace / HF's apply_rotary_pos_emb."""
         super().__init__()
         self.sp = bool(sequence_parallel)
         self.tpr = bool(token_parallel_rows) and self.sp
@@ -225,8 +231,17 @@ class QAttention(nn.Module):
             slices = [slice(self.rank * self.num_heads * d, (self.rank + 1) * self.num_heads * d),
                       slice(self.rank * self.num_key_value_heads * d, (self.rank + 1) * self.num_key_value_heads * d),
                       slice(self.rank * self.num_key_value_heads * d, (self.rank + 1) * self.num_key_value_heads * d)]
-        self.qkv_proj = build_input_group([originalAttn.q_proj, originalAttn.k_proj, originalAttn.v_proj], keys, p8_nums,
-                                          p6_nums, reorder_index, slices)
+        qkv = [originalAttn.q_proj, originalAttn.k_proj, originalAttn.v_proj]
+        shared = all(_same(reorder_index[k], reorder_index[keys[0]]) and _same(p8_nums[k], p8_nums[keys[0]]) and
+                     _same(p6_nums[k], p6_nums[keys[0]]) for k in keys[1:])
+        self.rope_epilogue = bool(rope_epilogue) and self.tp == 1 and not self.sp and shared and d == 128
+        if self.rope_epilogue:
+            def paired(lin, heads):
+                w = mixedgemm.pair_adjacent_rows(lin.weight.data, heads, d)
+                b = None if lin.bias is None else mixedgemm.pair_adjacent_rows(lin.bias.data, heads, d)
+                return _meta_linear(w, b)
+            qkv = [paired(qkv[0], self.num_heads), paired(qkv[1], self.num_key_value_heads), qkv[2]]
+        self.qkv_proj = build_input_group(qkv, keys, p8_nums, p6_nums, reorder_index, slices)
         ko = NAME.format(i, 'self_attn', 'o_proj', 'input')
         if self.tp > 1 and self.tpr:
             self.o_proj = TokenParallelQLinear(originalAttn.o_proj, p8_nums[ko], p6_nums[ko], reorder_index[ko], tp_group,
@@ -253,7 +268,22 @@ class QAttention(nn.Module):
         tables = None
         if len(self.qkv_proj) == 1 and position_embeddings is not None and self.head_dim % 16 == 0:
             tables = rope_tables_2d(position_embeddings, bsz, q_len, self.head_dim)
-        if tables is not None:
+        if self.rope_epilogue:
+            m = self.qkv_proj[0]
+            nrope = (self.num_heads + self.num_key_value_heads) * self.head_dim
+            if tables is not None:
+                y = m.forward_whole(hidden_states, norm, rope=(tables[0], tables[1], nrope))
+                tables = None  # done
+                position_embeddings_applied = True
+            else:
+                # no [S, d] tables (or no rotary embedding at all): undo the pair-adjacent column order of q / k
+                y = m.forward_whole(hidden_states, norm).reshape(bsz * q_len, -1)
+                qk = mixedgemm.pair_adjacent_rows(y[:, :nrope].t(), self.num_heads + self.num_key_value_heads, self.head_dim,
+                                                  inverse=True).t()
+                y = torch.cat([qk, y[:, nrope:]], dim=-1)
+                position_embeddings_applied = False
+            q, k, v = y.view(bsz, q_len, -1).split(m.splits, dim=-1)
+        elif tables is not None:
             m = self.qkv_proj[0]
             if self.sp:
                 y = m.forward_gathered_whole(hidden_states.reshape(-1, hidden_states.shape[-1]).contiguous(), bsz * q_len,
@@ -273,7 +303,10 @@ class QAttention(nn.Module):
         v = v.view(bsz, q_len, self.num_key_value_heads, self.head_dim).transpose(1, 2)
         if position_embeddings is not None:
             cos, sin = position_embeddings
-            if tables is None:
+            if self.rope_epilogue:
+                if not position_embeddings_applied:
+                    q, k = apply_rope(q, k, cos, sin)
+            elif tables is None:
                 q, k = apply_rope(q, k, cos, sin)
         else:
             cos = sin = None
@@ -399,8 +432,12 @@ class QDecoderLayer(nn.Module):
     (qLlamaLayer.py:116-158): returns (hidden_states,) [+ (attn_weights,)] [+ (present_key_value,)]."""
 
     def __init__(self, originalLayer, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx, tp_group=None, fused=False,
-                 workspace=None, sequence_parallel=False, token_parallel_rows=False):
-        """`workspace` (extension): a parallel_utils.PeerWorkspace shared by the model's row-parallel linears -- o_proj and
+                 workspace=None, sequence_parallel=False, token_parallel_rows=False, rope_epilogue=False):
+        """`rope_epilogue` (with fused, single GPU; OFF by default): RoPE in the qkv GEMM's epilogue instead of the in-place
+        kernel.  Bit-identical, but measured SLOWER (Llama-3-8B prefill 79.9 vs 75.2 ms, profiles/r02_rope_epilogue.txt): a
+        TMEM lane is a token row, so the cos / sin loads and the un-permuting stores of a warp touch 32 different lines per
+        instruction and the epilogue outlasts the MMAs of a K = 4096 tile.
+        `workspace` (extension): a parallel_utils.PeerWorkspace shared by the model's row-parallel linears -- o_proj and
         down_proj then run as GEMMs fused with their all-reduce instead of GEMM + NCCL all-reduce.
         `sequence_parallel` (extension, needs a workspace with a gather channel): the layer takes and returns THIS rank's
         token rows only ([1, rows, hidden], rows = workspace.shard_range(b*s)): o_proj / down_proj end in a reduce-scatter,
@@ -417,7 +454,8 @@ class QDecoderLayer(nn.Module):
         self._workspace = workspace
         self.hidden_size = getattr(originalLayer, "hidden_size", None) or originalLayer.self_attn.config.hidden_size
         self.self_attn = QAttention(originalLayer.self_attn, kv_cache, p8_nums, p6_nums, reorder_index, layer_idx,
-                                    tp_group, workspace, sequence_parallel=self.sp, token_parallel_rows=self.tpr)
+                                    tp_group, workspace, sequence_parallel=self.sp, token_parallel_rows=self.tpr,
+                                    rope_epilogue=self.fused and rope_epilogue)
         if self.sp and len(self.self_attn.qkv_proj) != 1:
             raise ValueError("sequence_parallel needs q/k/v to share one (reorder_index, p6, p8): one gather feeds ONE GEMM")
         self.mlp = self._build_mlp(originalLayer, p8_nums, p6_nums, reorder_index, layer_idx, tp_group)

@@ -92,6 +92,10 @@ struct MatmulExtra {
   uint8_t* act_sf[3] = {};
   int act_k[3] = {};
   const void* residual = nullptr;  // bf16 [M, N]: c = bf16(residual + product), see GemmParams::residual
+  const void* rope_cos = nullptr;  // rotary embedding in the epilogue, see GemmParams::rope_cos
+  const void* rope_sin = nullptr;
+  int rope_S = 0;
+  int rope_cols = 0;
 };
 int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao,
                 const uint8_t* bo, const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs,

@@ -136,6 +136,13 @@ struct GemmParams {
   // c = bf16(residual + bf16(acc)) -- the decoder layer's `residual + o_proj(...)` / `residual + down_proj(...)`
   // (model/qLlamaLayer.py:116-158) without a separate elementwise kernel; may alias c
   const __nv_bfloat16* residual;
+  // ROPE kernels (mmx_matmul_rope): the first rope_cols columns of C are q / k heads of 128 channels whose B rows were stored
+  // PAIR-ADJACENT (row 2j of a head = channel j, row 2j + 1 = channel j + 64), so a lane holds both partners of the rotary
+  // embedding in neighbouring accumulator columns; the epilogue applies HF's apply_rotary_pos_emb with its three bf16
+  // roundings (rope.cu) and stores every value at its ORIGINAL column -- C is what matmul + mmx_rope_inplace produce.
+  const __nv_bfloat16* rope_cos;  // bf16 [rope_S, 128]; row m uses table row m % rope_S
+  const __nv_bfloat16* rope_sin;
+  int rope_cols, rope_S;
   uint32_t* dbg;
   uint32_t flags;  // watchdog build only: 1 = skip SF copies, 2 = skip MMAs, 4 = skip C stores
 };
@@ -487,12 +494,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 // contiguous 1/SK of the tile's K stages in their own TMEM, park the fp32 accumulator in their (now idle) stage buffers,
 // and CTA r of the cluster sums column slice r of all SK copies through distributed shared memory -- in CTA order, so the
 // result does not depend on timing -- and writes bf16.  One tile per cluster, no global workspace, no atomics.
-template <int CG, bool WD, bool RS, int SK = 1, bool ACT = false>
+template <int CG, bool WD, bool RS, int SK = 1, bool ACT = false, bool ROPE = false>
 __global__ void __launch_bounds__(kThreads, 1)
 mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__ GemmParams p,
                   const __grid_constant__ std::conditional_t<RS, RsParams, NoRsParams> rs) {
   static_assert(SK == 1 || (CG == 1 && !WD && !RS), "split-K is a variant of the plain single-CTA kernel");
   static_assert(!ACT || (SK == 1 && !WD && !RS), "the fused activation is a variant of the plain kernels");
+  static_assert(!ROPE || (SK == 1 && !WD && !RS && !ACT), "the fused rotary embedding is a variant of the plain kernels");
   using G = Geo<CG, RS>;
   constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];  // no static smem in this kernel: offset 0 of the window
@@ -1032,7 +1040,7 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         }
       };
       uint4 rres0[4] = {}, rres1[4] = {};
-      const bool has_res = !RS && p.residual != nullptr;
+      const bool has_res = !RS && !ROPE && p.residual != nullptr;
       if (has_res) {
         res_issue(0, rres0);
         res_issue(1, rres1);
@@ -1042,6 +1050,51 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
         if (col0 < p.N) {  // warp-uniform
           uint32_t o[16];
           pack_chunk(r, o, p.bias ? p.bias + col0 : nullptr);
+          if constexpr (ROPE) {
+            if (col0 < p.rope_cols) {  // warp-uniform: a q / k chunk -- word e = (channel j0 + e, channel j0 + e + 64)
+              const int64_t row = row0 + lane;
+              if (row < p.M) {
+                const int hcol = col0 & ~127, j0 = (col0 & 127) >> 1;  // head's first column; first channel of the chunk
+                const int64_t toff = (row % p.rope_S) * 128 + j0;
+                const uint4* cl = reinterpret_cast<const uint4*>(p.rope_cos + toff);
+                const uint4* ch = reinterpret_cast<const uint4*>(p.rope_cos + toff + 64);
+                const uint4* sl = reinterpret_cast<const uint4*>(p.rope_sin + toff);
+                const uint4* sh = reinterpret_cast<const uint4*>(p.rope_sin + toff + 64);
+                uint32_t lo[8], hi[8];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                  const uint4 c1 = __ldg(cl + v), c2 = __ldg(ch + v), s1 = __ldg(sl + v), s2 = __ldg(sh + v);
+                  const uint32_t k1[4] = {c1.x, c1.y, c1.z, c1.w}, k2[4] = {c2.x, c2.y, c2.z, c2.w};
+                  const uint32_t n1[4] = {s1.x, s1.y, s1.z, s1.w}, n2[4] = {s2.x, s2.y, s2.z, s2.w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {  // table word u: channels 2u, 2u + 1 of this half-run (both halves)
+                    uint32_t out[2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                      const uint32_t w = o[8 * v + 2 * u + b];                       // (x1, x2)
+                      const uint32_t cw = __byte_perm(k1[u], k2[u], b ? 0x7632 : 0x5410);  // (cos[j], cos[j + 64])
+                      const uint32_t sw = __byte_perm(n1[u], n2[u], b ? 0x7632 : 0x5410);
+                      const uint32_t rot = __byte_perm(w, w, 0x1032) ^ 0x00008000u;  // (-x2, x1)
+                      const __nv_bfloat162 t1 = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&w),
+                                                           *reinterpret_cast<const __nv_bfloat162*>(&cw));
+                      const __nv_bfloat162 t2 = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&rot),
+                                                           *reinterpret_cast<const __nv_bfloat162*>(&sw));
+                      const __nv_bfloat162 sum = __hadd2_rn(t1, t2);
+                      out[b] = *reinterpret_cast<const uint32_t*>(&sum);
+                    }
+                    lo[4 * v + u] = __byte_perm(out[0], out[1], 0x5410);  // channels j, j + 1
+                    hi[4 * v + u] = __byte_perm(out[0], out[1], 0x7632);  // channels j + 64, j + 65
+                  }
+                }
+                __nv_bfloat16* d = p.c + row * p.N + hcol + j0;
+                *reinterpret_cast<uint4*>(d) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(d + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                *reinterpret_cast<uint4*>(d + 64) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(d + 72) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              }
+              return;
+            }
+          }
           if (has_res) {
             add_residual(o, res);
             if (inext < kChunks) res_issue(inext, res);
@@ -1198,6 +1251,32 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
           const uint2 rv = __ldg(reinterpret_cast<const uint2*>(p.residual + grow * p.N + gcol));
           w0 = add_bf16x2(w0, rv.x);
           w1 = add_bf16x2(w1, rv.y);
+        }
+        if (p.rope_cos != nullptr && gcol < p.rope_cols) {
+          // pair-adjacent q / k columns (see GemmParams::rope_cos): w0 = (x1[j], x2[j]), w1 = (x1[j + 1], x2[j + 1])
+          const int hcol = gcol & ~127, j = (gcol & 127) >> 1;
+          const int64_t toff = (grow % p.rope_S) * 128 + j;
+          const uint32_t c1 = __ldg(reinterpret_cast<const uint32_t*>(p.rope_cos + toff));
+          const uint32_t c2 = __ldg(reinterpret_cast<const uint32_t*>(p.rope_cos + toff + 64));
+          const uint32_t s1 = __ldg(reinterpret_cast<const uint32_t*>(p.rope_sin + toff));
+          const uint32_t s2 = __ldg(reinterpret_cast<const uint32_t*>(p.rope_sin + toff + 64));
+          uint32_t out[2];
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint32_t w = b ? w1 : w0;
+            const uint32_t cw = __byte_perm(c1, c2, b ? 0x7632 : 0x5410), sw = __byte_perm(s1, s2, b ? 0x7632 : 0x5410);
+            const uint32_t rot = __byte_perm(w, w, 0x1032) ^ 0x00008000u;
+            const __nv_bfloat162 t1 = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&w),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&cw));
+            const __nv_bfloat162 t2 = __hmul2_rn(*reinterpret_cast<const __nv_bfloat162*>(&rot),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&sw));
+            const __nv_bfloat162 sum = __hadd2_rn(t1, t2);
+            out[b] = *reinterpret_cast<const uint32_t*>(&sum);
+          }
+          __nv_bfloat16* d = p.c + grow * p.N + hcol + j;
+          *reinterpret_cast<uint32_t*>(d) = __byte_perm(out[0], out[1], 0x5410);
+          *reinterpret_cast<uint32_t*>(d + 64) = __byte_perm(out[0], out[1], 0x7632);
+          continue;
         }
         *reinterpret_cast<uint2*>(p.c + grow * p.N + gcol) = make_uint2(w0, w1);
       }
@@ -1407,7 +1486,8 @@ static uint32_t make_idesc(int kind, int a_bits, int b_bits, int mma_m) {
 }
 
 template <int CG>
-static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs, bool act = false) {
+static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const RsParams* rs, bool act = false,
+                       bool rope = false) {
   const int smem_bytes = rs != nullptr ? Geo<CG, true>::kSmemBytes : Geo<CG, false>::kSmemBytes;
   p.m_tiles = (int)((p.M + BM * CG - 1) / (BM * CG));
   p.n_tiles = (int)((p.N + BN - 1) / BN);
@@ -1441,7 +1521,7 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
   attr[1].val.programmaticStreamSerializationAllowed = options().pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  static bool attr_done[kMaxDevices][4] = {};
+  static bool attr_done[kMaxDevices][5] = {};
   static std::mutex attr_mu;
   const int dev = current_device_slot();
   auto prepare = [&](auto kern, int slot) -> cudaError_t {
@@ -1459,6 +1539,11 @@ static int launch_gemm(const TmapSet& tm, GemmParams& p, cudaStream_t st, const 
     const NoRsParams none = {0};
     auto kern = mixed_gemm_kernel<CG, false, false, 1, true>;
     MMX_CUDA_TRY(prepare(kern, 3));
+    MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, none));
+  } else if (rope) {
+    const NoRsParams none = {0};
+    auto kern = mixed_gemm_kernel<CG, false, false, 1, false, true>;
+    MMX_CUDA_TRY(prepare(kern, 4));
     MMX_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tm, p, none));
   } else {
     const NoRsParams none = {0};
@@ -1719,6 +1804,18 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     }
     p.residual = static_cast<const __nv_bfloat16*>(ex->residual);
   }
+  if (ex != nullptr && ex->rope_cos != nullptr) {
+    if (act || rsl != nullptr || grouped || gathered || ex->residual != nullptr || options().gemm_watchdog != 0 ||
+        !ex->rope_sin || (((uintptr_t)ex->rope_cos | (uintptr_t)ex->rope_sin) & 15) || ex->rope_S <= 0 || ex->rope_cols <= 0 ||
+        (ex->rope_cols % 128) || ex->rope_cols > N) {
+      set_error("matmul_rope: plain GEMM only; cos / sin = 16-byte aligned bf16 [S, 128] tables, rope_cols a multiple of 128 <= N");
+      return MMX_ERR_INVALID;
+    }
+    p.rope_cos = static_cast<const __nv_bfloat16*>(ex->rope_cos);
+    p.rope_sin = static_cast<const __nv_bfloat16*>(ex->rope_sin);
+    p.rope_cols = ex->rope_cols;
+    p.rope_S = ex->rope_S;
+  }
   static uint32_t* dbg_addr[kMaxDevices] = {};  // the symbol's address differs from device to device
   {
     const int dev = current_device_slot();
@@ -1756,7 +1853,8 @@ int matmul_impl(const uint8_t* an, const uint8_t* bn, const uint8_t* as, const u
     if (sk == 4) return launch_gemm_splitk<4>(tm, p, st, false, nullptr);
     return launch_gemm_splitk<2>(tm, p, st, false, nullptr);
   }
-  const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp, act) : launch_gemm<1>(tm, p, st, rsp, act);
+  const bool rope = p.rope_cos != nullptr;
+  const int rc = cg == 2 ? launch_gemm<2>(tm, p, st, rsp, act, rope) : launch_gemm<1>(tm, p, st, rsp, act, rope);
   if (rc == MMX_OK && rsl != nullptr) {
     rsl->cg = cg;
     rsl->m_tiles = p.m_tiles;
@@ -1792,6 +1890,31 @@ extern "C" __attribute__((visibility("default"))) int mmx_matmul_residual(
     void* stream) {
   mmx::MatmulExtra ex;
   ex.residual = residual;
+  return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c, stream,
+                          nullptr, &ex);
+}
+
+// mmx_matmul with the rotary position embedding of the q / k heads in the epilogue (extension; the reference applies HF's
+// apply_rotary_pos_emb with torch ops on the projection outputs, model/qLlamaLayer.py:25-54, 271-272).  The first rope_cols
+// columns of C are heads of 128 channels whose B (and bias) rows are stored PAIR-ADJACENT -- row 2j of a head = channel j,
+// row 2j + 1 = channel j + 64 (mixedgemm.pair_adjacent_rows) -- so both partners of a rotation sit in one lane; the epilogue
+// computes q * cos + rotate_half(q) * sin with the three bf16 roundings of the torch ops and stores every value at its
+// ORIGINAL column: C equals mmx_matmul (on the unpermuted weight) followed by mmx_rope_inplace, bit for bit.  cos / sin:
+// bf16 [S, 128], row m of C uses table row m % S.  Columns >= rope_cols (v) are plain.
+extern "C" __attribute__((visibility("default"))) int mmx_matmul_rope(
+    const uint8_t* an, const uint8_t* bn, const uint8_t* as, const uint8_t* bs, const uint8_t* ao, const uint8_t* bo,
+    const uint8_t* sfan, const uint8_t* sfbn, const uint8_t* sfas, const uint8_t* sfbs, const uint8_t* sfao,
+    const uint8_t* sfbo, int64_t M, int64_t N, int KN, int KS, int KO, int w4, const void* bias, const void* cos,
+    const void* sin, int64_t S, int rope_cols, void* c, void* stream) {
+  if (!cos || S <= 0 || S > 0x7fffffff) {
+    mmx::set_error("matmul_rope: null tables or bad S");
+    return MMX_ERR_INVALID;
+  }
+  mmx::MatmulExtra ex;
+  ex.rope_cos = cos;
+  ex.rope_sin = sin;
+  ex.rope_S = (int)S;
+  ex.rope_cols = rope_cols;
   return mmx::matmul_impl(an, bn, as, bs, ao, bo, sfan, sfbn, sfas, sfbs, sfao, sfbo, M, N, KN, KS, KO, w4, bias, c, stream,
                           nullptr, &ex);
 }

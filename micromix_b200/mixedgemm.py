@@ -102,12 +102,16 @@ def reorder_quantize_w4(W, reorder_index, KN, KS, KO):
                              lambda kn, ks, ko: (kn // 2, ks // 2, ko // 2), False)
 
 
-def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None, out=None, residual=None):
+def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None, out=None, residual=None, rope=None):
     """output = A @ B^T over the three mixed-MX segments (bindings.cpp:50-102) -> bf16 [M, N].
 
     `bias` (bf16 [N]), `out` and `residual` are extensions: bias is added in the epilogue with the rounding of the
     reference's separate `y + self.bias` (model/qLinearLayer.py:70-71); `residual` (bf16 [M, N], may be `out`) is then added
-    with the rounding of the decoder layer's separate `residual + hidden_states` (model/qLlamaLayer.py:116-158).
+    with the rounding of the decoder layer's separate `residual + hidden_states` (model/qLlamaLayer.py:116-158);
+    `rope` = (cos, sin, rope_cols), cos / sin bf16 [S, 128]: the first rope_cols output columns are q / k heads of 128
+    channels whose weight rows were stored with pair_adjacent_rows; HF's apply_rotary_pos_emb (qLlamaLayer.py:25-54) runs in
+    the epilogue and every value lands at its original column -- the result equals matmul on the unpermuted weight followed
+    by rope_inplace, bit for bit.  Row m uses table row m % S.
     """
     lib = _lib.load()
     names = ("AN", "BN", "AS", "BS", "AO", "BO", "SFAN", "SFBN", "SFAS", "SFBS", "SFAO", "SFBO")
@@ -147,7 +151,19 @@ def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None
             if tuple(out.shape) != (M, N):
                 raise ValueError(f"out must be [{M}, {N}]")
         rc = 0
-        if residual is not None:
+        if rope is not None:
+            cos, sin, rope_cols = rope
+            _check_cuda("cos", cos, torch.bfloat16, 2)
+            _check_cuda("sin", sin, torch.bfloat16, 2)
+            if residual is not None:
+                raise ValueError("rope and residual do not combine")
+            if cos.shape != sin.shape or cos.shape[1] != 128 or not cos.is_contiguous() or not sin.is_contiguous():
+                raise ValueError("cos / sin must be contiguous bf16 [S, 128] tables")
+            if M > 0:
+                rc = lib.mmx_matmul_rope(_ptr(AN), _ptr(BN), _ptr(AS), _ptr(BS), _ptr(AO), _ptr(BO), _ptr(SFAN), _ptr(SFBN),
+                                         _ptr(SFAS), _ptr(SFBS), _ptr(SFAO), _ptr(SFBO), M, N, KN, KS, KO, w4, _ptr(bias),
+                                         _ptr(cos), _ptr(sin), cos.shape[0], int(rope_cols), _ptr(out), _stream())
+        elif residual is not None:
             _check_cuda("residual", residual, torch.bfloat16, 2)
             if tuple(residual.shape) != (M, N) or not residual.is_contiguous():
                 raise ValueError(f"residual must be a contiguous [{M}, {N}] tensor")
@@ -161,6 +177,18 @@ def matmul(AN, BN, AS, BS, AO, BO, SFAN, SFBN, SFAS, SFBS, SFAO, SFBO, bias=None
                                 _ptr(out), _stream())
     _lib.check(rc, "mmx_matmul")
     return out
+
+
+def pair_adjacent_rows(t, heads, head_dim=128, inverse=False):
+    """Row order matmul(..., rope=) expects of the q / k weights (and biases): inside every head, row 2j = channel j and row
+    2j + 1 = channel j + head_dim / 2, so that the two partners of a rotary-embedding rotation are neighbouring output
+    columns.  t: dim 0 = heads * head_dim channels.  inverse=True undoes it."""
+    if t.shape[0] != heads * head_dim or head_dim % 2:
+        raise ValueError(f"dim 0 must be heads * head_dim = {heads * head_dim}, got {tuple(t.shape)}")
+    rest = t.shape[1:]
+    if inverse:
+        return t.reshape(heads, head_dim // 2, 2, *rest).transpose(1, 2).reshape(heads * head_dim, *rest).contiguous()
+    return t.reshape(heads, 2, head_dim // 2, *rest).transpose(1, 2).reshape(heads * head_dim, *rest).contiguous()
 
 
 def interleave_gate_up(gate, up, block=128):

@@ -378,3 +378,32 @@ def test_residual_epilogue_matches_separate_add(cuda, M, N, split, bias):
     _mm(a, b, bias=bv, residual=r2, out=r2)
     torch.cuda.synchronize()
     assert torch.equal(r2, want)
+
+
+@pytest.mark.parametrize("M,S,nh,nkv,extra,bias", [(1, 1, 4, 2, 256, False), (96, 48, 4, 2, 256, True), (300, 300, 2, 2, 128, False),
+                                                   (1000, 250, 6, 2, 1024, True), (515, 103, 3, 1, 0, False)])
+def test_rope_epilogue_matches_gemm_then_rope_inplace(cuda, M, S, nh, nkv, extra, bias):
+    """matmul(..., rope=) on pair-adjacent q / k weight rows == matmul on the plain rows followed by rope_inplace (itself
+    bit-identical to HF's apply_rotary_pos_emb, tests/test_models_gpu.py): split-K (M <= 128), single-CTA and pair kernels,
+    with and without a bias, v columns untouched, table rows reused modulo S."""
+    from micromix_b200 import mixedgemm
+    d, K, split = 128, 512, (256, 128, 128)
+    nrope = (nh + nkv) * d
+    N = nrope + extra
+    idx = H.make_index(K, seed=M)
+    x, w = H.make_activations(M, K, idx, seed=11 + M), H.make_weights(N, K, seed=12 + M)
+    g = torch.Generator(device=cuda).manual_seed(M + 1)
+    bv = (torch.randn(N, generator=g, device=cuda, dtype=torch.float32) * 0.1).to(torch.bfloat16) if bias else None
+    ang = torch.rand(S, d // 2, generator=g, device=cuda) * 6.28
+    cos = torch.cat([ang.cos(), ang.cos()], -1).to(torch.bfloat16).contiguous()
+    sin = torch.cat([ang.sin(), (ang * 1.01).sin()], -1).to(torch.bfloat16).contiguous()  # (not symmetric: both halves are read)
+    a, b = _quantize(cuda, x, w, idx, split, False)
+    want = _mm(a, b, bias=bv)
+    mixedgemm.rope_inplace(want, nh + nkv, d, cos, sin)
+    wp = torch.cat([mixedgemm.pair_adjacent_rows(w[:nrope], nh + nkv, d), w[nrope:]])
+    bp = None if bv is None else torch.cat([mixedgemm.pair_adjacent_rows(bv[:nrope], nh + nkv, d), bv[nrope:]])
+    _, b2 = _quantize(cuda, x, wp, idx, split, False)
+    got = _mm(a, b2, bias=bp, rope=(cos, sin, nrope))
+    torch.cuda.synchronize()
+    assert torch.equal(got[:, nrope:], want[:, nrope:])
+    assert torch.equal(got, want), f"{(got.float() - want.float()).abs().max().item()}"

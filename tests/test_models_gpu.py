@@ -167,6 +167,14 @@ def test_fused_norm_and_activation_mode(cuda, cls_path, bias):
     assert norm is not None
     assert torch.equal(fused.mlp(x, norm), two_ops(x, norm))
     assert torch.equal(fused.mlp(x), two_ops(x))
+    # ... and RoPE in the qkv GEMM's epilogue to GEMM -> rope_inplace; without tables the pair-adjacent columns are undone
+    from micromix_b200._qdecoder import QAttention
+    att = QAttention(layer.self_attn, False, p8, p6, idx, 1)
+    att_e = QAttention(layer.self_attn, False, p8, p6, idx, 1, rope_epilogue=True)  # (opt-in: measured slower)
+    assert att_e.rope_epilogue and not att.rope_epilogue and not fused.self_attn.rope_epilogue
+    assert torch.equal(att_e(hidden_states=x, position_embeddings=(cos, sin))[0],
+                       att(hidden_states=x, position_embeddings=(cos, sin))[0])
+    assert torch.equal(att_e(hidden_states=x, position_embeddings=None)[0], att(hidden_states=x, position_embeddings=None)[0])
     d = (a.float() - b.float()).abs()
     scale = a.float().pow(2).mean().sqrt()
     assert float(d.max()) <= 0.05 * float(scale) and float(d.mean()) <= 0.005 * float(scale), (float(d.max()), float(d.mean()), float(scale))
