@@ -52,6 +52,30 @@ def test_row_shard_plan_properties():
         row_shard_plan(H.make_index(4096), 1024, 512, 64, 0)
 
 
+def test_token_parallel_plan_is_the_rank_blocked_concatenation():
+    """token_parallel_plan: ONE global permutation / split under which a full-K GEMM sees exactly the ranks' local quantization
+    groups -- the FP4 blocks of all ranks, then their FP6, then their FP8 blocks, each at the offset the plan reports."""
+    from micromix_b200.parallel_utils import row_shard_plan, token_parallel_plan
+    for K, (p6, p8), tp in ((4096, (1024, 512), 8), (14336, (3584, 1792), 4), (5120, (1280, 640), 2)):
+        idx = H.make_index(K, seed=K + tp)
+        perm, tot, shards = token_parallel_plan(idx, p6, p8, tp)
+        assert perm.dtype == torch.int16 and sorted(perm.tolist()) == list(range(K))
+        assert sum(tot) == K and all(t % 128 == 0 for t in tot) and len(shards) == tp
+        seg0 = (0, tot[0], tot[0] + tot[1])
+        acc = [0, 0, 0]
+        for r, sh in enumerate(shards):
+            k0, k1, lidx, q4, q6, q8 = row_shard_plan(idx, p6, p8, tp, r)
+            assert (sh["k0"], sh["k1"]) == (k0, k1) and sh["split"] == (q4, q6, q8) and torch.equal(sh["index"], lidx)
+            assert sh["offset"] == tuple(acc)
+            g = lidx.to(torch.int64) + k0
+            parts = (g[:q4], g[q4:q4 + q6], g[q4 + q6:])
+            for i in range(3):  # rank r's block of total segment i is its local segment i, in local order
+                lo = seg0[i] + sh["offset"][i]
+                assert torch.equal(perm[lo:lo + parts[i].numel()].to(torch.int64), parts[i])
+                acc[i] += parts[i].numel()
+        assert tuple(acc) == tot
+
+
 def test_row_shard_plan_never_demotes():
     """the rank-local counts are rounded UP -- no globally-FP8 channel may land in a local FP6 / FP4 segment and
     no globally-FP6 channel in the local FP4 segment, at any tp (the stock 5:2:1 split at K=4096, tp=8 has ~64 FP8
