@@ -314,6 +314,16 @@ int mmx_matmul_grouped_activate_quantize(const uint8_t* an, const uint8_t* bn, c
 int mmx_activate_quantize_x_rows(const void* a, const void* b, int64_t ld, int64_t M, const int32_t* rows_dev, int KN, int KS,
                                  int KO, uint8_t* xn, uint8_t* xs, uint8_t* xo, uint8_t* sfn, uint8_t* sfs, uint8_t* sfo,
                                  void* stream);
+/* The routing tables of the grouped expert path in ONE launch (extension; the reference loops over the experts on the host,
+ * model/qMixtralLayer.py:437-450): a stable counting sort of the (token, slot) pairs by local expert, every expert's rows
+ * padded to whole m-tiles.  sel int64 [T, top_k] expert ids, local_slot int64 [experts] = slot of the expert on this rank or
+ * n_local (elsewhere), tile 128 | 256, Mp = a multiple of tile >= T * top_k + n_local * (tile - 1) rounded up.  Outputs (device,
+ * int32): row_src [Mp] token of each padded row (padding: 0), pair_row [T, top_k] padded row of each pair or -1,
+ * grp_rowblk [Mp / 128], grp_mtile [Mp / tile] expert slot per row block / m-tile (-1 = unused m-tile), rows_used [1].
+ * n_local <= 64, experts <= 256. */
+int mmx_moe_route(const int64_t* sel, const int64_t* local_slot, int64_t T, int top_k, int experts, int n_local, int tile, int64_t Mp,
+                  int32_t* row_src, int32_t* pair_row, int32_t* grp_rowblk, int32_t* grp_mtile, int32_t* rows_used,
+                  void* stream);
 /* out[t] = sum over the top_k slots of token t, in ascending expert order, of bf16(y[row[t,s]] * w[t,s]) with a bf16
  * rounding after every add -- exactly what the reference's per-expert `index_add_` loop leaves in its bf16 buffer
  * (model/qMixtralLayer.py:446-450).  row int32 [T, top_k] = row of y holding the pair's expert output, or -1 (expert not on

@@ -31,6 +31,7 @@ SYMBOLS = {
     "mmx_matmul_residual": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "mmx_matmul_grouped_activate_quantize": (_i32, [_vp] * 12 + [_i64, _i64] + [_i32] * 6 + [_vp, _vp] + [_i32] * 3 + [_vp] * 7),
     "mmx_matmul_rope": (_i32, [_vp] * 12 + [_i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "mmx_moe_route": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mmx_debug_silu_table": (_i32, [_vp, _vp, _vp]),
     "mmx_matmul_activate_quantize": (_i32, [_vp] * 12 + [_i64, _i64] + [_i32] * 7 + [_vp] * 7),
     "mmx_peer_alloc": (_i32, [_i64, ctypes.POINTER(_vp), ctypes.c_char_p]),

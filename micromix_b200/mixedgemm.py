@@ -432,6 +432,32 @@ def matmul_grouped(A, W, group_of_mtile, groups, tile_rows, out=None, rows_used=
     return out
 
 
+MOE_ROUTE_MAX_LOCAL = 64
+MOE_ROUTE_MAX_EXPERTS = 256
+
+
+def moe_route(sel, local_slot, n_local, tile):
+    """Extension: the routing tables of the grouped expert path in ONE kernel (qMixtralLayer.route_tables is the same
+    function in torch ops, ~20 launches): sel int64 [T, k], local_slot int64 [experts] (slot on this rank or n_local) ->
+    (row_src int32 [Mp], pair_row int32 [T, k], grp_rowblk int32 [Mp/128], grp_mtile int32 [Mp/tile], Mp, rows_used int32 [1])."""
+    lib = _lib.load()
+    _check_cuda("sel", sel, torch.int64, 2)
+    _check_cuda("local_slot", local_slot, torch.int64, 1)
+    T, k = sel.shape
+    if not (1 <= n_local <= MOE_ROUTE_MAX_LOCAL) or tile not in (128, 256):
+        raise ValueError(f"n_local must be 1..{MOE_ROUTE_MAX_LOCAL} and tile 128 | 256")
+    Mp = (T * k + n_local * (tile - 1) + tile - 1) // tile * tile
+    i32 = dict(dtype=torch.int32, device=sel.device)
+    with torch.cuda.device(sel.device):
+        row_src, pair_row = torch.empty(Mp, **i32), torch.empty((T, k), **i32)
+        grp_rowblk, grp_mtile, used = torch.empty(Mp // 128, **i32), torch.empty(Mp // tile, **i32), torch.empty(1, **i32)
+        rc = lib.mmx_moe_route(_ptr(sel.contiguous()), _ptr(local_slot), T, k, int(local_slot.numel()), int(n_local), int(tile),
+                               Mp, _ptr(row_src),
+                               pair_row.data_ptr(), _ptr(grp_rowblk), _ptr(grp_mtile), _ptr(used), _stream())
+    _lib.check(rc, "mmx_moe_route")
+    return row_src, pair_row, grp_rowblk, grp_mtile, Mp, used
+
+
 def moe_combine(Y, row, expert, weight, out=None):
     """out[t] = sum over token t's slots, ascending expert id, of bf16(Y[row[t,s]] * weight[t,s]) with a bf16 rounding
     after every add (the reference's index_add_ loop, qMixtralLayer.py:446-450); row < 0 = expert not on this rank."""

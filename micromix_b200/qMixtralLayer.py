@@ -184,7 +184,10 @@ class QMixtralSparseMoeBlock(nn.Module):
         T = x.shape[0]
         n_local = len(self.local)
         tile = 256 if T * self.top_k >= 256 * self.num_experts else 128
-        row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = route_tables(sel, self.local_slot, n_local, tile)
+        if n_local <= mixedgemm.MOE_ROUTE_MAX_LOCAL and self.num_experts <= mixedgemm.MOE_ROUTE_MAX_EXPERTS and T > 0:
+            row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = mixedgemm.moe_route(sel, self.local_slot, n_local, tile)
+        else:
+            row_src, pair_row, grp_rowblk, grp_mtile, Mp, used = route_tables(sel, self.local_slot, n_local, tile)
         a = mixedgemm.reorder_quantize_x_grouped(x, self.idx13, grp_rowblk, *self.s13, row_src=row_src, rows=Mp, rows_used=used)
         I = self.inter
         if self.fused and self.act_epilogue:

@@ -126,3 +126,29 @@ def test_moe_block_grouped_equals_expert_loop(cuda, fused, tokens):
         c, _ = two(x)
         torch.cuda.synchronize()
         assert torch.equal(c, b)
+
+
+@pytest.mark.parametrize("T,k,E,local,tile", [(1, 2, 8, [0, 1, 2, 3, 4, 5, 6, 7], 128), (37, 2, 8, [3], 128),
+                                              (700, 2, 8, [1, 5], 256), (16384, 2, 8, [0, 1, 2, 3, 4, 5, 6, 7], 256),
+                                              (5000, 3, 16, [2, 3, 9, 15], 128), (300, 1, 4, [0, 2], 128)])
+def test_moe_route_kernel_equals_the_torch_tables(cuda, T, k, E, local, tile):
+    """mixedgemm.moe_route (one kernel) == qMixtralLayer.route_tables (stable argsort + scatters + cumsums), table by table."""
+    from micromix_b200 import mixedgemm
+    from micromix_b200.qMixtralLayer import route_tables
+    g = torch.Generator(device=cuda).manual_seed(T + k)
+    logits = torch.randn(T, E, generator=g, device=cuda)
+    sel = torch.topk(logits, k, dim=-1).indices
+    slot = torch.full((E,), len(local), dtype=torch.int64)
+    for s_, j in enumerate(local):
+        slot[j] = s_
+    slot = slot.to(cuda)
+    want = route_tables(sel, slot, len(local), tile)
+    got = mixedgemm.moe_route(sel, slot, len(local), tile)
+    torch.cuda.synchronize()
+    assert got[4] == want[4]
+    used = int(want[5].item())
+    assert int(got[5].item()) == used
+    assert torch.equal(got[1], want[1])                                  # pair_row
+    assert torch.equal(got[0][:used], want[0][:used])                    # row_src (rows in use; the rest is never read)
+    assert torch.equal(got[2][: used // 128], want[2][: used // 128])    # grp_rowblk
+    assert torch.equal(got[3], want[3])                                  # grp_mtile (-1 past the rows in use)
