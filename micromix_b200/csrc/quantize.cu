@@ -396,9 +396,14 @@ struct QuantKernel {
             const uint32_t wv[4] = {pre[i][j].x, pre[i][j].y, pre[i][j].z, pre[i][j].w};
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-              const float lo = __uint_as_float(wv[m] << 16), hi = __uint_as_float(wv[m] & 0xffff0000u);
-              acc = __fmaf_rn(lo, lo, acc);
-              acc = __fmaf_rn(hi, hi, acc);
+              // acc = fma(lo, lo, acc); acc = fma(hi, hi, acc) with the bf16 halves as operands of the mixed-precision FMA
+              // (no unpack instructions; a bf16 square is exact in fp32, so the rounding is the plain fp32 FMA's)
+              asm("{.reg .b16 l, h;\n"
+                  "mov.b32 {l, h}, %1;\n"
+                  "fma.rn.f32.bf16 %0, l, l, %0;\n"
+                  "fma.rn.f32.bf16 %0, h, h, %0;}"
+                  : "+f"(acc)
+                  : "r"(wv[m]));
             }
           }
           ssq[j] = acc;
@@ -490,12 +495,28 @@ struct QuantKernel {
       const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        const float wv = __uint_as_float((c & 1) ? (ww[c >> 1] & 0xffff0000u) : (ww[c >> 1] << 16));
 #pragma unroll
         for (int k = 0; k < RW; ++k) {
-          const float y0 = __fmul_rn(__fmul_rn(__uint_as_float(g[c][k] << 16), wv), rinv[2 * k]);
-          const float y1 = __fmul_rn(__fmul_rn(__uint_as_float(g[c][k] & 0xffff0000u), wv), rinv[2 * k + 1]);
-          const __nv_bfloat162 y = __floats2bfloat162_rn(y0, y1);
+          // x * w: the product of two bf16 values is exact in fp32, so one mixed-precision FMA on the packed halves (addend
+          // -0.0: the sign of a zero product is kept) equals fmul(float(x), float(w)) without the three unpack instructions
+          float t0, t1;
+          if (c & 1)
+            asm("{.reg .b16 xl, xh, wl, wh;\n"
+                "mov.b32 {xl, xh}, %2;\n"
+                "mov.b32 {wl, wh}, %3;\n"
+                "fma.rn.f32.bf16 %0, xl, wh, 0f80000000;\n"
+                "fma.rn.f32.bf16 %1, xh, wh, 0f80000000;}"
+                : "=f"(t0), "=f"(t1)
+                : "r"(g[c][k]), "r"(ww[c >> 1]));
+          else
+            asm("{.reg .b16 xl, xh, wl, wh;\n"
+                "mov.b32 {xl, xh}, %2;\n"
+                "mov.b32 {wl, wh}, %3;\n"
+                "fma.rn.f32.bf16 %0, xl, wl, 0f80000000;\n"
+                "fma.rn.f32.bf16 %1, xh, wl, 0f80000000;}"
+                : "=f"(t0), "=f"(t1)
+                : "r"(g[c][k]), "r"(ww[c >> 1]));
+          const __nv_bfloat162 y = __floats2bfloat162_rn(__fmul_rn(t0, rinv[2 * k]), __fmul_rn(t1, rinv[2 * k + 1]));
           g[c][k] = *reinterpret_cast<const uint32_t*>(&y);
         }
       }
