@@ -1047,7 +1047,12 @@ mixed_gemm_kernel(const __grid_constant__ TmapSet tmaps, const __grid_constant__
       }
       auto emit = [&](const uint32_t (&r)[32], int sc, uint4 (&res)[4], int inext) {  // 32 rows x 32 columns: bf16, staged, TMA-stored
         const int col0 = n_blk * BN + sc * 32;
-        if (col0 < p.N) {  // warp-uniform
+        if (col0 >= p.N) {  // warp-uniform: a column block past N (last tile of an N % 256 == 128 matrix)
+          // the residual ring still advances: chunk inext travels in the slot this (skipped) chunk would have freed
+          if (has_res && inext < kChunks) res_issue(inext, res);
+          return;
+        }
+        {
           uint32_t o[16];
           pack_chunk(r, o, p.bias ? p.bias + col0 : nullptr);
           if constexpr (ROPE) {

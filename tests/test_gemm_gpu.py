@@ -359,7 +359,11 @@ def test_fast_silu_equals_reference_sequence_on_every_bf16_in_range(cuda, mmx_li
 
 @pytest.mark.parametrize("M,N,split,bias", [(1, 512, (256, 128, 128), False), (64, 1152, (640, 256, 128), True),
                                             (200, 512, (256, 128, 128), False), (1000, 1024, (640, 256, 128), True),
-                                            (515, 4096, (2560, 1024, 512), False)])
+                                            (515, 4096, (2560, 1024, 512), False),
+                                            # N % 256 == 128: the last tile's upper column blocks do not exist (single-CTA
+                                            # and pair kernels; several tiles per CTA so both accumulators are exercised)
+                                            (200, 1152, (256, 128, 128), False), (1000, 640, (256, 128, 128), True),
+                                            (5000, 384, (256, 0, 0), False)])
 def test_residual_epilogue_matches_separate_add(cuda, M, N, split, bias):
     """matmul(..., residual=r) == r + matmul(...) (torch's bf16 add), bit for bit: the decoder layer's residual adds in the
     GEMM epilogue, split-K (M <= 128), single-CTA and pair kernels, with and without the bias epilogue, in place too."""
