@@ -692,6 +692,12 @@ def run_ours(args, rank, world, local_rank):
                 line["prefill_tokens_per_s"] = line["prefill"]["tokens_per_s"]
             except Exception as e:  # noqa: BLE001 -- the headline line must survive a failure of the secondary leg
                 line["prefill"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_moe:
+            try:
+                line["moe"] = measure_moe(args, dev)
+                line["moe_tokens_per_s"] = line["moe"]["tokens_per_s"]
+            except Exception as e:  # noqa: BLE001 -- the headline line must survive a failure of the secondary leg
+                line["moe"] = {"error": repr(e)[:300]}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         return line
@@ -994,6 +1000,60 @@ def measure_e2e(args, rank, world, dev, chunks, total_flops):
                    "activation and returns only its rows of a row-parallel result (every byte crosses PCIe once per box)"}
 
 
+def measure_moe(args, dev):
+    """BASELINE config 5 in the driver's bench line (N = 1): the Mixtral-8x7B sparse-MoE block -- 8 experts, top-2, 16384
+    tokens, random-init weights, synthetic calibration -- through QMixtralSparseMoeBlock(fused=True): routing kernel, ONE grouped
+    quantize (token gather fused), ONE grouped GEMM over w1||w3 whose epilogue emits w2's quantized operand, ONE grouped GEMM
+    over w2, combine kernel; the whole block replayed from one CUDA graph.  (Expert parallel over 8 GPUs:
+    tools/bench_models.py mixtral_ep under torchrun, profiles/r02_mixtral_ep8_grouped_final.json.)"""
+    import torch
+    from micromix_b200 import mixedgemm
+    from micromix_b200 import model_shapes as S
+    from micromix_b200.qMixtralLayer import QMixtralSparseMoeBlock
+    cfg = S.MIXTRAL_8X7B
+    tokens = args.moe_tokens
+    layer = S.make_layer(cfg, dev, seed=0, moe=True)
+    idx, p6, p8 = S.make_calibration(cfg, 0, moe=True)
+    blk = QMixtralSparseMoeBlock(layer.block_sparse_moe, p8, p6, idx, 0, fused=True)
+    del layer
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(721)
+    x0 = torch.randn(1, tokens, cfg["hidden_size"], generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    with torch.no_grad():
+        for _ in range(2):
+            y = blk(x0)[0]
+    torch.cuda.synchronize()
+    finite = bool(torch.isfinite(y.float()).all())
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    l0 = mixedgemm.launch_count()
+    with torch.cuda.graph(graph, stream=side), torch.no_grad():
+        blk(x0)
+    launches = mixedgemm.launch_count() - l0
+    torch.cuda.synchronize()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    n = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 2.0 * tokens * cfg["num_experts_per_tok"] * 3 * cfg["hidden_size"] * cfg["intermediate_size"]
+    out = {"config": f"Mixtral-8x7B sparse-MoE block (8 experts, top-2), {tokens} tokens, one GPU, random-init weights, "
+                     "synthetic calibration", "path": "grouped" if blk.grouped else "expert loop",
+           "act_epilogue": bool(getattr(blk, "act_epilogue", False)), "ms_per_block": ms, "tokens_per_s": tokens / ms * 1e3,
+           "expert_tflops": flops / ms / 1e9, "mmx_launches_per_block": int(launches), "cuda_graph": True,
+           "output_finite": finite}
+    del graph, blk, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def measure_prefill(args, dev):
     """BASELINE config 3 -- the metric's "prefill tokens/s" half: ALL 32 Llama-3-8B decoder layers (random-init weights,
     synthetic reorder_index, 5-bit split), batch 8 x seq 2048 = 16384 tokens (/root/reference/prof_micromix.sh:1), through
@@ -1084,6 +1144,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (sweeps)")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-prefill", action="store_true", help="skip the 32-layer Llama-3-8B prefill leg (N = 1)")
+    ap.add_argument("--no-moe", action="store_true", help="skip the Mixtral-8x7B MoE-block leg (N = 1)")
+    ap.add_argument("--moe-tokens", type=int, default=16384)
     ap.add_argument("--prefill-batch", type=int, default=8)
     ap.add_argument("--prefill-seq", type=int, default=2048)
     ap.add_argument("--prefill-iters", type=int, default=5)

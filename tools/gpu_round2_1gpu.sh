@@ -16,8 +16,8 @@ timeout 200 python tools/m_sweep.py > $OUT/m_sweep.log 2>&1   # BASELINE config 
 timeout 200 python tools/quant_sweep.py --no-parity --shapes 8192x4096,8192x14336,16384x4096,32768x4096,16384x14336,65536x4096 > $OUT/quant_sweep.log 2>&1
 # launch list of the bench command itself (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prefill --no-e2e > $OUT/bench_under_ncu.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-prefill --no-moe --no-e2e > $OUT/bench_under_ncu.log 2>&1
 # full capture of ONE bench step: weights' quantization (4 launches) + 3 warm-up steps (24) precede it
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mixed_gemm|reorder_quantize" -s 28 -c 8 -o $OUT/prof_step \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-prefill --no-e2e > $OUT/prof_step.log 2>&1
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-prefill --no-moe --no-e2e > $OUT/prof_step.log 2>&1
 tail -3 $OUT/pytest.log; cut -c1-400 $OUT/bench.json; tail -8 $OUT/quant_sweep.log
